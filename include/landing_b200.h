@@ -1,0 +1,146 @@
+/*
+ * landing_b200.h -- C ABI of the B200-native batched solver for the SRB landing NLP of
+ * se-hwan/landing-controller.  Plain pointers and sizes only; every entry point either runs on
+ * the GPU or fails (there is no CPU fallback).
+ *
+ * Two groups of symbols are exported by liblanding_b200.so (= drop-in landingCtrller_IPOPT.so):
+ *
+ * (1) The CasADi-generated-C function ABI that the reference's solver object binds by name
+ *     (reference: optimizations/landing/codegen_casadi/landingCtrller_IPOPT.c:10916-10992 for the
+ *     per-function template; callers external.cpp:63-111,325-362, nlpsol.cpp:100-109):
+ *     for F in {nlp, nlp_f, nlp_g, nlp_grad, nlp_grad_f, nlp_hess_l, nlp_jac_g}
+ *       F, F_alloc_mem, F_init_mem, F_free_mem, F_checkout, F_release, F_incref, F_decref,
+ *       F_n_in, F_n_out, F_default_in, F_name_in, F_name_out, F_sparsity_in, F_sparsity_out, F_work
+ *     declared in casadi_symbols.h.  One scenario per call (latency bound; for drop-in and parity).
+ *
+ * (2) The batched entry points below (new; SURVEY 8b "Batched extension"): thousands of scenarios
+ *     per call, host or device buffers, AoS (CasADi vector per scenario) or SoA layout.
+ */
+#ifndef LANDING_B200_H
+#define LANDING_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct landing_ctx landing_ctx;
+
+enum { LANDING_OK = 0, LANDING_ERR_ARG = 1, LANDING_ERR_CUDA = 2, LANDING_ERR_NOGPU = 3 };
+enum { LANDING_HOST = 0, LANDING_DEVICE = 1 }; /* where the caller's buffers live */
+enum { LANDING_AOS = 0, LANDING_SOA = 1 };     /* [B][n] (one CasADi vector per scenario) | [n][B] */
+
+/* per-scenario solve status (replaces IPOPT's return status, which the reference drops:
+ * generate_landingCtrller_IPOPT.m:269 solve_limited) */
+enum {
+  LANDING_ST_CONVERGED = 0,
+  LANDING_ST_MAX_ITER = 1,
+  LANDING_ST_LINESEARCH_FAIL = 2,
+  LANDING_ST_NAN = 3,
+  LANDING_ST_FACTOR_FAIL = 4,
+  LANDING_ST_RUNNING = 9
+};
+
+/* Create a context for the N-knot problem on CUDA device `device`.
+ * Sizes: n_x = 36N-24, n_p = 13N+81, m = 104N-92, nnz(J) = 385N-421, nnz(H) = 189(N-1). */
+int landing_create(int n_knots, int device, landing_ctx **ctx);
+void landing_destroy(landing_ctx *ctx);
+const char *landing_last_error(void);
+
+/* dims = {N, n_x, n_p, m, nnzJ, nnzH} */
+int landing_dims(const landing_ctx *ctx, long long dims[6]);
+/* host-only size query (no GPU needed) */
+int landing_dims_for(int n_knots, long long dims[6]);
+/* CasADi CCS pattern {nrow, ncol, colind[ncol+1], row[nnz]} (mem.h:73-92) of
+ * which = 0: jac_g_x (casadi_s5, landingCtrller_IPOPT.c:64), 1: hess_gamma_x_x upper triangle
+ * (casadi_s4, :63); 2: dense x (casadi_s0), 3: dense p (s1), 4: scalar (s2), 5: dense g (s3).
+ * Host pointers owned by the library; no GPU needed. */
+const long long *landing_sparsity(const landing_ctx *ctx, int which);
+const long long *landing_sparsity_for(int n_knots, int which);
+
+/* Batched evaluation of the generated functions (replaces nlp_f :10995, nlp_g :11161,
+ * nlp_grad_f :52602, nlp_jac_g :94014, nlp_hess_l :53527, nlp_grad :22015).
+ * Inputs x[B x n_x], p[B x n_p]; lam_f[B], lam_g[B x m] needed for hess / grad_x / grad_p.
+ * NULL inputs are all-zero (as `arg[i]==0` in the generated C); NULL outputs are skipped.
+ * status[B] (optional, int32): 0 ok, -1 a NaN/Inf was produced (oracle_function.cpp:218-266). */
+typedef struct landing_eval_io {
+  const double *x, *p, *lam_f, *lam_g;
+  double *f;      /* [B]        */
+  double *g;      /* [B x m]    */
+  double *grad_f; /* [B x n_x]  */
+  double *jac;    /* [B x nnzJ] */
+  double *hess;   /* [B x nnzH] */
+  double *grad_x; /* [B x n_x]  grad_gamma_x */
+  double *grad_p; /* [B x n_p]  grad_gamma_p */
+  int *status;    /* [B]        */
+} landing_eval_io;
+
+int landing_eval_batch(landing_ctx *ctx, long long B, int memspace, int layout,
+                       const landing_eval_io *io);
+
+/* lbg(p), ubg(p): the bounds the reference's .casadi wrapper computes from the parameters
+ * (generate_landingCtrller_IPOPT.m:319-321; optistack_internal.cpp:742-870). +-inf one-sided. */
+int landing_bounds_batch(landing_ctx *ctx, long long B, int memspace, int layout, const double *p,
+                         double *lbg, double *ubg);
+
+/* Shared numeric data of a sweep (generate_landingCtrller_IPOPT.m:173-196). */
+typedef struct landing_problem {
+  double T; /* horizon, dt = T/(N-1) */
+  double q_min[6], q_max[6], qd_min[6], qd_max[6];
+  double q_term_min[6], q_term_max[6], qd_term_min[6], qd_term_max[6];
+  double q_term_ref[6], qd_term_ref[6];
+  double c_ref[12];
+  double QN[12];
+  double mu, l_leg_max, f_max, mass, Ib[3], Ib_inv[3];
+} landing_problem;
+
+void landing_problem_default(landing_problem *pb);
+
+/* p[B x n_p] and x0[B x n_x] from drop conditions drops[B x 12] = (q_init[6], qd_init[6]),
+ * generated on the device (generate_landingCtrller_IPOPT.m:199-208, 336: Xref linspace,
+ * Uref feet = Xref_pos + c_ref, forces 0, x0 = [Xref(:);Uref(:)]).  drops is always AoS. */
+int landing_build_batch(landing_ctx *ctx, long long B, int memspace, int layout,
+                        const landing_problem *pb, const double *drops, double *p, double *x0);
+
+/* Interior-point options; names follow the IPOPT options the reference sets
+ * (generate_landingCtrller_IPOPT.m:232-263). */
+typedef struct landing_options {
+  int max_iter;              /* 3000 */
+  double tol;                /* 1e-4 */
+  double constr_viol_tol;    /* 1e-3 */
+  double dual_inf_tol;       /* 1 (IPOPT default) */
+  double compl_inf_tol;      /* 1e-4 (IPOPT default) */
+  double mu_init;            /* 0.1 */
+  double bound_push;         /* 0.5 */
+  double bound_frac;         /* 0.5 */
+  double bound_relax_factor; /* 1e-6 */
+  int max_soc;               /* 4 */
+  int reserved[7];
+} landing_options;
+
+void landing_options_default(landing_options *opt);
+
+/* Solve B independent landing NLPs, one per drop condition (replaces one call of the
+ * serialized solver function per scenario: main_scripts/landing_optimization.m:305-311,
+ * generate_data/generate_training_data_automated.m:130-136).
+ * Outputs (host or device per memspace, AoS): x_star[B x n_x], f_star[B], status[B] (int32),
+ * iters[B] (int32); optional lam_g[B x m]. x0 may be NULL (reference initial guess). */
+typedef struct landing_solve_io {
+  const double *drops; /* [B x 12] */
+  const double *x0;    /* [B x n_x] or NULL */
+  double *x_star, *f_star, *lam_g;
+  double *viol; /* [B] final max constraint violation, optional */
+  int *status, *iters;
+} landing_solve_io;
+
+int landing_solve_batch(landing_ctx *ctx, long long B, int memspace, const landing_problem *pb,
+                        const landing_options *opt, const landing_solve_io *io);
+
+/* number of kernel launches issued by this context so far (bench accounting) */
+long long landing_launch_count(const landing_ctx *ctx);
+/* CUDA stream (cudaStream_t) the context launches on; for event timing by the caller */
+void *landing_stream(const landing_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

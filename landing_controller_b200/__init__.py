@@ -1,0 +1,5 @@
+"""landing_controller_b200 -- B200-native batched solver for the SRB landing NLP hot path of
+se-hwan/landing-controller.  See DESIGN.md; the C ABI is in include/landing_b200.h."""
+from .api import (AOS, DEVICE, DROPIN_PATH, HOST, LIB_PATH, SOA, STATUS, LandingSolver, contact_set,  # noqa: F401
+                  dims_for, load_library, sparsity_for)
+from .sweeps import grid_sweep, random_sweep, single_drop  # noqa: F401

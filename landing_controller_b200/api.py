@@ -1,0 +1,229 @@
+"""Host-side Python mirror of the reference's solver interface for the landing hot path.
+
+The reference's callers (MATLAB) do
+
+    f = Function.load('landingCtrller_IPOPT.casadi')
+    [x, cost] = f(Xref, Uref, dt, q_min, ..., x0, mu, l_leg_max, f_max, mass, Ib, Ib_inv)
+
+(optimizations/landing/main_scripts/landing_optimization.m:300-311,
+ generate_data/generate_training_data_automated.m:130-136) one drop condition at a time.  Here
+`LandingSolver.solve(drops)` does the same for a batch of drop conditions through the C ABI of
+liblanding_b200.so (include/landing_b200.h).  PyTorch only provides device memory / streams.
+
+There is no CPU path: if the CUDA library is missing or no GPU is present, construction fails.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "liblanding_b200.so")
+DROPIN_PATH = os.path.join(_HERE, "dropin", "landingCtrller_IPOPT.so")
+
+HOST, DEVICE = 0, 1
+AOS, SOA = 0, 1
+
+STATUS = {0: "converged", 1: "max_iter", 2: "linesearch_fail", 3: "nan", 4: "factor_fail", 9: "running"}
+
+_dp = ctypes.POINTER(ctypes.c_double)
+_ip = ctypes.POINTER(ctypes.c_int)
+
+
+class EvalIO(ctypes.Structure):
+    _fields_ = [(n, _dp) for n in ("x", "p", "lam_f", "lam_g", "f", "g", "grad_f", "jac", "hess",
+                                   "grad_x", "grad_p")] + [("status", _ip)]
+
+
+class Problem(ctypes.Structure):
+    _fields_ = [("T", ctypes.c_double)] + [(n, ctypes.c_double * 6) for n in (
+        "q_min", "q_max", "qd_min", "qd_max", "q_term_min", "q_term_max", "qd_term_min",
+        "qd_term_max", "q_term_ref", "qd_term_ref")] + [
+        ("c_ref", ctypes.c_double * 12), ("QN", ctypes.c_double * 12),
+        ("mu", ctypes.c_double), ("l_leg_max", ctypes.c_double), ("f_max", ctypes.c_double),
+        ("mass", ctypes.c_double), ("Ib", ctypes.c_double * 3), ("Ib_inv", ctypes.c_double * 3)]
+
+
+class Options(ctypes.Structure):
+    _fields_ = [("max_iter", ctypes.c_int), ("tol", ctypes.c_double), ("constr_viol_tol", ctypes.c_double),
+                ("dual_inf_tol", ctypes.c_double), ("compl_inf_tol", ctypes.c_double),
+                ("mu_init", ctypes.c_double), ("bound_push", ctypes.c_double),
+                ("bound_frac", ctypes.c_double), ("bound_relax_factor", ctypes.c_double),
+                ("max_soc", ctypes.c_int), ("reserved", ctypes.c_int * 7)]
+
+
+class SolveIO(ctypes.Structure):
+    _fields_ = [("drops", _dp), ("x0", _dp), ("x_star", _dp), ("f_star", _dp), ("lam_g", _dp),
+                ("viol", _dp), ("status", _ip), ("iters", _ip)]
+
+
+def load_library(path=LIB_PATH):
+    if not os.path.exists(path):
+        raise RuntimeError(
+            "landing_controller_b200: %s is missing -- build it with __graft_entry__.build() "
+            "(there is no CPU fallback)" % path)
+    lib = ctypes.CDLL(path)
+    lib.landing_last_error.restype = ctypes.c_char_p
+    lib.landing_sparsity_for.restype = ctypes.POINTER(ctypes.c_longlong)
+    lib.landing_sparsity_for.argtypes = [ctypes.c_int, ctypes.c_int]
+    lib.landing_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]
+    lib.landing_destroy.argtypes = [ctypes.c_void_p]
+    lib.landing_eval_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                       ctypes.POINTER(EvalIO)]
+    lib.landing_bounds_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                         _dp, _dp, _dp]
+    lib.landing_build_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                        ctypes.POINTER(Problem), _dp, _dp, _dp]
+    lib.landing_solve_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int,
+                                        ctypes.POINTER(Problem), ctypes.POINTER(Options),
+                                        ctypes.POINTER(SolveIO)]
+    lib.landing_launch_count.restype = ctypes.c_longlong
+    lib.landing_launch_count.argtypes = [ctypes.c_void_p]
+    lib.landing_stream.restype = ctypes.c_void_p
+    lib.landing_stream.argtypes = [ctypes.c_void_p]
+    lib.landing_dims_for.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
+    return lib
+
+
+def dims_for(N, lib=None):
+    lib = lib or load_library()
+    d = (ctypes.c_longlong * 6)()
+    if lib.landing_dims_for(N, d) != 0:
+        raise ValueError(lib.landing_last_error().decode())
+    return dict(N=d[0], nx=d[1], np=d[2], m=d[3], nnzJ=d[4], nnzH=d[5])
+
+
+def sparsity_for(N, which, lib=None):
+    """CasADi CCS array of which = 0 jac_g, 1 hess_l (upper), 2 x, 3 p, 4 scalar, 5 g. No GPU needed."""
+    lib = lib or load_library()
+    s = lib.landing_sparsity_for(N, which)
+    ncol = s[1]
+    nnz = s[2 + ncol]
+    return np.ctypeslib.as_array(s, shape=(2 + ncol + 1 + nnz,)).copy()
+
+
+def _ptr(a, typ=_dp):
+    """numpy array (host) or torch tensor (host/device) -> C pointer."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data_as(typ)
+    assert a.is_contiguous()
+    return ctypes.cast(a.data_ptr(), typ)
+
+
+class LandingSolver:
+    """Batched GPU solver / evaluator for the N-knot SRB landing NLP."""
+
+    def __init__(self, N=21, device=0, lib_path=LIB_PATH):
+        self.lib = load_library(lib_path)
+        self.ctx = ctypes.c_void_p()
+        rc = self.lib.landing_create(N, device, ctypes.byref(self.ctx))
+        if rc != 0:
+            raise RuntimeError("landing_create failed (%d): %s" % (rc, self.lib.landing_last_error().decode()))
+        self.N, self.device = N, device
+        self.dims = dims_for(N, self.lib)
+        self.problem = Problem()
+        self.lib.landing_problem_default(ctypes.byref(self.problem))
+        self.options = Options()
+        self.lib.landing_options_default(ctypes.byref(self.options))
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.landing_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (what, rc, self.lib.landing_last_error().decode()))
+
+    @property
+    def launches(self):
+        return self.lib.landing_launch_count(self.ctx)
+
+    @property
+    def stream_ptr(self):
+        return self.lib.landing_stream(self.ctx)
+
+    # ---- batched evaluation of the generated functions ------------------------------------
+    def eval(self, B, memspace, layout, x=None, p=None, lam_f=None, lam_g=None, f=None, g=None,
+             grad_f=None, jac=None, hess=None, grad_x=None, grad_p=None, status=None):
+        io = EvalIO(_ptr(x), _ptr(p), _ptr(lam_f), _ptr(lam_g), _ptr(f), _ptr(g), _ptr(grad_f),
+                    _ptr(jac), _ptr(hess), _ptr(grad_x), _ptr(grad_p), _ptr(status, _ip))
+        self._check(self.lib.landing_eval_batch(self.ctx, B, memspace, layout, ctypes.byref(io)),
+                    "landing_eval_batch")
+
+    def eval_host(self, x, p, lam_f=None, lam_g=None, want=("f", "g", "grad_f", "jac", "hess"), layout=AOS):
+        """Convenience: host numpy AoS [B, n] in -> dict of host numpy outputs."""
+        d = self.dims
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        B = x.shape[0] if layout == AOS else x.shape[1]
+        sizes = dict(f=1, g=d["m"], grad_f=d["nx"], jac=d["nnzJ"], hess=d["nnzH"], grad_x=d["nx"], grad_p=d["np"])
+        outs = {k: np.zeros((B, sizes[k]) if layout == AOS else (sizes[k], B)) for k in want}
+        status = np.zeros(B, dtype=np.int32)
+        self.eval(B, HOST, layout, x=x, p=np.ascontiguousarray(p, dtype=np.float64),
+                  lam_f=None if lam_f is None else np.ascontiguousarray(lam_f, dtype=np.float64),
+                  lam_g=None if lam_g is None else np.ascontiguousarray(lam_g, dtype=np.float64),
+                  status=status, **outs)
+        outs["status"] = status
+        return outs
+
+    def bounds_host(self, p, layout=AOS):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        B = p.shape[0] if layout == AOS else p.shape[1]
+        shape = (B, self.dims["m"]) if layout == AOS else (self.dims["m"], B)
+        lb, ub = np.zeros(shape), np.zeros(shape)
+        self._check(self.lib.landing_bounds_batch(self.ctx, B, HOST, layout, _ptr(p), _ptr(lb), _ptr(ub)),
+                    "landing_bounds_batch")
+        return lb, ub
+
+    def build_host(self, drops, layout=AOS):
+        """drops [B,12] -> (p [B,np], x0 [B,nx]) as the reference's callers build them."""
+        drops = np.ascontiguousarray(drops, dtype=np.float64)
+        B = drops.shape[0]
+        p = np.zeros((B, self.dims["np"]) if layout == AOS else (self.dims["np"], B))
+        x0 = np.zeros((B, self.dims["nx"]) if layout == AOS else (self.dims["nx"], B))
+        self._check(self.lib.landing_build_batch(self.ctx, B, HOST, layout, ctypes.byref(self.problem),
+                                                 _ptr(drops), _ptr(p), _ptr(x0)), "landing_build_batch")
+        return p, x0
+
+    # ---- the solve: one NLP per drop condition ----------------------------------------------
+    def solve(self, drops, x0=None, want_lam=False):
+        """drops: host numpy [B,12] (q_init[6], qd_init[6]). Returns dict of host arrays."""
+        drops = np.ascontiguousarray(drops, dtype=np.float64)
+        B = drops.shape[0]
+        d = self.dims
+        out = dict(x=np.zeros((B, d["nx"])), f=np.zeros(B), viol=np.zeros(B),
+                   status=np.full(B, 9, dtype=np.int32), iters=np.zeros(B, dtype=np.int32))
+        if want_lam:
+            out["lam_g"] = np.zeros((B, d["m"]))
+        x0c = None if x0 is None else np.ascontiguousarray(x0, dtype=np.float64)
+        io = SolveIO(_ptr(drops), _ptr(x0c), _ptr(out["x"]), _ptr(out["f"]), _ptr(out.get("lam_g")),
+                     _ptr(out["viol"]), _ptr(out["status"], _ip), _ptr(out["iters"], _ip))
+        self._check(self.lib.landing_solve_batch(self.ctx, B, HOST, ctypes.byref(self.problem),
+                                                 ctypes.byref(self.options), ctypes.byref(io)),
+                    "landing_solve_batch")
+        return out
+
+    def solve_device(self, drops, x_star, f_star, status, iters, viol=None, lam_g=None, x0=None):
+        """All arguments are CUDA torch tensors already resident in HBM (no copies)."""
+        B = drops.shape[0]
+        io = SolveIO(_ptr(drops), _ptr(x0), _ptr(x_star), _ptr(f_star), _ptr(lam_g), _ptr(viol),
+                     _ptr(status, _ip), _ptr(iters, _ip))
+        self._check(self.lib.landing_solve_batch(self.ctx, B, DEVICE, ctypes.byref(self.problem),
+                                                 ctypes.byref(self.options), ctypes.byref(io)),
+                    "landing_solve_batch")
+
+
+def contact_set(x, N, thresh=1.0):
+    """cs[leg,k] = f_z > 1  (optimizations/landing/codegen_casadi/test_loadCasadi_ws.m:144-147)."""
+    x = np.asarray(x)
+    U = x[..., 12 * N:].reshape(x.shape[:-1] + (N - 1, 24))
+    return U[..., 12 + 2::3][..., :4] > thresh

@@ -1,0 +1,302 @@
+// capi.cu -- the thin C-ABI layer of liblanding_b200.so (include/landing_b200.h).
+// Host side only: context, device staging of host buffers, launches.  No CPU compute path:
+// every entry point that produces numbers needs a CUDA device and fails loudly without one.
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "kernels.cuh"
+#include "solver.cuh"
+
+using namespace srb;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return fail(LANDING_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
+  } while (0)
+}  // namespace
+
+struct landing_ctx {
+  int N = 0, device = 0;
+  std::shared_ptr<const HostPlan> plan;
+  DevicePlan dpl{};
+  cudaStream_t stream = nullptr;
+  int* d_maps = nullptr;
+  long long launches = 0;
+  // grow-only device staging for host-buffer calls
+  void* stage = nullptr;
+  size_t stage_bytes = 0;
+  SolverWorkspace ws;
+};
+
+static int ensure_stage(landing_ctx* c, size_t bytes) {
+  if (bytes <= c->stage_bytes) return LANDING_OK;
+  if (c->stage) cudaFree(c->stage);
+  c->stage = nullptr;
+  c->stage_bytes = 0;
+  CU(cudaMalloc(&c->stage, bytes));
+  c->stage_bytes = bytes;
+  return LANDING_OK;
+}
+
+extern "C" {
+
+const char* landing_last_error(void) { return g_err.c_str(); }
+
+int landing_dims_for(int N, long long d[6]) {
+  if (N < 3 || !d) return fail(LANDING_ERR_ARG, "landing_dims_for: need N >= 3");
+  d[0] = N;
+  d[1] = 36LL * N - 24;
+  d[2] = 13LL * N + 81;
+  d[3] = 104LL * N - 92;
+  d[4] = 385LL * N - 421;
+  d[5] = 189LL * (N - 1);
+  return LANDING_OK;
+}
+
+const long long* landing_sparsity_for(int N, int which) {
+  if (N < 3) return nullptr;
+  auto pl = get_plan(N);
+  switch (which) {
+    case 0: return pl->spJ.data();
+    case 1: return pl->spH.data();
+    case 2: return pl->spDense[0].data();  // x
+    case 3: return pl->spDense[1].data();  // p
+    case 4: return pl->spDense[2].data();  // scalar
+    case 5: return pl->spDense[3].data();  // g / lam_g
+    default: return nullptr;
+  }
+}
+
+int landing_create(int N, int device, landing_ctx** out) {
+  if (!out || N < 3) return fail(LANDING_ERR_ARG, "landing_create: need N >= 3 and a ctx pointer");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(LANDING_ERR_NOGPU, "landing_create: no CUDA device (this library has no CPU path)");
+  if (device < 0 || device >= ndev) return fail(LANDING_ERR_ARG, "landing_create: bad device index");
+  CU(cudaSetDevice(device));
+  landing_ctx* c = new landing_ctx();
+  c->N = N;
+  c->device = device;
+  c->plan = get_plan(N);
+  const HostPlan& pl = *c->plan;
+  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  const size_t nj = pl.jmap.size(), nh = pl.hmap.size();
+  CU(cudaMalloc(&c->d_maps, sizeof(int) * (nj + nh + 36 + 12)));
+  CU(cudaMemcpy(c->d_maps, pl.jmap.data(), sizeof(int) * nj, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->d_maps + nj, pl.hmap.data(), sizeof(int) * nh, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->d_maps + nj + nh, pl.jbnd, sizeof(int) * 36, cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(c->d_maps + nj + nh + 36, pl.hterm, sizeof(int) * 12, cudaMemcpyHostToDevice));
+  c->dpl = DevicePlan{pl.N, pl.nx, pl.np, pl.m, pl.nnzJ, pl.nnzH, pl.off,
+                      c->d_maps, c->d_maps + nj, c->d_maps + nj + nh, c->d_maps + nj + nh + 36};
+  *out = c;
+  return LANDING_OK;
+}
+
+void landing_destroy(landing_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  solver_free(c->ws);
+  if (c->stage) cudaFree(c->stage);
+  if (c->d_maps) cudaFree(c->d_maps);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+int landing_dims(const landing_ctx* c, long long d[6]) {
+  if (!c) return fail(LANDING_ERR_ARG, "landing_dims: null ctx");
+  return landing_dims_for(c->N, d);
+}
+
+const long long* landing_sparsity(const landing_ctx* c, int which) {
+  return c ? landing_sparsity_for(c->N, which) : nullptr;
+}
+
+long long landing_launch_count(const landing_ctx* c) { return c ? c->launches : 0; }
+void* landing_stream(const landing_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+void landing_problem_default(landing_problem* pb) {
+  // generate_landingCtrller_IPOPT.m:173-196
+  static const double qmin[6] = {-10, -10, 0.1, -10, -10, -10}, qmax[6] = {10, 10, 1.0, 10, 10, 10};
+  static const double qdmin[6] = {-10, -10, -10, -40, -40, -40}, qdmax[6] = {10, 10, 10, 40, 40, 40};
+  static const double qtmin[6] = {-10, -10, 0.2, -0.1, -0.1, -10}, qtmax[6] = {10, 10, 5, 0.1, 0.1, 10};
+  static const double qtref[6] = {0, 0, 0.275, 0, 0, 0};
+  static const double QN[12] = {0, 0, 100, 100, 100, 0, 10, 10, 10, 10, 10, 10};
+  static const double sgn[12] = {1, -1, 1, 1, 1, 1, -1, -1, 1, -1, 1, 1};
+  static const double cr[3] = {0.2, 0.1, -0.2};
+  pb->T = 0.6;
+  for (int i = 0; i < 6; i++) {
+    pb->q_min[i] = qmin[i]; pb->q_max[i] = qmax[i];
+    pb->qd_min[i] = qdmin[i]; pb->qd_max[i] = qdmax[i];
+    pb->q_term_min[i] = qtmin[i]; pb->q_term_max[i] = qtmax[i];
+    pb->qd_term_min[i] = qdmin[i]; pb->qd_term_max[i] = qdmax[i];
+    pb->q_term_ref[i] = qtref[i]; pb->qd_term_ref[i] = 0.0;
+  }
+  for (int i = 0; i < 12; i++) { pb->QN[i] = QN[i]; pb->c_ref[i] = sgn[i] * cr[i % 3]; }
+  pb->mu = 1.0;
+  pb->l_leg_max = 0.35;
+  pb->f_max = 200.0;
+  // composite rigid-body inertia at q_home (get_mass_matrix.m:19-54, generate_landingCtrller_IPOPT.m:99-104)
+  pb->mass = 8.252;
+  pb->Ib[0] = 0.05757729845; pb->Ib[1] = 0.23400899482; pb->Ib[2] = 0.27967384827;
+  pb->Ib_inv[0] = 17.37746888890; pb->Ib_inv[1] = 4.27334000930; pb->Ib_inv[2] = 3.57755192380;
+}
+
+void landing_options_default(landing_options* o) {
+  // generate_landingCtrller_IPOPT.m:232-263
+  std::memset(o, 0, sizeof(*o));
+  o->max_iter = 3000;
+  o->tol = 1e-4;
+  o->constr_viol_tol = 1e-3;
+  o->dual_inf_tol = 1.0;
+  o->compl_inf_tol = 1e-4;
+  o->mu_init = 0.1;
+  o->bound_push = 0.5;
+  o->bound_frac = 0.5;
+  o->bound_relax_factor = 1e-6;
+  o->max_soc = 4;
+}
+
+int landing_eval_batch(landing_ctx* c, long long B, int memspace, int layout, const landing_eval_io* io) {
+  if (!c || !io || B <= 0) return fail(LANDING_ERR_ARG, "landing_eval_batch: bad arguments");
+  CU(cudaSetDevice(c->device));
+  const DevicePlan& pl = c->dpl;
+  const long long nx = pl.nx, np = pl.np, m = pl.m, nj = pl.nnzJ, nh = pl.nnzH;
+  // sizes (doubles) of the 4 inputs and 7 outputs
+  const long long in_n[4] = {nx, np, 1, m};
+  const double* in_p[4] = {io->x, io->p, io->lam_f, io->lam_g};
+  const long long out_n[7] = {1, m, nx, nj, nh, nx, np};
+  double* out_p[7] = {io->f, io->g, io->grad_f, io->jac, io->hess, io->grad_x, io->grad_p};
+  const double* din[4];
+  double* dout[7];
+  int* dstatus = io->status;
+  if (memspace == LANDING_HOST) {
+    size_t tot = 0;
+    for (int i = 0; i < 4; i++) if (in_p[i]) tot += sizeof(double) * in_n[i] * B;
+    for (int i = 0; i < 7; i++) if (out_p[i]) tot += sizeof(double) * out_n[i] * B;
+    tot += sizeof(int) * B + 256;
+    int rc = ensure_stage(c, tot);
+    if (rc) return rc;
+    char* cur = (char*)c->stage;
+    for (int i = 0; i < 4; i++) {
+      din[i] = nullptr;
+      if (in_p[i]) {
+        din[i] = (const double*)cur;
+        CU(cudaMemcpyAsync(cur, in_p[i], sizeof(double) * in_n[i] * B, cudaMemcpyHostToDevice, c->stream));
+        cur += sizeof(double) * in_n[i] * B;
+      }
+    }
+    for (int i = 0; i < 7; i++) {
+      dout[i] = nullptr;
+      if (out_p[i]) { dout[i] = (double*)cur; cur += sizeof(double) * out_n[i] * B; }
+    }
+    dstatus = io->status ? (int*)cur : nullptr;
+  } else {
+    for (int i = 0; i < 4; i++) din[i] = in_p[i];
+    for (int i = 0; i < 7; i++) dout[i] = out_p[i];
+  }
+  EvalArgs a{};
+  a.pl = pl;
+  a.B = B;
+  a.x = make_cview(din[0], nx, B, layout);
+  a.p = make_cview(din[1], np, B, layout);
+  a.lam_f = make_cview(din[2], 1, B, layout);
+  a.lam_g = make_cview(din[3], m, B, layout);
+  a.f = make_view(dout[0], 1, B, layout);
+  a.g = make_view(dout[1], m, B, layout);
+  a.grad_f = make_view(dout[2], nx, B, layout);
+  a.jac = make_view(dout[3], nj, B, layout);
+  a.hess = make_view(dout[4], nh, B, layout);
+  a.grad_x = make_view(dout[5], nx, B, layout);
+  a.grad_p = make_view(dout[6], np, B, layout);
+  a.status = dstatus;
+  c->launches += launch_eval(a, c->stream);
+  CU(cudaGetLastError());
+  if (memspace == LANDING_HOST) {
+    for (int i = 0; i < 7; i++)
+      if (out_p[i])
+        CU(cudaMemcpyAsync(out_p[i], dout[i], sizeof(double) * out_n[i] * B, cudaMemcpyDeviceToHost, c->stream));
+    if (io->status)
+      CU(cudaMemcpyAsync(io->status, dstatus, sizeof(int) * B, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return LANDING_OK;
+}
+
+int landing_bounds_batch(landing_ctx* c, long long B, int memspace, int layout, const double* p,
+                         double* lbg, double* ubg) {
+  if (!c || !p || !lbg || !ubg || B <= 0) return fail(LANDING_ERR_ARG, "landing_bounds_batch: bad arguments");
+  CU(cudaSetDevice(c->device));
+  const DevicePlan& pl = c->dpl;
+  const double* dp = p;
+  double *dl = lbg, *du = ubg;
+  if (memspace == LANDING_HOST) {
+    int rc = ensure_stage(c, sizeof(double) * B * (pl.np + 2LL * pl.m));
+    if (rc) return rc;
+    double* s = (double*)c->stage;
+    CU(cudaMemcpyAsync(s, p, sizeof(double) * B * pl.np, cudaMemcpyHostToDevice, c->stream));
+    dp = s;
+    dl = s + B * pl.np;
+    du = dl + B * pl.m;
+  }
+  c->launches += launch_bounds(pl, B, make_cview(dp, pl.np, B, layout), make_view(dl, pl.m, B, layout),
+                               make_view(du, pl.m, B, layout), c->stream);
+  CU(cudaGetLastError());
+  if (memspace == LANDING_HOST) {
+    CU(cudaMemcpyAsync(lbg, dl, sizeof(double) * B * pl.m, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(ubg, du, sizeof(double) * B * pl.m, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return LANDING_OK;
+}
+
+int landing_build_batch(landing_ctx* c, long long B, int memspace, int layout, const landing_problem* pb,
+                        const double* drops, double* p, double* x0) {
+  if (!c || !pb || !drops || B <= 0) return fail(LANDING_ERR_ARG, "landing_build_batch: bad arguments");
+  CU(cudaSetDevice(c->device));
+  const DevicePlan& pl = c->dpl;
+  const double* dd = drops;
+  double *dp = p, *dx = x0;
+  if (memspace == LANDING_HOST) {
+    int rc = ensure_stage(c, sizeof(double) * B * (12 + pl.np + pl.nx));
+    if (rc) return rc;
+    double* s = (double*)c->stage;
+    CU(cudaMemcpyAsync(s, drops, sizeof(double) * B * 12, cudaMemcpyHostToDevice, c->stream));
+    dd = s;
+    dp = p ? s + 12 * B : nullptr;
+    dx = x0 ? s + 12 * B + B * pl.np : nullptr;
+  }
+  c->launches += launch_build(pl, B, *pb, dd, make_view(dp, pl.np, B, layout), make_view(dx, pl.nx, B, layout),
+                              c->stream);
+  CU(cudaGetLastError());
+  if (memspace == LANDING_HOST) {
+    if (p) CU(cudaMemcpyAsync(p, dp, sizeof(double) * B * pl.np, cudaMemcpyDeviceToHost, c->stream));
+    if (x0) CU(cudaMemcpyAsync(x0, dx, sizeof(double) * B * pl.nx, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return LANDING_OK;
+}
+
+int landing_solve_batch(landing_ctx* c, long long B, int memspace, const landing_problem* pb,
+                        const landing_options* opt, const landing_solve_io* io) {
+  if (!c || !pb || !io || !io->drops || B <= 0) return fail(LANDING_ERR_ARG, "landing_solve_batch: bad arguments");
+  CU(cudaSetDevice(c->device));
+  landing_options o;
+  if (opt) o = *opt; else landing_options_default(&o);
+  std::string err;
+  int launches = 0;
+  int rc = solver_run(c->ws, c->dpl, B, memspace, *pb, o, *io, c->stream, &launches, &err);
+  c->launches += launches;
+  if (rc) return fail(rc, err);
+  return LANDING_OK;
+}
+
+}  // extern "C"

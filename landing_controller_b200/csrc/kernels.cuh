@@ -1,0 +1,52 @@
+// kernels.cuh -- launcher declarations shared by capi.cu, eval.cu and solver.cu
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/landing_b200.h"
+#include "plan.cuh"
+
+namespace srb {
+
+// strided view of a [n x B] family of per-scenario vectors: element i of scenario b at p[i*si + b*sb]
+struct View {
+  double* p;
+  long long si, sb;
+  __host__ __device__ __forceinline__ double& at(long long i, long long b) const { return p[i * si + b * sb]; }
+};
+struct CView {
+  const double* p;
+  long long si, sb;
+  __host__ __device__ __forceinline__ double get(long long i, long long b) const {
+    return p ? p[i * si + b * sb] : 0.0;  // NULL input == all zeros (landingCtrller_IPOPT.c:69)
+  }
+};
+
+inline View make_view(double* p, long long n, long long B, int layout) {
+  return layout == LANDING_SOA ? View{p, B, 1} : View{p, 1, n};
+}
+inline CView make_cview(const double* p, long long n, long long B, int layout) {
+  return layout == LANDING_SOA ? CView{p, B, 1} : CView{p, 1, n};
+}
+
+struct DevicePlan {  // device copies of the scatter maps
+  int N, nx, np, m, nnzJ, nnzH;
+  ParamOff off;
+  const int *jmap, *hmap, *jbnd, *hterm;
+};
+
+struct EvalArgs {
+  DevicePlan pl;
+  long long B;
+  CView x, p, lam_f, lam_g;
+  View f, g, grad_f, jac, hess, grad_x, grad_p;
+  int* status;
+  int k0 = 0;  // first knot slice handled by blockIdx.y == 0
+};
+
+// returns number of kernel launches issued
+int launch_eval(const EvalArgs& a, cudaStream_t st);
+int launch_bounds(const DevicePlan& pl, long long B, CView p, View lbg, View ubg, cudaStream_t st);
+int launch_build(const DevicePlan& pl, long long B, const landing_problem& pb, const double* drops,
+                 View p, View x0, cudaStream_t st);
+
+}  // namespace srb

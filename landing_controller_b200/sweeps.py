@@ -1,0 +1,68 @@
+"""Synthetic drop-condition sweeps (the workloads of BASELINE.json `configs`).
+
+A drop condition is the 12-vector (q_init[6] = x,y,z,roll,pitch,yaw ; qd_init[6] = omega_body, v_world),
+the quantity the reference's sweep scripts draw per sample
+(optimizations/landing/generate_data/generate_training_data_automated.m:44-60,
+ optimizations/landing/analysis/foot_positions.m:18-44).
+"""
+import numpy as np
+
+
+def single_drop():
+    """BASELINE config 0: 0.5 m, level, 1 m/s forward."""
+    d = np.zeros((1, 12))
+    d[0, 2] = 0.5
+    d[0, 9] = 1.0
+    return d
+
+
+def _factor(B):
+    """B = nz*np*nr*nv with the 1:2:1:2 proportions of SURVEY 8d (1024 = 4x8x4x8, 16384 = 8x16x8x16)."""
+    dims = [1, 1, 1, 1]
+    order = [1, 3, 0, 2]
+    i = 0
+    rem = B
+    while rem > 1:
+        if rem % 2:
+            raise ValueError("grid sweep size must be a power of two")
+        dims[order[i % 4]] *= 2
+        rem //= 2
+        i += 1
+    return dims
+
+
+def grid_sweep(B=1024, vz=-3.0):
+    """Tensor grid height x pitch x roll x forward velocity (BASELINE configs 1 and 2)."""
+    nz, npi, nr, nv = _factor(B)
+    z = np.linspace(0.4, 0.7, nz) if nz > 1 else np.array([0.5])
+    pitch = np.linspace(-np.pi / 3, np.pi / 3, npi) if npi > 1 else np.array([0.0])
+    roll = np.linspace(-0.25, 0.25, nr) if nr > 1 else np.array([0.0])
+    vx = np.linspace(-1.75, 1.75, nv) if nv > 1 else np.array([0.0])
+    Z, P, R, V = np.meshgrid(z, pitch, roll, vx, indexing="ij")
+    d = np.zeros((B, 12))
+    d[:, 2] = Z.ravel()
+    d[:, 3] = R.ravel()
+    d[:, 4] = P.ravel()
+    d[:, 9] = V.ravel()
+    d[:, 11] = vz
+    return d
+
+
+def random_sweep(B, seed=0, large_tilt=False):
+    """Seeded random drops after generate_training_data_automated.m:44-60 (BASELINE config 4)."""
+    rng = np.random.default_rng(seed)
+    d = np.zeros((B, 12))
+    lim = (np.pi / 2 - 0.1) if large_tilt else np.pi / 3
+    d[:, 3] = rng.uniform(-0.25, 0.25, B)
+    d[:, 4] = rng.uniform(-lim, lim, B)
+    d[:, 5] = rng.uniform(-0.25, 0.25, B)
+    d[:, 6:9] = rng.uniform(-0.5, 0.5, (B, 3))
+    d[:, 9:11] = rng.uniform(-1.75, 1.75, (B, 2))
+    d[:, 11] = rng.uniform(-6.0, -3.0, B)
+    # z0 = 0.35 + |min_l (R hip_l)_z| + |dt*vz|  (:52-60); hip_z = 0, dt = 0.03
+    sr, cr = np.sin(d[:, 3]), np.cos(d[:, 3])
+    sp, cp = np.sin(d[:, 4]), np.cos(d[:, 4])
+    hip = np.array([[0.19, -0.1], [0.19, 0.1], [-0.19, -0.1], [-0.19, 0.1]])
+    hz = -sp[:, None] * hip[None, :, 0] + (sr * cp)[:, None] * hip[None, :, 1]
+    d[:, 2] = 0.35 + np.abs(hz.min(axis=1)) + np.abs(0.03 * d[:, 11])
+    return d
