@@ -299,8 +299,10 @@ __global__ void __launch_bounds__(TPB) k_build(DevicePlan pl, long long B, Probl
   const double t = (double)k / (double)(N - 1);
   double xr[12];
   for (int i = 0; i < 6; i++) {
-    xr[i] = (k == N - 1) ? pb.q_term_ref[i] : d[i] + (pb.q_term_ref[i] - d[i]) * t;
-    xr[6 + i] = (k == N - 1) ? pb.qd_term_ref[i] : d[6 + i] + (pb.qd_term_ref[i] - d[6 + i]) * t;
+    // unfused multiply-add so that Xref is bit-identical to the host-side construction
+    xr[i] = (k == N - 1) ? pb.q_term_ref[i] : __dadd_rn(d[i], __dmul_rn(pb.q_term_ref[i] - d[i], t));
+    xr[6 + i] = (k == N - 1) ? pb.qd_term_ref[i]
+                             : __dadd_rn(d[6 + i], __dmul_rn(pb.qd_term_ref[i] - d[6 + i], t));
   }
   for (int i = 0; i < 12; i++) {
     if (p.p) p.at(12 * k + i, b) = xr[i];

@@ -25,8 +25,8 @@ static const double GRAV[3] = {0.0, 0.0, -9.81};
 #define FRIC 0.71
 
 /* knot-local variable numbering: 0-11 X, 12-23 c, 24-35 f, 36-47 X+, 48-59 c+ */
-typedef struct { short r, v; } jpat_t;
-typedef struct { short a, b; } hpat_t;
+typedef srb_jpat jpat_t;
+typedef srb_hpat hpat_t;
 
 static void mat3mul(const double A[9], const double B[9], double C[9]) {
   for (int i = 0; i < 3; i++)
@@ -735,6 +735,21 @@ int srb_grad(const srb_plan *pl, const double *x, const double *p, double lam_f,
   free(gtmp);
   free(jac);
   return ok ? 0 : -1;
+}
+
+void srb_knot_pattern(int last, srb_jpat *jp, srb_hpat *hp) {
+  double z[60] = {0}, prm[9] = {0.03, 1, 1, 1, 1, 1, 1, 1, 1};
+  knot_eval(z, z + 12, z + 24, z + 36, z + 48, prm, last, NULL, NULL, jp, NULL, NULL, hp);
+}
+
+void srb_knot_lists(const srb_plan *pl, const double *x, const double *p, int k,
+                    const double *lam_local, double *gl, double *Jl, double *Hl) {
+  int N = pl->N, last = (k == N - 2);
+  double prm[9];
+  knot_prm(pl, p, k, prm);
+  const double *U = x + 12 * N + 24 * k;
+  knot_eval(x + 12 * k, U, U + 12, x + 12 * (k + 1), last ? NULL : U + 24, prm, last, gl, Jl, NULL,
+            lam_local, Hl, NULL);
 }
 
 /* ------------------------------------------------------------------ bounds */

@@ -55,6 +55,15 @@ int srb_hess_l(const srb_plan *pl, const double *x, const double *p, double lam_
 int srb_grad(const srb_plan *pl, const double *x, const double *p, double lam_f,
              const double *lam_g, double *f, double *g, double *ggx, double *ggp);
 
+/* knot-level access for the interior-point reference (oracle/ip_ref.c): emission-order lists of
+ * one knot's Jacobian / Hessian entries and their (row,var) / (var,var) patterns.
+ * knot-local variables: 0-11 X_k, 12-23 c_k, 24-35 f_k, 36-47 X_{k+1}, 48-59 c_{k+1}. */
+typedef struct { short r, v; } srb_jpat;
+typedef struct { short a, b; } srb_hpat;
+void srb_knot_pattern(int last, srb_jpat *jp, srb_hpat *hp);
+void srb_knot_lists(const srb_plan *pl, const double *x, const double *p, int k,
+                    const double *lam_local, double *gl, double *Jl, double *Hl);
+
 /* lbg(p), ubg(p): the Opti canonicalisation (optistack_internal.cpp:742-870) of
  * generate_landingCtrller_IPOPT.m:90-169; +-HUGE_VAL for one-sided rows. */
 void srb_bounds(const srb_plan *pl, const double *p, double *lbg, double *ubg);

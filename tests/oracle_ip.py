@@ -1,0 +1,60 @@
+"""ctypes binding of the CPU interior-point reference (oracle/ip_ref.c). TEST INFRASTRUCTURE."""
+import ctypes
+import os
+
+import numpy as np
+
+from oracle_lib import Problem, _dp, build_oracle
+
+
+class IpOptions(ctypes.Structure):
+    _fields_ = [("max_iter", ctypes.c_int), ("tol", ctypes.c_double), ("constr_viol_tol", ctypes.c_double),
+                ("dual_inf_tol", ctypes.c_double), ("compl_inf_tol", ctypes.c_double),
+                ("mu_init", ctypes.c_double), ("bound_push", ctypes.c_double), ("bound_frac", ctypes.c_double),
+                ("bound_relax_factor", ctypes.c_double), ("max_soc", ctypes.c_int), ("verbose", ctypes.c_int)]
+
+
+class IpResult(ctypes.Structure):
+    _fields_ = [("status", ctypes.c_int), ("iters", ctypes.c_int), ("n_factor", ctypes.c_int),
+                ("f", ctypes.c_double), ("viol", ctypes.c_double), ("dual_inf", ctypes.c_double),
+                ("compl_inf", ctypes.c_double), ("mu", ctypes.c_double)]
+
+
+def _lib():
+    lib = ctypes.CDLL(build_oracle())
+    return lib
+
+
+def default_options(**kw):
+    o = IpOptions()
+    _lib().ip_options_default(ctypes.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def default_problem(**kw):
+    pb = Problem()
+    _lib().srb_problem_default(ctypes.byref(pb))
+    for k, v in kw.items():
+        setattr(pb, k, v)
+    return pb
+
+
+def solve_cpu(N, drops, opt=None, pb=None, threads=0):
+    """drops [B,12] -> dict(x [B,nx], status, iters, f, viol, n_factor)."""
+    lib = _lib()
+    drops = np.ascontiguousarray(drops, dtype=np.float64)
+    B = drops.shape[0]
+    nx = 36 * N - 24
+    opt = opt or default_options()
+    pb = pb or default_problem()
+    x = np.zeros((B, nx))
+    res = (IpResult * B)()
+    rc = lib.ip_solve_batch(N, B, _dp(drops), ctypes.byref(pb), ctypes.byref(opt), _dp(x), res,
+                            threads or (os.cpu_count() or 1))
+    assert rc == 0
+    return dict(x=x, status=np.array([r.status for r in res]), iters=np.array([r.iters for r in res]),
+                f=np.array([r.f for r in res]), viol=np.array([r.viol for r in res]),
+                n_factor=np.array([r.n_factor for r in res]), mu=np.array([r.mu for r in res]),
+                dual_inf=np.array([r.dual_inf for r in res]), compl_inf=np.array([r.compl_inf for r in res]))
