@@ -145,9 +145,9 @@ void landing_problem_default(landing_problem* pb) {
   pb->l_leg_max = 0.35;
   pb->f_max = 200.0;
   // composite rigid-body inertia at q_home (get_mass_matrix.m:19-54, generate_landingCtrller_IPOPT.m:99-104)
-  pb->mass = 8.252;
-  pb->Ib[0] = 0.05757729845; pb->Ib[1] = 0.23400899482; pb->Ib[2] = 0.27967384827;
-  pb->Ib_inv[0] = 17.37746888890; pb->Ib_inv[1] = 4.27334000930; pb->Ib_inv[2] = 3.57755192380;
+  pb->mass = 8.251999999999999;
+  pb->Ib[0] = 0.05757729852959269; pb->Ib[1] = 0.23400899479539086; pb->Ib[2] = 0.2796738482657981;
+  pb->Ib_inv[0] = 17.37746888893693; pb->Ib_inv[1] = 4.27334000932043; pb->Ib_inv[2] = 3.577551923825657;
 }
 
 void landing_options_default(landing_options* o) {

@@ -896,6 +896,8 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* sm, const doubl
     double dwreg = 0.0;
     bool ok = false;
     int tries = 0;
+    // while the previous iteration needed regularisation start from a third of it (ip_ref.c)
+    if (dw_last > 0.0) { dwreg = dw_last / 3.0; if (dwreg < 1e-7) dwreg = 0.0; }
     for (;;) {
       if (backward_sweep(P, w, sm, tab, dwreg, lane)) { ok = true; break; }
       __syncwarp();
@@ -905,7 +907,7 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* sm, const doubl
       if (dwreg > 1e40) break;
     }
     if (!ok) { status = LANDING_ST_FACTOR_FAIL; break; }
-    if (dwreg > 0.0) dw_last = dwreg;
+    dw_last = dwreg;
     StepInfo si;
     forward_sweep(P, w, sm, tab, drop, mu, tau, si, lane);
     __syncwarp();

@@ -817,9 +817,9 @@ void srb_problem_default(srb_problem *pb) {
   pb->l_leg_max = 0.35;
   pb->f_max = 200.0;
   /* CRBA at q_home (get_mass_matrix.m:19-54); restated in oracle/crba_constants.py */
-  pb->mass = 8.252;
-  pb->Ib[0] = 0.05757729845; pb->Ib[1] = 0.23400899482; pb->Ib[2] = 0.27967384827;
-  pb->Ib_inv[0] = 17.37746888890; pb->Ib_inv[1] = 4.27334000930; pb->Ib_inv[2] = 3.57755192380;
+  pb->mass = 8.251999999999999;
+  pb->Ib[0] = 0.05757729852959269; pb->Ib[1] = 0.23400899479539086; pb->Ib[2] = 0.2796738482657981;
+  pb->Ib_inv[0] = 17.37746888893693; pb->Ib_inv[1] = 4.27334000932043; pb->Ib_inv[2] = 3.577551923825657;
 }
 
 void srb_build_p_x0(const srb_plan *pl, const srb_problem *pb, const double *q_init,

@@ -104,7 +104,7 @@ def test_nan_is_reported_per_scenario():
     drops = lc.grid_sweep(8)
     p, x0 = s.build_host(drops)
     x0[3, 4] = np.pi / 2
-    x0[3, 7] = 1.0
+    x0[3, 8] = 1.0  # yaw-axis body rate -> tan(pitch) term
     out = s.eval_host(x0, p, want=("g",))
     assert out["status"][3] == -1 or np.max(np.abs(out["g"][3])) > 1e10
     assert np.all(out["status"][[0, 1, 2, 4, 5, 6, 7]] == 0)

@@ -1,0 +1,49 @@
+"""CPU tests of the interior-point restatement (oracle/ip_ref.c) and of the model constants."""
+import numpy as np
+
+import landing_controller_b200 as lc
+from oracle_ip import default_options, default_problem, solve_cpu
+from oracle_lib import Oracle
+
+
+def test_crba_constants_match_reference_pin():
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    from crba_constants import constants
+    c = constants()
+    # generate_data/data/data_stats.mat of the reference stores mass = 8.251999999999999
+    assert c["mass"] == 8.251999999999999
+    pb = default_problem()
+    assert pb.mass == c["mass"]
+    assert np.allclose(list(pb.Ib), c["Ib"], rtol=0, atol=1e-16) and np.allclose(list(pb.Ib_inv), c["Ib_inv"], rtol=1e-15)
+    # SURVEY 8a-10 probe values
+    assert np.allclose(c["Ib"], [0.0575772985, 0.2340089948, 0.2796738483], atol=1e-10)
+    assert abs(c["Ic"][0, 2] + 0.0029689956) < 1e-10
+
+
+def test_single_drop_converges_to_a_kkt_point():
+    """BASELINE config 0 drop condition (0.5 m, level, 1 m/s forward), N = 21."""
+    N = 21
+    d = lc.single_drop()
+    r = solve_cpu(N, d, threads=1)
+    assert r["status"][0] == 0 and r["iters"][0] < 400
+    o = Oracle(N)
+    p, _ = o.build_p_x0(default_problem(), d[0, :6], d[0, 6:])
+    lb, ub = o.bounds(p)
+    _, g = o.g(r["x"][0], p)
+    assert np.max(np.maximum(lb - g, g - ub)) <= 1e-3
+    _, f = o.f(r["x"][0], p)
+    assert abs(f - r["f"][0]) < 1e-12 and f < 1e-3  # the terminal reference is reachable
+    # touchdown: every leg carries load at some knot, none while the foot is in the air
+    cs = lc.contact_set(r["x"][0], N)
+    assert cs.any(axis=0).all()
+    U = r["x"][0][12 * N:].reshape(N - 1, 24)
+    assert np.all(U[:, 2:12:3][cs] < 0.02)  # c_z ~ 0 wherever f_z > 1 (complementarity f_z c_z <= 1e-3)
+
+
+def test_small_sweep_converges_and_is_deterministic():
+    d = lc.grid_sweep(1024)[::64]
+    a = solve_cpu(21, d, default_options(max_iter=1500))
+    b = solve_cpu(21, d, default_options(max_iter=1500), threads=2)
+    assert (a["status"] == 0).mean() >= 0.9
+    assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["iters"], b["iters"])

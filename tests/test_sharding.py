@@ -1,0 +1,67 @@
+"""CPU tests of the N>1 path: scenario sharding + the single all-gather of result records,
+world_size 2 over gloo (the GPU runs use the same code over NCCL)."""
+import os
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import landing_controller_b200 as lc
+
+
+def test_shard_bounds_cover_everything():
+    for n in (1, 7, 1024, 16384, 1000):
+        for w in (1, 2, 4, 8):
+            b = [lc.shard_bounds(n, w, r) for r in range(w)]
+            assert b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
+            assert max(h - l for l, h in b) - min(h - l for l, h in b) <= 1
+
+
+def test_grid_sweep_shapes():
+    for B in (1024, 2048, 16384):
+        d = lc.grid_sweep(B)
+        assert d.shape == (B, 12) and len(np.unique(d, axis=0)) == B
+    d = lc.grid_sweep(1024)
+    assert set(np.round(np.unique(d[:, 2]), 3)) == {0.4, 0.5, 0.6, 0.7}
+    assert np.isclose(d[:, 4].min(), -np.pi / 3) and np.isclose(d[:, 9].max(), 1.75)
+    r = lc.random_sweep(100, seed=0)
+    assert np.array_equal(r, lc.random_sweep(100, seed=0)) and r[:, 2].min() > 0.35
+
+
+def _worker(rank, world, port, n, nx, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    drops = lc.grid_sweep(1024)[:n]
+    lo, hi = lc.shard_bounds(n, world, rank)
+    mine = drops[lo:hi]
+    # stand-in for the GPU solve: a deterministic function of the drop condition
+    x = np.repeat(mine[:, :1] + mine[:, 2:3] * 10 + mine[:, 4:5] * 100 + mine[:, 9:10] * 1000, nx, axis=1)
+    rec = lc.pack_records(x, mine[:, 2], np.arange(lo, hi) % 3, np.arange(lo, hi))
+    full = lc.gather_records(rec, n, world, rank).numpy()
+    if rank == 0:
+        q.put(full)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_gather_of_records_world2_gloo():
+    n, nx, world = 37, 5, 2  # ragged on purpose
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, nx, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    full = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    out = lc.unpack_records(full)
+    drops = lc.grid_sweep(1024)[:n]
+    assert out["x"].shape == (n, nx)
+    assert np.array_equal(out["iters"], np.arange(n)) and np.array_equal(out["status"], np.arange(n) % 3)
+    assert np.allclose(out["f"], drops[:, 2])
+    assert np.allclose(out["x"][:, 0], drops[:, 0] + drops[:, 2] * 10 + drops[:, 4] * 100 + drops[:, 9] * 1000)
