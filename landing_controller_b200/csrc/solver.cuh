@@ -11,12 +11,15 @@ namespace srb {
 struct SolverTables {
   int *dev = nullptr;  // one allocation
   const int *jl_last, *hl_last;            // emission index of the last-knot template -> interior index
-  const int *g_e, *g_t; int g_n;           // dynamics entries -> G[state*36 + var]
-  const int *h_t;                          // Hessian entry -> M target i*48+j
-  const int *t_ptr, *t_ij, *t_terms; int t_n;  // condensing targets: sum sigma_rho J_ea J_eb
-  const int *q_ptr, *q_terms;              // stage gradient: per stage variable, sum yhat_rho J_e
   const int *r_ptr, *r_terms;              // per inequality row rho: sum J_e dw[idx]
-  const int *c_ptr, *c_terms;              // per local variable (60): sum J_e y_rho  (grad of Lagrangian)
+  const int *c_ptr, *c_terms;              // per local variable (60): sum J_e y_rho  (grad of the Lagrangian)
+  // tables the sweeps keep in SHARED memory (copied once per CTA): offsets into sm_src[0..sm_count)
+  const int *sm_src; int sm_count;
+  int o_g, n_g;          // dynamics entries: e | (state*36 + var) << 10   -> G
+  int o_qptr, o_qterms;  // stage gradient per stage variable (elimination order): (rho << 10) | e, padded to pairs
+  // condensing targets of the stage matrix (lower triangle, elimination order m = (s+24) mod 48):
+  //   M[a][b] += H[h] (if any) + sum sigma_rho J_ea J_eb over terms (rho<<20 | ea<<10 | eb), padded to pairs
+  int o_uabh, o_uptr, o_uterms, n_u;   // uabh = (a*48+b) | (h+1) << 12
 };
 
 struct SolverWorkspace {

@@ -1,0 +1,842 @@
+// solver_dev.cuh -- device side of the batched interior-point solver (included by solver.cu only).
+//
+// ONE CTA (128 threads) = ONE SCENARIO for the whole solve; 4 CTAs are resident per SM and pull
+// scenario ids from an atomic queue.  Phases of one interior-point iteration:
+//   (parallel over knots / rows, all 128 threads)
+//     eval        J lists by threads 0-63 (one knot each), H lists by threads 64-127
+//     row passes  sigma, yhat, optimality-error pieces, grad of the Lagrangian, step recovery,
+//                 fraction-to-the-boundary, merit function  -> block reductions
+//   (sequential over stages, all 128 threads cooperate on one stage)
+//     backward    stage lists staged in shared memory -> condensed 48x48 stage matrix ->
+//                 + G'PG terms -> Cholesky of the 24x24 control block -> Y = L^-1 M_ux -> P_k
+//     forward     u = -L^-T (Y xi + yv), xi+ = G [xi;u] + r, costates
+// All reductions end with the identical value in every thread, so control flow is block-uniform.
+#pragma once
+
+namespace srb {
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+constexpr int NT = 256;          // threads per CTA (= per scenario)
+constexpr int NWARP = NT / 32;
+constexpr int CTAS_PER_SM = 2;
+constexpr int NS = 24;           // stage state / control size
+constexpr int NW = 48;           // stage variables X(12) c(12) f(12) c+(12)
+constexpr int LDM = 49, LDP = 25, LDG = 37;  // leading dimensions (padding against bank conflicts)
+constexpr int MAXFILTER = 64;
+constexpr int RK = 104;          // rows per knot (interior numbering)
+constexpr int NROWTAB = 36 + RK;
+constexpr int NJ_PAD = 388, NH_PAD = 192;  // strides of the per-knot entry lists in the scratch (16-byte chunks; padding = 0)
+
+// ---- shared memory carve-up (doubles) per CTA
+constexpr int SM_M = 0;                        // 48 x 49 stage matrix (lower triangle, elimination order)
+constexpr int SM_P = SM_M + NW * LDM;          // 24 x 25   P_{k+1}
+constexpr int SM_G = SM_P + NS * LDP;          // 12 x 37   dynamics Jacobian G
+constexpr int SM_T = SM_G + 12 * LDG;          // 12 x 37   Pxx*G
+// stage list buffers (double-buffered, filled by cp.async): J | H | sigma | yhat | dynamics defects
+constexpr int LB_J = 0, LB_H = 388, LB_SIG = 580, LB_YH = 684, LB_GD = 788, LB_SIZE = 800;
+constexpr int SM_LB0 = SM_T + 12 * LDG;
+constexpr int SM_V = SM_LB0 + 2 * LB_SIZE;     // vectors
+constexpr int V_Q = 0, V_QH = 48, V_R = 96, V_T = 108, V_YV = 120, V_PN = 144, V_XI = 168, V_U = 192, V_END = 216;
+constexpr int SM_RED = SM_V + V_END;           // block-reduction scratch NWARP x 8
+constexpr int SM_TAB = SM_RED + NWARP * 8;     // lb[140] ub[140] lbo[140] ubo[140]
+constexpr int TL_WORDS = 296;                  // static tile tables (unsigned short), see sweeps.cuh
+constexpr int SM_TL = SM_TAB + 4 * NROWTAB;
+constexpr int TBL_INTS = 1700;                 // index tables of the sweeps (SolverTables::sm_src)
+constexpr int SM_TBL = SM_TL + TL_WORDS;
+constexpr int SM_TOTAL = SM_TBL + TBL_INTS / 2;
+static_assert(CTAS_PER_SM * (SM_TOTAL * 8 + 1024) <= 232448, "shared memory budget (227 KB per SM)");
+
+struct KParams {
+  int N, K, nx, MR;
+  long long B;
+  landing_problem pb;
+  landing_options opt;
+  const double* drops;
+  const double* x0;
+  double *x_star, *f_star, *lam_g, *viol;
+  int *status, *iters;
+  int* counter;
+  double* scratch;
+  long long slot;  // doubles per CTA slot
+  SolverTables tab;
+  unsigned long long* prof;  // optional per-phase cycle counters (LANDING_PROF=1), else nullptr
+};
+
+// phase ids of the optional cycle profile
+enum { PH_EVAL = 0, PH_ERR, PH_DUAL, PH_MU, PH_BACK, PH_FWD, PH_ROWS, PH_LS, PH_ACCEPT, PH_NBACK, PH_NITER,
+       PH_B_WAIT, PH_B_P1, PH_B_P2, PH_B_P3, PH_B_P4, PH_B_CHOL, PH_B_P6, PH_B_STAGES, PH_COUNT };
+struct Prof {
+  unsigned long long* c;
+  long long t;
+  __device__ __forceinline__ void start() { if (c && threadIdx.x == 0) t = clock64(); }
+  __device__ __forceinline__ void lap(int ph) {
+    if (c && threadIdx.x == 0) { const long long n = clock64(); atomicAdd(c + ph, (unsigned long long)(n - t)); t = n; }
+  }
+  __device__ __forceinline__ void count(int ph) { if (c && threadIdx.x == 0) atomicAdd(c + ph, 1ull); }
+};
+
+struct Ws {  // pointers into one CTA's scratch slot
+  double *x, *xt, *dx;
+  double *S, *Y, *ZL, *ZU, *G, *GT, *DS, *YN, *DZL, *DZU, *SIG, *YH;
+  double *JL, *HL;
+  double *FY, *rf, *yvf, *PX, *PV, *L0;  // FY: per stage [48][24] = L (rows 0-23) | Yt (rows 24-47)
+  double *FT, *FP;
+};
+
+__host__ __device__ inline long long slot_doubles(int N) {
+  const long long K = N - 1, nx = 36LL * N - 24, MR = 36 + RK * K;
+  const long long n = 3 * nx + 12 * MR + K * (NJ_PAD + NH_PAD) + K * (1152 + 12 + 24) + (K + 1) * (288 + 24) + 144 +
+                      2 * MAXFILTER;
+  return (n + 31) / 32 * 32;
+}
+
+__device__ inline Ws carve(double* base, int N) {
+  const long long K = N - 1, nx = 36LL * N - 24, MR = 36 + RK * K;
+  Ws w;
+  double* p = base;  // every array starts 16-byte aligned (all sizes are even)
+  w.x = p; p += nx; w.xt = p; p += nx; w.dx = p; p += nx;
+  w.S = p; p += MR; w.Y = p; p += MR; w.ZL = p; p += MR; w.ZU = p; p += MR; w.G = p; p += MR;
+  w.GT = p; p += MR; w.DS = p; p += MR; w.YN = p; p += MR; w.DZL = p; p += MR; w.DZU = p; p += MR;
+  w.SIG = p; p += MR; w.YH = p; p += MR;
+  w.JL = p; p += K * NJ_PAD; w.HL = p; p += K * NH_PAD;
+  w.FY = p; p += K * 1152; w.rf = p; p += K * 12;
+  w.yvf = p; p += K * 24; w.PX = p; p += (K + 1) * 288; w.PV = p; p += (K + 1) * 24;
+  w.L0 = p; p += 144; w.FT = p; p += MAXFILTER; w.FP = p; p += MAXFILTER;
+  return w;
+}
+
+// ---------------------------------------------------------------- block reductions
+enum { R_SUM = 0, R_MAX = 1, R_MIN = 2 };
+__device__ __forceinline__ double rcomb(int op, double a, double b) {
+  return op == R_SUM ? a + b : (op == R_MAX ? fmax(a, b) : fmin(a, b));
+}
+// Reduces NQ quantities over the CTA; every thread returns with the identical results in v[].
+template <int NQ>
+__device__ __forceinline__ void block_reduce(double* red, double (&v)[NQ], const int (&op)[NQ]) {
+  static_assert(NQ <= 8, "reduction scratch holds 8 values per warp");
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v[q] = rcomb(op[q], v[q], __shfl_xor_sync(FULL, v[q], o));
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int q = 0; q < NQ; q++) red[warp * 8 + q] = v[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    double a = red[q];
+#pragma unroll
+    for (int w2 = 1; w2 < NWARP; w2++) a = rcomb(op[q], a, red[w2 * 8 + q]);
+    v[q] = a;
+  }
+  __syncthreads();
+}
+__device__ __forceinline__ double bsum(double* red, double x) {
+  double v[1] = {x};
+  const int op[1] = {R_SUM};
+  block_reduce<1>(red, v, op);
+  return v[0];
+}
+__device__ __forceinline__ double bmax(double* red, double x) {
+  double v[1] = {x};
+  const int op[1] = {R_MAX};
+  block_reduce<1>(red, v, op);
+  return v[0];
+}
+
+// last-knot template row -> interior row numbering
+template <bool LAST> __device__ __forceinline__ constexpr int rowmap(int r) {
+  if (!LAST) return r;
+  if (r < 16) return r;
+  if (r < 40) return 16 + 12 * ((r - 16) / 6) + (((r - 16) % 6) < 2 ? ((r - 16) % 6) : ((r - 16) % 6) + 6);
+  return r + 24;
+}
+__device__ __forceinline__ bool is_noslip(int rho) { return rho >= 16 && rho < 64 && ((rho - 16) % 12) >= 2 && ((rho - 16) % 12) < 8; }
+// dynamics row (0..11: pos,rpy,v,om) <-> state index (pos,rpy,om,v)
+__device__ __forceinline__ int dyn_state(int rho) { return rho < 6 ? rho : (rho < 9 ? rho + 3 : rho - 3); }
+
+// row kinds
+enum { ROW_EQ = 0, ROW_INEQ = 1, ROW_FREE = 2 };
+__device__ __forceinline__ int row_kind(int idx, int K) {
+  if (idx < 12) return ROW_EQ;
+  if (idx < 36) return ROW_INEQ;
+  const int k = (idx - 36) / RK, rho = (idx - 36) - k * RK;
+  if (rho < 12) return ROW_EQ;
+  if (k == K - 1 && is_noslip(rho)) return ROW_FREE;
+  return ROW_INEQ;
+}
+__device__ __forceinline__ int row_tab(int idx) { return idx < 36 ? idx : 36 + (idx - 36) % RK; }
+
+// ---- sinks for the thread-per-knot evaluation
+template <bool LAST> struct JSink {  // g rows + Jacobian entry list
+  double *gp, *jl;
+  const int* jmap;
+  __device__ __forceinline__ void g(int r, double v) { gp[rowmap<LAST>(r)] = v; }
+  __device__ __forceinline__ void j(int e, int, int, double v) { jl[LAST ? __ldg(jmap + e) : e] = v; }
+  __device__ __forceinline__ void h(int, int, int, double) {}
+};
+template <bool LAST> struct HSink {  // Hessian entry list
+  double* hl;
+  const int* hmap;
+  __device__ __forceinline__ void g(int, double) {}
+  __device__ __forceinline__ void j(int, int, int, double) {}
+  __device__ __forceinline__ void h(int e, int, int, double v) { hl[LAST ? __ldg(hmap + e) : e] = v; }
+};
+template <bool LAST> struct GSink {
+  double* gp;
+  __device__ __forceinline__ void g(int r, double v) { gp[rowmap<LAST>(r)] = v; }
+  __device__ __forceinline__ void j(int, int, int, double) {}
+  __device__ __forceinline__ void h(int, int, int, double) {}
+};
+template <bool LAST> struct LamY {
+  const double* y;  // multipliers of this knot's rows (interior numbering)
+  __device__ __forceinline__ double operator()(int r) const { return y[rowmap<LAST>(r)]; }
+};
+
+__device__ __forceinline__ void load_knot(const KParams& P, const double* x, int k, Knot& kn) {
+  const int N = P.N;
+  const bool last = (k == N - 2);
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    kn.X[i] = x[12 * k + i];
+    kn.Xn[i] = x[12 * (k + 1) + i];
+    kn.c[i] = x[12 * N + 24 * k + i];
+    kn.f[i] = x[12 * N + 24 * k + 12 + i];
+    kn.cn[i] = last ? 0.0 : x[12 * N + 24 * (k + 1) + i];
+  }
+  kn.h = P.pb.T / (double)(N - 1);
+  kn.mu = P.pb.mu;
+  kn.mass = P.pb.mass;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { kn.Ib[i] = P.pb.Ib[i]; kn.Ibinv[i] = P.pb.Ib_inv[i]; }
+}
+
+__device__ __noinline__ void eval_knot_j(const KParams& P, const Ws& w, const double* x, double* gout, int k) {
+  Knot kn;
+  load_knot(P, x, k, kn);
+  NoLam nl;
+  if (k == P.K - 1) {
+    JSink<true> s{gout + 36 + RK * k, w.JL + (long long)k * NJ_PAD, P.tab.jl_last};
+    knot_eval<true, true, true, false>(kn, s, nl);
+  } else {
+    JSink<false> s{gout + 36 + RK * k, w.JL + (long long)k * NJ_PAD, nullptr};
+    knot_eval<false, true, true, false>(kn, s, nl);
+  }
+}
+__device__ __noinline__ void eval_knot_h(const KParams& P, const Ws& w, const double* x, int k) {
+  Knot kn;
+  load_knot(P, x, k, kn);
+  if (k == P.K - 1) {
+    HSink<true> s{w.HL + (long long)k * NH_PAD, P.tab.hl_last};
+    LamY<true> lam{w.Y + 36 + RK * k};
+    knot_eval<true, false, false, true>(kn, s, lam);
+  } else {
+    HSink<false> s{w.HL + (long long)k * NH_PAD, nullptr};
+    LamY<false> lam{w.Y + 36 + RK * k};
+    knot_eval<false, false, false, true>(kn, s, lam);
+  }
+}
+__device__ __noinline__ void eval_knot_g(const KParams& P, const double* x, double* gout, int k) {
+  Knot kn;
+  load_knot(P, x, k, kn);
+  NoLam nl;
+  if (k == P.K - 1) {
+    GSink<true> s{gout + 36 + RK * k};
+    knot_eval<true, true, false, false>(kn, s, nl);
+  } else {
+    GSink<false> s{gout + 36 + RK * k};
+    knot_eval<false, true, false, false>(kn, s, nl);
+  }
+}
+
+// g(x) (and, when LISTS, the J/H entry lists with multipliers Y) for all knots; returns f(x)
+template <bool LISTS>
+__device__ double eval_all(const KParams& P, const Ws& w, const double* x, double* gout, double* red) {
+  const int N = P.N, K = P.K, tid = threadIdx.x;
+  if (LISTS) {
+    const int part = tid >> 6, t64 = tid & 63;  // warps 0-1: Jacobian lists, warps 4-5: Hessian lists
+    if (part == 0) {
+      for (int k = t64; k < K; k += 64) eval_knot_j(P, w, x, gout, k);
+    } else if (part == 2) {
+      for (int k = t64; k < K; k += 64) eval_knot_h(P, w, x, k);
+    }
+  } else {
+    for (int k = tid; k < K; k += NT) eval_knot_g(P, x, gout, k);
+  }
+  // boundary rows 0..35 and objective (generate_landingCtrller_IPOPT.m:83-97)
+  double fl = 0.0;
+  const int xo = 12 * (N - 1);
+  if (tid >= 224 && tid < 236) {
+    const int i = tid - 224;
+    gout[i] = x[i];
+    const double q = x[xo + i];
+    const int r1 = i < 6 ? 12 + i : 24 + (i - 6);
+    gout[r1] = q;
+    gout[r1 + 6] = q;
+    const double ref = i < 6 ? P.pb.q_term_ref[i] : P.pb.qd_term_ref[i - 6];
+    fl = P.pb.QN[i] * (q - ref) * (q - ref);
+  }
+  return bsum(red, fl);  // (syncs: gout / lists are visible to the whole CTA afterwards)
+}
+
+struct StepInfo {
+  double a_pr, a_du, dphi_bar, phi_bar, theta;  // barrier parts of dphi / phi, and theta at the current point
+};
+
+// per-row step recovery for one inequality row: ds, new multiplier, dz, step limits, merit pieces
+__device__ __forceinline__ void row_step(const Ws& w, int idx, double lb, double ub, double jdx, double mu, double tau,
+                                         StepInfo& si) {
+  const double s = w.S[idx], rd = w.G[idx] - s;
+  const double ds = jdx + rd;
+  double yn = w.SIG[idx] * ds, dzl = 0.0, dzu = 0.0;
+  si.theta += fabs(rd);
+  if (isfinite(lb)) {
+    const double d = s - lb, z = w.ZL[idx];
+    yn -= mu / d;
+    dzl = mu / d - z - z / d * ds;
+    if (ds < 0) si.a_pr = fmin(si.a_pr, -tau * d / ds);
+    if (dzl < 0) si.a_du = fmin(si.a_du, -tau * z / dzl);
+    si.dphi_bar -= mu * ds / d;
+    si.phi_bar -= mu * log(d);
+  }
+  if (isfinite(ub)) {
+    const double d = ub - s, z = w.ZU[idx];
+    yn += mu / d;
+    dzu = mu / d - z + z / d * ds;
+    if (ds > 0) si.a_pr = fmin(si.a_pr, tau * d / ds);
+    if (dzu < 0) si.a_du = fmin(si.a_du, -tau * z / dzu);
+    si.dphi_bar += mu * ds / d;
+    si.phi_bar -= mu * log(d);
+  }
+  w.DS[idx] = ds;
+  w.YN[idx] = yn;
+  w.DZL[idx] = dzl;
+  w.DZU[idx] = dzu;
+}
+
+#include "sweeps.cuh"
+
+// stage variable (X 0-11, c 12-23, f 24-35, c+ 36-47) of knot k -> index into x / dx
+__device__ __forceinline__ int stage_var(int N, int k, int sv) {
+  if (sv < 12) return 12 * k + sv;
+  if (sv < 36) return 12 * N + 24 * k + (sv - 12);
+  return 12 * N + 24 * (k + 1) + (sv - 36);
+}
+
+// ds = J_row . dx + (g - s), new multipliers, dz, fraction-to-the-boundary limits, merit pieces: all rows in parallel
+__device__ __noinline__ void row_steps(const KParams& P, const Ws& w, const double* tab, const double* drop,
+                                       double* red, double mu, double tau, StepInfo& si) {
+  const int N = P.N, K = P.K, MR = P.MR, tid = threadIdx.x;
+  const SolverTables& tb = P.tab;
+  si.a_pr = 1.0; si.a_du = 1.0; si.dphi_bar = 0.0; si.phi_bar = 0.0; si.theta = 0.0;
+  for (int idx = tid; idx < MR; idx += NT) {
+    if (idx < 12) { si.theta += fabs(w.G[idx] - drop[idx]); continue; }
+    if (idx < 36) {
+      const int j = idx - 12, i = (j < 12 ? j % 6 : 6 + (j - 12) % 6);
+      row_step(w, idx, tab[idx], tab[NROWTAB + idx], w.dx[12 * (N - 1) + i], mu, tau, si);
+      continue;
+    }
+    const int k = (idx - 36) / RK, rho = (idx - 36) - k * RK;
+    if (rho < 12) { si.theta += fabs(w.G[idx]); continue; }
+    if (k == K - 1 && is_noslip(rho)) continue;
+    const double* Jk = w.JL + (long long)k * NJ_PAD;
+    double jdx = 0.0;
+    const int p0 = __ldg(tb.r_ptr + rho), p1 = __ldg(tb.r_ptr + rho + 1);
+    for (int p = p0; p < p1; p++) {
+      const int term = __ldg(tb.r_terms + p), sv = term >> 10;
+      if (k == K - 1 && sv >= 36) continue;  // no c+ at the last knot
+      jdx += Jk[term & 1023] * w.dx[stage_var(N, k, sv)];
+    }
+    row_step(w, idx, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
+  }
+  double v[5] = {si.a_pr, si.a_du, si.dphi_bar, si.phi_bar, si.theta};
+  const int op[5] = {R_MIN, R_MIN, R_SUM, R_SUM, R_SUM};
+  block_reduce<5>(red, v, op);
+  si.a_pr = v[0]; si.a_du = v[1]; si.dphi_bar = v[2]; si.phi_bar = v[3]; si.theta = v[4];
+}
+
+// merit function pieces at the trial point (x + a dx, s + a ds) with g(trial) in GT
+__device__ __forceinline__ void merit_trial(const KParams& P, const Ws& w, const double* tab, const double* drop,
+                                            double* red, double alpha, double mu, double& phi_bar, double& theta) {
+  const int K = P.K, MR = P.MR;
+  double ph = 0.0, th = 0.0;
+  for (int idx = threadIdx.x; idx < MR; idx += NT) {
+    const int kind = row_kind(idx, K);
+    if (kind == ROW_FREE) continue;
+    if (kind == ROW_EQ) {
+      th += fabs(w.GT[idx] - (idx < 12 ? drop[idx] : 0.0));
+      continue;
+    }
+    const int t = row_tab(idx);
+    const double lb = tab[t], ub = tab[NROWTAB + t];
+    const double s = w.S[idx] + alpha * w.DS[idx];
+    th += fabs(w.GT[idx] - s);
+    if (isfinite(lb)) ph -= mu * log(s - lb);
+    if (isfinite(ub)) ph -= mu * log(ub - s);
+  }
+  double v[2] = {ph, th};
+  const int op[2] = {R_SUM, R_SUM};
+  block_reduce<2>(red, v, op);
+  phi_bar = v[0];
+  theta = v[1];
+}
+
+struct Errs {
+  double dual, prim, c0, cmu, ysum, zsum, viol;
+  int nzb;
+};
+
+// sigma per row and the pieces of the optimality error (oracle/ip_ref.c: assemble)
+__device__ __forceinline__ void row_errors(const KParams& P, const Ws& w, const double* tab, const double* drop,
+                                           double* red, double mu, Errs& e) {
+  const int K = P.K, MR = P.MR;
+  double dual = 0, prim = 0, c0 = 0, cmu = 0, ys = 0, zs = 0, viol = 0, nb = 0;
+  for (int idx = threadIdx.x; idx < MR; idx += NT) {
+    const int kind = row_kind(idx, K);
+    if (kind == ROW_FREE) continue;
+    const double g = w.G[idx], y = w.Y[idx];
+    ys += fabs(y);
+    if (kind == ROW_EQ) {
+      const double c = fabs(g - (idx < 12 ? drop[idx] : 0.0));
+      prim = fmax(prim, c);
+      viol = fmax(viol, c);
+      w.SIG[idx] = 0.0;
+      continue;
+    }
+    const int t = row_tab(idx);
+    const double lb = tab[t], ub = tab[NROWTAB + t];
+    viol = fmax(viol, fmax(tab[2 * NROWTAB + t] - g, g - tab[3 * NROWTAB + t]));
+    const double s = w.S[idx];
+    double sg = 0, rs = -y;
+    if (isfinite(lb)) {
+      const double d = s - lb, z = w.ZL[idx];
+      sg += z / d;
+      rs -= z;
+      c0 = fmax(c0, fabs(z * d));
+      cmu = fmax(cmu, fabs(z * d - mu));
+      zs += z;
+      nb += 1.0;
+    }
+    if (isfinite(ub)) {
+      const double d = ub - s, z = w.ZU[idx];
+      sg += z / d;
+      rs += z;
+      c0 = fmax(c0, fabs(z * d));
+      cmu = fmax(cmu, fabs(z * d - mu));
+      zs += z;
+      nb += 1.0;
+    }
+    prim = fmax(prim, fabs(g - s));
+    dual = fmax(dual, fabs(rs));
+    w.SIG[idx] = sg;
+  }
+  double v[8] = {dual, prim, c0, cmu, ys, zs, viol, nb};
+  const int op[8] = {R_MAX, R_MAX, R_MAX, R_MAX, R_SUM, R_SUM, R_MAX, R_SUM};
+  block_reduce<8>(red, v, op);
+  e.dual = v[0]; e.prim = v[1]; e.c0 = v[2]; e.cmu = v[3]; e.ysum = v[4]; e.zsum = v[5]; e.viol = v[6];
+  e.nzb = (int)(v[7] + 0.5);
+}
+
+__device__ __forceinline__ double compl_at(const KParams& P, const Ws& w, const double* tab, double* red, double mu) {
+  const int K = P.K, MR = P.MR;
+  double cmu = 0;
+  for (int idx = threadIdx.x; idx < MR; idx += NT) {
+    if (row_kind(idx, K) != ROW_INEQ) continue;
+    const int t = row_tab(idx);
+    const double lb = tab[t], ub = tab[NROWTAB + t], s = w.S[idx];
+    if (isfinite(lb)) cmu = fmax(cmu, fabs(w.ZL[idx] * (s - lb) - mu));
+    if (isfinite(ub)) cmu = fmax(cmu, fabs(w.ZU[idx] * (ub - s) - mu));
+  }
+  return bmax(red, cmu);
+}
+
+// yhat = sigma (g - s) - mu/(s-lb) + mu/(ub-s)
+__device__ __forceinline__ void row_yhat(const KParams& P, const Ws& w, const double* tab, double mu) {
+  const int K = P.K, MR = P.MR;
+  for (int idx = threadIdx.x; idx < MR; idx += NT) {
+    if (row_kind(idx, K) != ROW_INEQ) { w.YH[idx] = 0.0; continue; }
+    const int t = row_tab(idx);
+    const double lb = tab[t], ub = tab[NROWTAB + t], s = w.S[idx];
+    double yh = w.SIG[idx] * (w.G[idx] - s);
+    if (isfinite(lb)) yh -= mu / (s - lb);
+    if (isfinite(ub)) yh += mu / (ub - s);
+    w.YH[idx] = yh;
+  }
+}
+
+// max |grad f + J' y| (gradient of the Lagrangian w.r.t. x): one (knot, variable) item per thread
+__device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, double* red) {
+  const int N = P.N, K = P.K, tid = threadIdx.x;
+  const SolverTables& tb = P.tab;
+  double dmax = 0.0;
+  for (int item = tid; item < K * 36; item += NT) {
+    const int k = item / 36, v = item - k * 36;
+    const double* Jk = w.JL + (long long)k * NJ_PAD;
+    const double* yk = w.Y + 36 + RK * k;
+    double a = 0.0;
+    {
+      const int p0 = __ldg(tb.c_ptr + v), p1 = __ldg(tb.c_ptr + v + 1);
+      for (int p = p0; p < p1; p++) {
+        const int term = __ldg(tb.c_terms + p);
+        a += Jk[term & 1023] * yk[term >> 10];
+      }
+    }
+    if (v < NS) {
+      if (k > 0) {  // what knot k-1 contributes to (X_k, c_k) through its X+ / c+ columns
+        const double* Jp = Jk - NJ_PAD;
+        const double* yp = yk - RK;
+        const int p0 = __ldg(tb.c_ptr + 36 + v), p1 = __ldg(tb.c_ptr + 36 + v + 1);
+        for (int p = p0; p < p1; p++) {
+          const int term = __ldg(tb.c_terms + p);
+          a += Jp[term & 1023] * yp[term >> 10];
+        }
+      } else if (v < 12) {
+        a += w.Y[v];  // initial-state rows act on X_0
+      }
+    }
+    dmax = fmax(dmax, fabs(a));
+  }
+  if (tid < 12) {  // terminal state: last knot's X+ columns, objective gradient and terminal rows
+    const double* Jk = w.JL + (long long)(K - 1) * NJ_PAD;
+    const double* yk = w.Y + 36 + RK * (K - 1);
+    double a = 0.0;
+    const int p0 = __ldg(tb.c_ptr + 36 + tid), p1 = __ldg(tb.c_ptr + 36 + tid + 1);
+    for (int p = p0; p < p1; p++) {
+      const int term = __ldg(tb.c_terms + p);
+      a += Jk[term & 1023] * yk[term >> 10];
+    }
+    const int r1 = tid < 6 ? 12 + tid : 24 + (tid - 6);
+    const double q = w.x[12 * (N - 1) + tid];
+    const double ref = tid < 6 ? P.pb.q_term_ref[tid] : P.pb.qd_term_ref[tid - 6];
+    dmax = fmax(dmax, fabs(a + 2.0 * P.pb.QN[tid] * (q - ref) + w.Y[r1] + w.Y[r1 + 6]));
+  }
+  return bmax(red, dmax);
+}
+
+// slacks pushed inside their bounds at the current g; mu-based bound multipliers (ip_ref.c: init_slacks)
+__device__ __forceinline__ void init_slacks(const KParams& P, const Ws& w, const double* tab, double mu) {
+  const int K = P.K, MR = P.MR;
+  const double bp = P.opt.bound_push, bf = P.opt.bound_frac;
+  for (int idx = threadIdx.x; idx < MR; idx += NT) {
+    w.Y[idx] = 0.0; w.ZL[idx] = 0.0; w.ZU[idx] = 0.0; w.S[idx] = 0.0;
+    if (row_kind(idx, K) != ROW_INEQ) continue;
+    const int t = row_tab(idx);
+    const double l = tab[t], u = tab[NROWTAB + t];
+    double sv = w.G[idx];
+    if (isfinite(l) && isfinite(u)) {
+      const double pL = fmin(bp * fmax(1.0, fabs(l)), bf * (u - l));
+      const double pU = fmin(bp * fmax(1.0, fabs(u)), bf * (u - l));
+      sv = fmin(fmax(sv, l + pL), u - pU);
+    } else if (isfinite(l)) {
+      sv = fmax(sv, l + bp * fmax(1.0, fabs(l)));
+    } else {
+      sv = fmin(sv, u - bp * fmax(1.0, fabs(u)));
+    }
+    w.S[idx] = sv;
+    double zl = 0.0, zu = 0.0;
+    if (isfinite(l)) zl = mu / (sv - l);
+    if (isfinite(u)) zu = mu / (u - sv);
+    w.ZL[idx] = zl;
+    w.ZU[idx] = zu;
+    w.Y[idx] = zu - zl;
+  }
+  __syncthreads();
+}
+
+// bound tables of one CTA: [lb | ub | lb_orig | ub_orig] x (36 boundary rows + 104 interior knot rows)
+__device__ void build_tables(const KParams& P, double* tab) {
+  const landing_problem& pb = P.pb;
+  const double INF = HUGE_VAL;
+  for (int t = threadIdx.x; t < NROWTAB; t += blockDim.x) {
+    double lb = 0.0, ub = 0.0;
+    if (t < 12) { lb = ub = 0.0; }
+    else if (t < 18) { lb = pb.q_term_min[t - 12]; ub = INF; }
+    else if (t < 24) { lb = -INF; ub = pb.q_term_max[t - 18]; }
+    else if (t < 30) { lb = pb.qd_term_min[t - 24]; ub = INF; }
+    else if (t < 36) { lb = -INF; ub = pb.qd_term_max[t - 30]; }
+    else {
+      const int rho = t - 36;
+      if (rho < 12) { lb = ub = 0.0; }
+      else if (rho < 16) { lb = 0.0; ub = pb.f_max; }
+      else if (rho < 64) {
+        const int j = (rho - 16) % 12;
+        if (j == 0) { lb = 0.0; ub = INF; }
+        else if (j == 1) { lb = -INF; ub = 0.001; }
+        else if (j < 5) { lb = -INF; ub = 0.01; }
+        else if (j < 8) { lb = -0.01; ub = INF; }
+        else if (j < 10) { lb = -0.15; ub = 0.15; }
+        else if (j == 10) { lb = -0.30; ub = 0.0; }
+        else { lb = -INF; ub = pb.l_leg_max * pb.l_leg_max; }
+      }
+      else if (rho < 80) { lb = -INF; ub = 0.0; }
+      else if (rho < 86) { lb = -INF; ub = pb.q_max[rho - 80]; }
+      else if (rho < 92) { lb = pb.q_min[rho - 86]; ub = INF; }
+      else if (rho < 98) { lb = -INF; ub = pb.qd_max[rho - 92]; }
+      else { lb = pb.qd_min[rho - 98]; ub = INF; }
+    }
+    tab[2 * NROWTAB + t] = lb;
+    tab[3 * NROWTAB + t] = ub;
+    if (lb != ub) {  // bound_relax_factor on inequality rows
+      if (isfinite(lb)) lb -= P.opt.bound_relax_factor * fmax(1.0, fabs(lb));
+      if (isfinite(ub)) ub += P.opt.bound_relax_factor * fmax(1.0, fabs(ub));
+    }
+    tab[t] = lb;
+    tab[NROWTAB + t] = ub;
+  }
+}
+
+// ---------------------------------------------------------------- one scenario
+__device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long b) {
+  const int N = P.N, K = P.K, nx = P.nx, MR = P.MR, tid = threadIdx.x;
+  const landing_options& opt = P.opt;
+  const double kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
+  const double gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8, s_theta = 1.1, s_phi = 2.3, delta_sw = 1.0;
+  const double kappa_sigma = 1e10, s_max = 100.0;
+  const double* drop = P.drops + 12 * b;
+  const double* tab = smem + SM_TAB;
+  double* red = smem + SM_RED;
+
+  // initial guess: user x0 or the reference's [Xref(:); Uref(:)] (generate_landingCtrller_IPOPT.m:199-208,336)
+  if (P.x0) {
+    for (int i = tid; i < nx; i += NT) w.x[i] = P.x0[b * nx + i];
+  } else {
+    for (int k = tid; k < N; k += NT) {
+      const double t = (double)k / (double)(N - 1);
+      double xr[12];
+      for (int i = 0; i < 6; i++) {
+        xr[i] = (k == N - 1) ? P.pb.q_term_ref[i] : __dadd_rn(drop[i], __dmul_rn(P.pb.q_term_ref[i] - drop[i], t));
+        xr[6 + i] = (k == N - 1) ? P.pb.qd_term_ref[i]
+                                 : __dadd_rn(drop[6 + i], __dmul_rn(P.pb.qd_term_ref[i] - drop[6 + i], t));
+      }
+      for (int i = 0; i < 12; i++) w.x[12 * k + i] = xr[i];
+      if (k < N - 1)
+        for (int l = 0; l < 4; l++)
+          for (int i = 0; i < 3; i++) {
+            w.x[12 * N + 24 * k + 3 * l + i] = xr[i] + P.pb.c_ref[3 * l + i];
+            w.x[12 * N + 24 * k + 12 + 3 * l + i] = 0.0;
+          }
+    }
+  }
+  // rows / list slots the last knot never writes (no no-slip rows there)
+  // list slots never written: the padding of every knot and the no-slip entries of the last knot
+  for (int i = tid; i < K * NJ_PAD; i += NT) w.JL[i] = 0.0;
+  for (int i = tid; i < K * NH_PAD; i += NT) w.HL[i] = 0.0;
+  for (int i = tid; i < MR; i += NT) {
+    w.G[i] = 0.0; w.GT[i] = 0.0; w.DS[i] = 0.0; w.YN[i] = 0.0; w.DZL[i] = 0.0; w.DZU[i] = 0.0;
+    w.SIG[i] = 0.0; w.YH[i] = 0.0; w.Y[i] = 0.0;
+  }
+  __syncthreads();
+  double f = eval_all<false>(P, w, w.x, w.G, red);
+  double mu = opt.mu_init;
+  init_slacks(P, w, tab, mu);
+
+  int nfilt = 0, restarts = 0, status = LANDING_ST_MAX_ITER, it = 0;
+  double theta0 = -1.0, dw_last = 0.0, viol = 0.0;
+  Prof pf{P.prof, 0};
+  for (it = 0; it <= opt.max_iter; it++) {
+    pf.start();
+    f = eval_all<true>(P, w, w.x, w.G, red);
+    pf.lap(PH_EVAL);
+    Errs er;
+    row_errors(P, w, tab, drop, red, mu, er);
+    pf.lap(PH_ERR);
+    const double dual = fmax(er.dual, dual_inf_x(P, w, red));
+    pf.lap(PH_DUAL);
+    pf.count(PH_NITER);
+    const double s_d = fmax(s_max, (er.ysum + er.zsum) / (double)(P.opt.reserved[0] + er.nzb)) / s_max;
+    const double s_c = fmax(s_max, er.zsum / (double)(er.nzb > 0 ? er.nzb : 1)) / s_max;
+    const double E0 = fmax(fmax(dual / s_d, er.prim), er.c0 / s_c);
+    viol = er.viol;
+    if (!isfinite(E0) || !isfinite(f)) { status = LANDING_ST_NAN; break; }
+    if (E0 <= opt.tol && dual <= opt.dual_inf_tol && viol <= opt.constr_viol_tol && er.c0 <= opt.compl_inf_tol) {
+      status = LANDING_ST_CONVERGED;
+      break;
+    }
+    if (it == opt.max_iter) { status = LANDING_ST_MAX_ITER; break; }
+    // monotone barrier update
+    {
+      double cmu = er.cmu;
+      bool changed = false;
+      for (;;) {
+        const double Emu = fmax(fmax(dual / s_d, er.prim), cmu / s_c);
+        if (!(Emu <= kappa_eps * mu) || mu <= opt.tol / 10.0 * 1.0000001) break;
+        mu = fmax(opt.tol / 10.0, fmin(kappa_mu * mu, pow(mu, theta_mu)));
+        changed = true;
+        cmu = compl_at(P, w, tab, red, mu);
+      }
+      if (changed) nfilt = 0;
+    }
+    row_yhat(P, w, tab, mu);
+    __syncthreads();
+    pf.lap(PH_MU);
+    const double tau = fmax(tau_min, 1.0 - mu);
+    // factorise with inertia correction (IPOPT's delta_w schedule)
+    double dwreg = 0.0;
+    bool ok = false;
+    int tries = 0;
+    // while the previous iteration needed regularisation start from a third of it (ip_ref.c)
+    if (dw_last > 0.0) { dwreg = dw_last / 3.0; if (dwreg < 1e-7) dwreg = 0.0; }
+    for (;;) {
+      pf.count(PH_NBACK);
+      if (backward_sweep(P, w, smem, dwreg)) { ok = true; break; }
+      __syncthreads();
+      if (dwreg == 0.0) dwreg = (dw_last == 0.0) ? 1e-4 : fmax(1e-20, dw_last / 3.0);
+      else dwreg *= (dw_last == 0.0 && tries < 8) ? 100.0 : 8.0;
+      tries++;
+      if (dwreg > 1e40) break;
+    }
+    if (!ok) { status = LANDING_ST_FACTOR_FAIL; break; }
+    dw_last = dwreg;
+    pf.lap(PH_BACK);
+    forward_sweep(P, w, smem, drop);
+    costates(P, w);
+    pf.lap(PH_FWD);
+    StepInfo si;
+    row_steps(P, w, tab, drop, red, mu, tau, si);
+    pf.lap(PH_ROWS);
+    // filter line search
+    const double theta = si.theta, phi = f + si.phi_bar;
+    if (theta0 < 0) theta0 = theta;
+    const double theta_max = 1e4 * fmax(1.0, theta0), theta_min = 1e-4 * fmax(1.0, theta0);
+    double dphi = si.dphi_bar;
+    {
+      double d = 0.0;
+      if (tid < 12) {
+        const double q = w.x[12 * (N - 1) + tid];
+        const double ref = tid < 6 ? P.pb.q_term_ref[tid] : P.pb.qd_term_ref[tid - 6];
+        d = 2.0 * P.pb.QN[tid] * (q - ref) * w.dx[12 * (N - 1) + tid];
+      }
+      dphi += bsum(red, d);
+    }
+    double alpha = si.a_pr, ft = f;
+    bool accepted = false, ftype = false;
+    int ls = 0;
+    while (alpha > 1e-12 * si.a_pr && ls < 40) {
+      for (int i = tid; i < nx; i += NT) w.xt[i] = w.x[i] + alpha * w.dx[i];
+      __syncthreads();
+      ft = eval_all<false>(P, w, w.xt, w.GT, red);
+      double phb, tht;
+      merit_trial(P, w, tab, drop, red, alpha, mu, phb, tht);
+      const double pht = ft + phb;
+      int filt_ok = 1;
+      for (int i = tid; i < nfilt; i += NT)
+        if (tht >= w.FT[i] && pht >= w.FP[i]) filt_ok = 0;
+      filt_ok = __syncthreads_and(filt_ok);
+      if (isfinite(pht) && isfinite(tht) && tht <= theta_max && filt_ok) {
+        const bool sw = (theta <= theta_min) && (dphi < 0) && (alpha * pow(-dphi, s_phi) > delta_sw * pow(theta, s_theta));
+        if (sw) {
+          if (pht <= phi + eta_phi * alpha * dphi) { accepted = true; ftype = true; }
+        } else if (tht <= (1.0 - gamma_theta) * theta || pht <= phi - gamma_phi * theta) {
+          accepted = true;
+        }
+      }
+      if (accepted) break;
+      alpha *= 0.5;
+      ls++;
+    }
+    pf.lap(PH_LS);
+    if (!accepted) {
+      if (restarts < 20) {  // re-centre: slacks back inside their bounds, multipliers reset, mu = mu_init
+        restarts++;
+        mu = opt.mu_init;
+        init_slacks(P, w, tab, mu);
+        nfilt = 0;
+        theta0 = -1.0;
+        continue;
+      }
+      status = LANDING_ST_LINESEARCH_FAIL;
+      break;
+    }
+    if (!ftype) {
+      if (nfilt == MAXFILTER) {  // drop the oldest entry
+        double a = 0, c = 0;
+        if (tid + 1 < MAXFILTER) { a = w.FT[tid + 1]; c = w.FP[tid + 1]; }
+        __syncthreads();
+        if (tid + 1 < MAXFILTER) { w.FT[tid] = a; w.FP[tid] = c; }
+        nfilt--;
+      }
+      __syncthreads();
+      if (tid == 0) { w.FT[nfilt] = (1.0 - gamma_theta) * theta; w.FP[nfilt] = phi - gamma_phi * theta; }
+      nfilt++;
+    }
+    // accept the trial point
+    for (int i = tid; i < nx; i += NT) w.x[i] = w.xt[i];
+    f = ft;
+    for (int idx = tid; idx < MR; idx += NT) {
+      const int kind = row_kind(idx, K);
+      if (kind == ROW_FREE) continue;
+      w.G[idx] = w.GT[idx];
+      const double y = w.Y[idx];
+      w.Y[idx] = y + alpha * (w.YN[idx] - y);
+      if (kind == ROW_EQ) continue;
+      const int t = row_tab(idx);
+      const double lb = tab[t], ub = tab[NROWTAB + t];
+      const double s = w.S[idx] + alpha * w.DS[idx];
+      w.S[idx] = s;
+      if (isfinite(lb)) {
+        const double d = s - lb;
+        double z = w.ZL[idx] + si.a_du * w.DZL[idx];
+        z = fmax(fmin(z, kappa_sigma * mu / d), mu / (kappa_sigma * d));
+        w.ZL[idx] = z;
+      }
+      if (isfinite(ub)) {
+        const double d = ub - s;
+        double z = w.ZU[idx] + si.a_du * w.DZU[idx];
+        z = fmax(fmin(z, kappa_sigma * mu / d), mu / (kappa_sigma * d));
+        w.ZU[idx] = z;
+      }
+    }
+    __syncthreads();
+    pf.lap(PH_ACCEPT);
+  }
+  // results (AoS, CasADi order)
+  for (int i = tid; i < nx; i += NT) P.x_star[b * nx + i] = w.x[i];
+  if (P.lam_g) {
+    const long long m = 104LL * N - 92;
+    for (int idx = tid; idx < MR; idx += NT) {
+      if (idx < 36 + RK * (K - 1)) { P.lam_g[b * m + idx] = w.Y[idx]; continue; }
+      // last knot: interior numbering -> the 80-row layout of the generated functions
+      const int rho = idx - 36 - RK * (K - 1);
+      if (is_noslip(rho)) continue;
+      int r = rho;
+      if (rho >= 64) r = rho - 24;
+      else if (rho >= 16) { const int l = (rho - 16) / 12, j = (rho - 16) % 12; r = 16 + 6 * l + (j < 2 ? j : j - 6); }
+      P.lam_g[b * m + 36 + RK * (K - 1) + r] = w.Y[idx];
+    }
+  }
+  if (tid == 0) {
+    P.f_star[b] = f;
+    P.status[b] = status;
+    P.iters[b] = it;
+    if (P.viol) P.viol[b] = viol;
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_solve(KParams P) {
+  extern __shared__ double smem[];
+  __shared__ long long s_next;
+  build_tables(P, smem + SM_TAB);
+  build_tile_tables(reinterpret_cast<unsigned short*>(smem + SM_TL));
+  {
+    int* tbl = reinterpret_cast<int*>(smem + SM_TBL);
+    for (int i = threadIdx.x; i < P.tab.sm_count; i += NT) tbl[i] = __ldg(P.tab.sm_src + i);
+  }
+  __syncthreads();
+  const Ws w = carve(P.scratch + (long long)blockIdx.x * P.slot, P.N);
+  for (;;) {
+    if (threadIdx.x == 0) s_next = atomicAdd(P.counter, 1);
+    __syncthreads();
+    const long long b = s_next;
+    __syncthreads();
+    if (b >= P.B) break;
+    solve_one(P, w, smem, b);
+  }
+}
+
+}  // namespace
+}  // namespace srb

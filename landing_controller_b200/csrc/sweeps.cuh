@@ -1,0 +1,524 @@
+// sweeps.cuh -- the two sequential passes of the Riccati solve, one stage at a time, all 128
+// threads of the CTA on one stage (included by solver_dev.cuh).
+//
+// Stage matrix layout: the 48 stage variables are stored in ELIMINATION order
+//     m = 0..11 f_k | 12..23 c_{k+1} | 24..35 X_k | 36..47 c_k          (m = (s + 24) mod 48)
+// and only the lower triangle M[a][b], a >= b, is kept.  One blocked right-looking partial Cholesky
+// (24 pivots, blocks of 4, the stage gradient carried as row 48) then leaves, in place,
+//     L (control block) | Yt = M_xu L^-T (rows 24..47, cols 0..23) | P_k = M_xx - Yt Yt' | yv, p_k
+// i.e. oracle/ip_ref.c: riccati_factor + the backward half of riccati_solve in one pass.
+#pragma once
+// (textually included inside namespace srb { namespace { ... } } by solver_dev.cuh)
+
+// ---- static tile tables (built once per CTA in shared memory)
+//   [0,78)    symmetric G'(Pxx G) tiles (ti >= tj), 3x3, G-column tile coordinates 0..11
+//   [78,126)  cross tiles G' Pxc: (ti 0..11, tc 0..3)
+//   [CH_OFF[b], CH_OFF[b+1])  trailing 2x2 tiles (tr >= tc) of block step b; tr == T_b is the gradient row
+constexpr int NB = 4;                         // pivot block size
+constexpr int NBLK = NS / NB;                 // 6 block steps
+__host__ __device__ constexpr int ch_T(int b) { return (NW - NB * (b + 1)) / 2; }          // tile rows of step b
+__host__ __device__ constexpr int ch_count(int b) { return ch_T(b) * (ch_T(b) + 1) / 2 + ch_T(b); }
+__host__ __device__ constexpr int ch_off(int b) {
+  int o = 126;
+  for (int i = 0; i < b; i++) o += ch_count(i);
+  return o;
+}
+constexpr int TL_COUNT = ch_off(NBLK);
+static_assert(TL_COUNT <= TL_WORDS * 4, "tile table does not fit its shared-memory region");
+
+__device__ void build_tile_tables(unsigned short* tl) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    int n = 0;
+    for (int ti = 0; ti < 12; ti++)
+      for (int tj = 0; tj <= ti; tj++) tl[n++] = (unsigned short)(ti | (tj << 8));
+    for (int ti = 0; ti < 12; ti++)
+      for (int tc = 0; tc < 4; tc++) tl[n++] = (unsigned short)(ti | (tc << 8));
+  } else if (tid <= NBLK) {
+    const int b = tid - 1, T = ch_T(b);
+    int n = ch_off(b);
+    // gradient-row tiles first (cheap), then the triangle, longest rows last so that the strided
+    // assignment i = tid, tid + NT, ... mixes them
+    for (int tc = 0; tc < T; tc++) tl[n++] = (unsigned short)(T | (tc << 8));
+    for (int tr = 0; tr < T; tr++)
+      for (int tc = 0; tc <= tr; tc++) tl[n++] = (unsigned short)(tr | (tc << 8));
+  }
+}
+
+__device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) {  // 16 bytes, L2 only
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+
+// stage lists of knot k -> list buffer (asynchronously, 16-byte chunks)
+__device__ __forceinline__ void prefetch_lists(const Ws& w, int k, double* lb) {
+  const int tid = threadIdx.x, rb = 36 + RK * k;
+  const double* Jk = w.JL + (long long)k * NJ_PAD;
+  const double* Hk = w.HL + (long long)k * NH_PAD;
+  if (tid < NJ_PAD / 2) cp_async16(lb + LB_J + 2 * tid, Jk + 2 * tid);
+  else if (tid < NJ_PAD / 2 + RK / 2) { const int i = tid - NJ_PAD / 2; cp_async16(lb + LB_SIG + 2 * i, w.SIG + rb + 2 * i); }
+  if (tid < NH_PAD / 2) cp_async16(lb + LB_H + 2 * tid, Hk + 2 * tid);
+  else if (tid < NH_PAD / 2 + RK / 2) { const int i = tid - NH_PAD / 2; cp_async16(lb + LB_YH + 2 * i, w.YH + rb + 2 * i); }
+  else if (tid < NH_PAD / 2 + RK / 2 + 6) { const int i = tid - NH_PAD / 2 - RK / 2; cp_async16(lb + LB_GD + 2 * i, w.G + rb + 2 * i); }
+  cp_async_commit();
+}
+
+// G-column tile (0..11: X,c,f) -> tile index in elimination order
+__device__ __forceinline__ int rot_tile(int t) { return t < 8 ? t + 8 : t - 8; }
+
+// Blocked partial Cholesky of the lower-stored 48x48 matrix M (+ gradient row qh), 24 pivots.
+// Every thread computes the 4x4 diagonal factor redundantly (no broadcast needed); false -> a pivot
+// was not positive (wrong inertia).
+__device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const unsigned short* tl) {
+  const int tid = threadIdx.x;
+#pragma unroll 1
+  for (int b = 0; b < NBLK; b++) {
+    const int p0 = NB * b, i0 = p0 + NB;
+    const double* D = M + p0 * LDM + p0;
+    const double d00 = D[0];
+    const double d10 = D[LDM], d11 = D[LDM + 1];
+    const double d20 = D[2 * LDM], d21 = D[2 * LDM + 1], d22 = D[2 * LDM + 2];
+    const double d30 = D[3 * LDM], d31 = D[3 * LDM + 1], d32 = D[3 * LDM + 2], d33 = D[3 * LDM + 3];
+    if (!(d00 > 1e-14)) return false;
+    const double r0 = rsqrt(d00);
+    const double l10 = d10 * r0, l20 = d20 * r0, l30 = d30 * r0;
+    const double e11 = d11 - l10 * l10;
+    if (!(e11 > 1e-14)) return false;
+    const double r1 = rsqrt(e11);
+    const double l21 = (d21 - l20 * l10) * r1, l31 = (d31 - l30 * l10) * r1;
+    const double e22 = d22 - l20 * l20 - l21 * l21;
+    if (!(e22 > 1e-14)) return false;
+    const double r2 = rsqrt(e22);
+    const double l32 = (d32 - l30 * l20 - l31 * l21) * r2;
+    const double e33 = d33 - l30 * l30 - l31 * l31 - l32 * l32;
+    if (!(e33 > 1e-14)) return false;
+    const double r3 = rsqrt(e33);
+    // panel: rows below the block (row 48 = gradient) times L_D^-T
+    const int nrows = NW + 1 - i0;
+    if (tid < nrows) {
+      const int r = i0 + tid;
+      double* a = (r < NW) ? (M + r * LDM + p0) : (qh + p0);
+      const double x0 = a[0] * r0;
+      const double x1 = (a[1] - x0 * l10) * r1;
+      const double x2 = (a[2] - x0 * l20 - x1 * l21) * r2;
+      const double x3 = (a[3] - x0 * l30 - x1 * l31 - x2 * l32) * r3;
+      a[0] = x0; a[1] = x1; a[2] = x2; a[3] = x3;
+    }
+    __syncthreads();
+    if (tid == NT - 1) {  // the block's own factor; the diagonal keeps 1/l_jj (what the solves need)
+      double* Dw = M + p0 * LDM + p0;
+      Dw[0] = r0;
+      Dw[LDM] = l10; Dw[LDM + 1] = r1;
+      Dw[2 * LDM] = l20; Dw[2 * LDM + 1] = l21; Dw[2 * LDM + 2] = r2;
+      Dw[3 * LDM] = l30; Dw[3 * LDM + 1] = l31; Dw[3 * LDM + 2] = l32; Dw[3 * LDM + 3] = r3;
+    }
+    // trailing update, 2x2 tiles of the lower triangle (+ gradient row)
+    const int T = (NW - i0) / 2, cnt = T * (T + 1) / 2 + T;
+    const unsigned short* list = tl + ch_off(b);
+    for (int i = tid; i < cnt; i += NT) {
+      const int e = list[i], tr = e & 255, tc = e >> 8;
+      const int c0 = i0 + 2 * tc;
+      const double* xc0 = M + c0 * LDM + p0;
+      const double* xc1 = xc0 + LDM;
+      const double a0 = xc0[0], a1 = xc0[1], a2 = xc0[2], a3 = xc0[3];
+      const double b0 = xc1[0], b1 = xc1[1], b2 = xc1[2], b3 = xc1[3];
+      if (tr < T) {
+        const int rr = i0 + 2 * tr;
+        const double* xr0 = M + rr * LDM + p0;
+        const double* xr1 = xr0 + LDM;
+        const double u0 = xr0[0], u1 = xr0[1], u2 = xr0[2], u3 = xr0[3];
+        const double v0 = xr1[0], v1 = xr1[1], v2 = xr1[2], v3 = xr1[3];
+        double* o = M + rr * LDM + c0;
+        o[0] -= u0 * a0 + u1 * a1 + u2 * a2 + u3 * a3;
+        o[LDM] -= v0 * a0 + v1 * a1 + v2 * a2 + v3 * a3;
+        o[LDM + 1] -= v0 * b0 + v1 * b1 + v2 * b2 + v3 * b3;
+        if (tr > tc) o[1] -= u0 * b0 + u1 * b1 + u2 * b2 + u3 * b3;
+      } else {
+        const double u0 = qh[p0], u1 = qh[p0 + 1], u2 = qh[p0 + 2], u3 = qh[p0 + 3];
+        qh[c0] -= u0 * a0 + u1 * a1 + u2 * a2 + u3 * a3;
+        qh[c0 + 1] -= u0 * b0 + u1 * b1 + u2 * b2 + u3 * b3;
+      }
+    }
+    __syncthreads();
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------- backward sweep
+// Condenses every stage from the entry lists, factors it and propagates P, p.  false -> not PD.
+__device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, double* smem, double dwreg) {
+  const int N = P.N, K = P.K, tid = threadIdx.x;
+  double* M = smem + SM_M;
+  double* Pn = smem + SM_P;
+  double* Gs = smem + SM_G;
+  double* Ts = smem + SM_T;
+  double* V = smem + SM_V;
+  const unsigned short* tl = reinterpret_cast<const unsigned short*>(smem + SM_TL);
+  const int* tbl = reinterpret_cast<const int*>(smem + SM_TBL);
+  const SolverTables& tb = P.tab;
+  const int* t_g = tbl + tb.o_g;
+  const int* t_qptr = tbl + tb.o_qptr;
+  const int* t_qterms = tbl + tb.o_qterms;
+  const int* t_uabh = tbl + tb.o_uabh;
+  const int* t_uptr = tbl + tb.o_uptr;
+  const int* t_uterms = tbl + tb.o_uterms;
+  // this thread's GEMM tile
+  int g_ti = 0, g_tj = 0;
+  if (tid < 126) { const int e = tl[tid]; g_ti = e & 255; g_tj = e >> 8; }
+  prefetch_lists(w, K - 1, smem + SM_LB0 + ((K - 1) & 1) * LB_SIZE);
+  // terminal block P_K, p_K; G's zero pattern is set once (only its structural entries change)
+  for (int i = tid; i < NS * LDP; i += NT) Pn[i] = 0.0;
+  for (int i = tid; i < 12 * LDG; i += NT) Gs[i] = 0.0;
+  if (tid < NS) V[V_PN + tid] = 0.0;
+  __syncthreads();
+  if (tid < 12) {
+    const int r1 = tid < 6 ? 12 + tid : 24 + (tid - 6), r2 = r1 + 6;
+    const double q = w.x[12 * (N - 1) + tid];
+    const double ref = tid < 6 ? P.pb.q_term_ref[tid] : P.pb.qd_term_ref[tid - 6];
+    Pn[tid * LDP + tid] = 2.0 * P.pb.QN[tid] + w.SIG[r1] + w.SIG[r2] + dwreg;
+    V[V_PN + tid] = 2.0 * P.pb.QN[tid] * (q - ref) + w.YH[r1] + w.YH[r2];
+  }
+  __syncthreads();
+  for (int i = tid; i < 288; i += NT) w.PX[(long long)K * 288 + i] = Pn[(i / 24) * LDP + (i % 24)];
+  if (tid < NS) w.PV[K * 24 + tid] = V[V_PN + tid];
+
+  Prof pf{P.prof, 0};
+  pf.start();
+  for (int k = K - 1; k >= 0; k--) {
+    pf.count(PH_B_STAGES);
+    const double* lb = smem + SM_LB0 + (k & 1) * LB_SIZE;
+    const double* Js = lb + LB_J;
+    const double* Hs = lb + LB_H;
+    const double* SIGs = lb + LB_SIG;
+    const double* YHs = lb + LB_YH;
+    cp_async_wait_all();
+    __syncthreads();  // lists of stage k are in shared memory; P_{k+1}, p_{k+1} complete
+    pf.lap(PH_B_WAIT);
+    if (k > 0) prefetch_lists(w, k - 1, smem + SM_LB0 + ((k - 1) & 1) * LB_SIZE);
+    // P1. dynamics Jacobian G | stage gradient q (elimination order) | defects r
+    if (tid < tb.n_g) {
+      const int e = t_g[tid], t = e >> 10;
+      Gs[(t / 36) * LDG + (t % 36)] = -Js[e & 1023];
+    } else if (tid >= 160 && tid < 208) {
+      const int m = tid - 160;
+      double a0 = 0.0, a1 = 0.0;
+      const int p0 = t_qptr[m], p1 = t_qptr[m + 1];
+      for (int p = p0; p < p1; p += 2) {
+        const int u0 = t_qterms[p], u1 = t_qterms[p + 1];
+        a0 += YHs[u0 >> 10] * Js[u0 & 1023];
+        a1 += YHs[u1 >> 10] * Js[u1 & 1023];
+      }
+      V[V_Q + m] = a0 + a1;
+    } else if (tid >= 224 && tid < 236) {
+      V[V_R + dyn_state(tid - 224)] = -lb[LB_GD + tid - 224];
+    }
+    __syncthreads();
+    pf.lap(PH_B_P1);
+    // P2. T = Pxx G (12 x 36; thread = 1 x 4 strip), t = Pxx r + p_x  |  condensing sums (threads 128..255)
+    double cacc[3] = {0.0, 0.0, 0.0};
+    if (tid < 108) {
+      const int i = tid / 9, j0 = (tid - i * 9) * 4;
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+      for (int l = 0; l < 12; l++) {
+        const double pv = Pn[i * LDP + l];
+        const double* g = Gs + l * LDG + j0;
+        s0 += pv * g[0]; s1 += pv * g[1]; s2 += pv * g[2]; s3 += pv * g[3];
+      }
+      double* t = Ts + i * LDG + j0;
+      t[0] = s0; t[1] = s1; t[2] = s2; t[3] = s3;
+    } else if (tid < 120) {
+      const int i = tid - 108;
+      double s = V[V_PN + i];
+#pragma unroll
+      for (int l = 0; l < 12; l++) s += Pn[i * LDP + l] * V[V_R + l];
+      V[V_T + i] = s;
+    } else if (tid >= 128) {
+      // Hessian entry + sigma-weighted outer products of the inequality rows (+ delta_w) per target
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int t = tid - 128 + 128 * j;
+        if (t < tb.n_u) {
+          const int abh = t_uabh[t], h = abh >> 12;
+          double a0 = h ? Hs[h - 1] : 0.0, a1 = 0.0;
+          const int p0 = t_uptr[t], p1 = t_uptr[t + 1];
+          for (int p = p0; p < p1; p += 2) {
+            const int u0 = t_uterms[p], u1 = t_uterms[p + 1];
+            a0 += SIGs[u0 >> 20] * Js[(u0 >> 10) & 1023] * Js[u0 & 1023];
+            a1 += SIGs[u1 >> 20] * Js[(u1 >> 10) & 1023] * Js[u1 & 1023];
+          }
+          const int ab = abh & 4095, a = ab / NW, b2 = ab - a * NW;
+          double acc = a0 + a1;
+          if (a == b2) acc += (a >= 12 && a < 24) ? (k == K - 1 ? 1.0 : 0.0) : dwreg;  // dummy c+ of the last stage
+          cacc[j] = acc;
+        }
+      }
+    }
+    __syncthreads();
+    pf.lap(PH_B_P2);
+    // P3. M (lower, elimination order) = [G'PxxG, G'Pxc; ., Pcc]; qh = q + G't (+ p_c + Pcx r)
+    if (tid < 126) {
+      double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+      const double* ga = Gs + 3 * g_ti;
+      const bool sym = tid < 78;
+      const double* bb = sym ? (Ts + 3 * g_tj) : (Pn + 12 + 3 * g_tj);
+      const int ldb = sym ? LDG : LDP;
+#pragma unroll
+      for (int l = 0; l < 12; l++) {
+        const double a0 = ga[l * LDG], a1 = ga[l * LDG + 1], a2 = ga[l * LDG + 2];
+        const double b0 = bb[l * ldb], b1 = bb[l * ldb + 1], b2 = bb[l * ldb + 2];
+        acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[0][2] += a0 * b2;
+        acc[1][0] += a1 * b0; acc[1][1] += a1 * b1; acc[1][2] += a1 * b2;
+        acc[2][0] += a2 * b0; acc[2][1] += a2 * b1; acc[2][2] += a2 * b2;
+      }
+      const int ri = 3 * rot_tile(g_ti), rj = sym ? 3 * rot_tile(g_tj) : 12 + 3 * g_tj;
+      if (ri > rj) {
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) M[(ri + a) * LDM + rj + c] = acc[a][c];
+      } else if (ri < rj) {
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int c = 0; c < 3; c++) M[(rj + c) * LDM + ri + a] = acc[a][c];
+      } else {
+#pragma unroll
+        for (int a = 0; a < 3; a++)
+#pragma unroll
+          for (int c = 0; c <= a; c++) M[(ri + a) * LDM + rj + c] = acc[a][c];
+      }
+    } else if (tid >= 128 && tid < 206) {  // Pcc, lower triangle
+      int i = 0, rem = tid - 128;
+      while (rem > i) { rem -= i + 1; i++; }
+      M[(12 + i) * LDM + 12 + rem] = Pn[(12 + i) * LDP + 12 + rem];
+    } else if (tid >= 208) {
+      const int m = tid - 208;  // elimination-order index
+      double s = V[V_Q + m];
+      if (m >= 12 && m < 24) {
+        const int j = m - 12;
+        s += V[V_PN + 12 + j];
+#pragma unroll
+        for (int l = 0; l < 12; l++) s += Pn[(12 + j) * LDP + l] * V[V_R + l];
+      } else {
+        const int g = m < 12 ? m + 24 : m - 24;  // G column of this variable
+#pragma unroll
+        for (int l = 0; l < 12; l++) s += Gs[l * LDG + g] * V[V_T + l];
+      }
+      V[V_QH + m] = s;
+    }
+    __syncthreads();
+    pf.lap(PH_B_P3);
+    // P4. add the condensing sums
+    if (tid >= 128) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        const int t = tid - 128 + 128 * j;
+        if (t < tb.n_u) {
+          const int ab = t_uabh[t] & 4095, a = ab / NW, b2 = ab - a * NW;
+          M[a * LDM + b2] += cacc[j];
+        }
+      }
+    }
+    __syncthreads();
+    pf.lap(PH_B_P4);
+    // P5. eliminate the controls
+    if (!partial_cholesky(M, V + V_QH, tl)) {
+      cp_async_wait_all();  // no prefetch may still be in flight when the sweep is retried
+      __syncthreads();
+      return false;
+    }
+    pf.lap(PH_B_CHOL);
+    // P6. P_k, p_k, yv and what the forward sweep needs
+    for (int idx = tid; idx < NS * NS; idx += NT) {
+      const int i = idx / NS, j = idx - i * NS, a = i < j ? j : i, b2 = i < j ? i : j;
+      const double v = M[(24 + a) * LDM + 24 + b2];
+      Pn[i * LDP + j] = v;
+      if (i < 12) w.PX[(long long)k * 288 + idx] = v;
+    }
+    if (tid < NS) {
+      V[V_PN + tid] = V[V_QH + 24 + tid];
+      w.PV[k * 24 + tid] = V[V_QH + 24 + tid];
+      w.yvf[k * 24 + tid] = V[V_QH + tid];
+    } else if (tid >= 32 && tid < 44) {
+      w.rf[k * 12 + tid - 32] = V[V_R + tid - 32];
+    }
+    double* FY = w.FY + (long long)k * 1152;
+    for (int idx = tid; idx < 1152; idx += NT) {
+      const int i = idx / NS, j = idx - i * NS;
+      FY[idx] = M[i * LDM + j];  // rows 0-23: L (strict lower, 1/l_ii on the diagonal); rows 24-47: Yt
+    }
+    pf.lap(PH_B_P6);
+  }
+  // free initial foot positions: Cholesky of P_0's (c,c) block (12 x 12) by warp 0, 1/l_ii on the diagonal
+  __shared__ int s_ok;
+  __syncthreads();
+  if (tid == 0) s_ok = 1;
+  for (int idx = tid; idx < 144; idx += NT) M[(idx / 12) * LDM + (idx % 12)] = Pn[(12 + idx / 12) * LDP + 12 + (idx % 12)];
+  __syncthreads();
+  if (tid < 32) {
+    const int lane = tid;
+    bool ok = true;
+    for (int j = 0; j < 12 && ok; j++) {
+      double v = 0.0;
+      if (lane >= j && lane < 12) {
+        v = M[lane * LDM + j];
+        for (int l = 0; l < j; l++) v -= M[lane * LDM + l] * M[j * LDM + l];
+      }
+      const double d = __shfl_sync(FULL, v, j);
+      if (!(d > 1e-14)) { ok = false; break; }
+      const double rs = rsqrt(d);
+      if (lane == j) M[j * LDM + j] = rs;
+      else if (lane > j && lane < 12) M[lane * LDM + j] = v * rs;
+      __syncwarp();
+    }
+    if (!ok && lane == 0) s_ok = 0;
+  }
+  __syncthreads();
+  if (!s_ok) return false;
+  for (int idx = tid; idx < 144; idx += NT) w.L0[idx] = M[(idx / 12) * LDM + (idx % 12)];
+  __syncthreads();  // Pn still holds P_0, V_PN p_0 for the forward start
+  return true;
+}
+
+// ---------------------------------------------------------------- forward sweep
+// forward-stage buffer (doubles): FY 48x24 (L | Yt) | J list 388 | yv 24 | r 12 ; G (12x37) is rebuilt per stage
+constexpr int FB_FY = 0, FB_J = 1152, FB_YV = FB_J + NJ_PAD, FB_R = FB_YV + NS, FB_SIZE = FB_R + 12;
+static_assert(FB_SIZE <= NW * LDM && FB_SIZE <= 2 * 12 * LDG + 2 * LB_SIZE, "forward buffers alias the backward regions");
+
+__device__ __forceinline__ void prefetch_factors(const Ws& w, int k, double* fb) {
+  const int tid = threadIdx.x;
+  const double* FY = w.FY + (long long)k * 1152;
+  const double* Jk = w.JL + (long long)k * NJ_PAD;
+  for (int i = tid; i < 576; i += NT) cp_async16(fb + FB_FY + 2 * i, FY + 2 * i);
+  if (tid < NJ_PAD / 2) cp_async16(fb + FB_J + 2 * tid, Jk + 2 * tid);
+  else if (tid < NJ_PAD / 2 + 12) { const int i = tid - NJ_PAD / 2; cp_async16(fb + FB_YV + 2 * i, w.yvf + k * 24 + 2 * i); }
+  else if (tid < NJ_PAD / 2 + 18) { const int i = tid - NJ_PAD / 2 - 12; cp_async16(fb + FB_R + 2 * i, w.rf + k * 12 + 2 * i); }
+  cp_async_commit();
+}
+
+// dx for all stages; equality multipliers of the initial-state rows into YN (dynamics costates: costates())
+__device__ __noinline__ void forward_sweep(const KParams& P, const Ws& w, double* smem, const double* drop) {
+  const int N = P.N, K = P.K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* fbuf[2] = {smem + SM_M, smem + SM_G};
+  double* Pn = smem + SM_P;  // holds P_0 on entry; afterwards the dense G of the current stage
+  double* V = smem + SM_V;
+  double* xi = V + V_XI;
+  double* u = V + V_U;
+  double* rhs = V + V_Q;     // 24
+  const int* t_g = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_g;
+  // initial state step and free initial feet
+  if (tid < 12) xi[tid] = -(w.G[tid] - drop[tid]);
+  __syncthreads();
+  if (warp == 0) {
+    // b = -(p_c + P_cx dX0); solve L0 L0' dc0 = b   (12 x 12; lanes 0..11 own rows, shuffles broadcast)
+    double b = 0.0;
+    if (lane < 12) {
+      b = -V[V_PN + 12 + lane];
+      for (int l = 0; l < 12; l++) b -= Pn[(12 + lane) * LDP + l] * xi[l];
+    }
+    for (int i = 0; i < 12; i++) {  // forward
+      const double bi = __shfl_sync(FULL, b, i) * w.L0[i * 12 + i];
+      if (lane == i) b = bi;
+      else if (lane > i && lane < 12) b -= w.L0[lane * 12 + i] * bi;
+    }
+    for (int i = 11; i >= 0; i--) {  // backward
+      const double bi = __shfl_sync(FULL, b, i) * w.L0[i * 12 + i];
+      if (lane == i) b = bi;
+      else if (lane < i) b -= w.L0[i * 12 + lane] * bi;
+    }
+    if (lane < 12) xi[12 + lane] = b;
+  }
+  __syncthreads();
+  if (tid < 12) {  // multipliers of the initial-state rows: -dV0/dX
+    double v = V[V_PN + tid];
+    for (int l = 0; l < NS; l++) v += Pn[tid * LDP + l] * xi[l];
+    w.YN[tid] = -v;
+    w.DS[tid] = 0.0;
+  }
+  __syncthreads();  // P_0 consumed: every backward region may now be overwritten
+  prefetch_factors(w, 0, fbuf[0]);
+  double* Gs = Pn;
+  for (int i = tid; i < 12 * LDG; i += NT) Gs[i] = 0.0;
+  for (int k = 0; k < K; k++) {
+    const bool last = (k == K - 1);
+    const double* fb = fbuf[k & 1];
+    const double* Ls = fb + FB_FY;             // 24 x 24
+    const double* Ys = fb + FB_FY + NS * NS;   // Yt[i][c]
+    cp_async_wait_all();
+    __syncthreads();  // factors of stage k in shared memory, xi complete, previous G no longer read
+    if (!last) prefetch_factors(w, k + 1, fbuf[(k + 1) & 1]);
+    // rhs = -(Y xi + yv): thread (c, part) sums 6 terms, the 4 parts sit in neighbouring lanes | G | dx
+    if (tid < 96) {
+      const int c = tid >> 2, p = tid & 3;
+      double v = 0.0;
+#pragma unroll
+      for (int ii = 0; ii < 6; ii++) v += Ys[(4 * ii + p) * NS + c] * xi[4 * ii + p];
+      v += __shfl_xor_sync(FULL, v, 1);
+      v += __shfl_xor_sync(FULL, v, 2);
+      if (p == 0) rhs[c] = -(v + fb[FB_YV + c]);
+    } else if (tid < 96 + P.tab.n_g) {
+      const int e = t_g[tid - 96], t = e >> 10;
+      Gs[(t / 36) * LDG + (t % 36)] = -fb[FB_J + (e & 1023)];
+    } else if (tid >= 240 && tid < 252) {  // step of this knot's state / foot variables
+      const int i = tid - 240;
+      w.dx[12 * k + i] = xi[i];
+      w.dx[12 * N + 24 * k + i] = xi[12 + i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      // u = L^-T rhs (diagonal of Ls holds 1/l_ii)
+      double my = lane < NS ? rhs[lane] : 0.0;
+      for (int i = NS - 1; i >= 0; i--) {
+        const double ui = __shfl_sync(FULL, my * Ls[i * NS + i], i);
+        if (lane == i) my = ui;
+        else if (lane < i) my -= Ls[i * NS + lane] * ui;
+      }
+      if (lane < NS) u[lane] = my;
+      if (lane < 12) w.dx[12 * N + 24 * k + 12 + lane] = my;
+      __syncwarp();
+      // next state: lanes (row, half) sum 18 terms each
+      double xn = 0.0;
+      if (lane < NS) {
+        const int i = lane >> 1, hf = lane & 1;
+        double v = 0.0;
+#pragma unroll
+        for (int l = 0; l < 18; l++) {
+          const int j = 18 * hf + l;
+          v += Gs[i * LDG + j] * (j < NS ? xi[j] : u[j - NS]);
+        }
+        v += __shfl_xor_sync(0x00ffffffu, v, 1);
+        xn = v + fb[FB_R + i];
+      }
+      __syncwarp();
+      if (lane < NS && (lane & 1) == 0) xi[lane >> 1] = xn;
+      if (lane >= 12 && lane < NS) xi[lane] = last ? 0.0 : u[lane];
+    }
+  }
+  __syncthreads();
+  if (tid < 12) w.dx[12 * (N - 1) + tid] = xi[tid];
+  __syncthreads();
+}
+
+// costates = multipliers of the dynamics rows of knot k: -(P_{k+1} [dX_{k+1}; dc_{k+1}] + p_{k+1}), all knots in parallel
+__device__ __noinline__ void costates(const KParams& P, const Ws& w) {
+  const int N = P.N, K = P.K;
+  for (int item = threadIdx.x; item < K * 12; item += NT) {
+    const int k = item / 12, i = item - k * 12;
+    const double* PX = w.PX + (long long)(k + 1) * 288 + i * 24;
+    double v = w.PV[(k + 1) * 24 + i];
+#pragma unroll
+    for (int l = 0; l < 12; l++) v += PX[l] * w.dx[12 * (k + 1) + l];
+    if (k + 1 < K) {
+#pragma unroll
+      for (int l = 0; l < 12; l++) v += PX[12 + l] * w.dx[12 * N + 24 * (k + 1) + l];
+    }
+    const int rho = i < 6 ? i : (i < 9 ? i + 3 : i - 3);
+    w.YN[36 + RK * k + rho] = -v;
+    w.DS[36 + RK * k + rho] = 0.0;
+  }
+  __syncthreads();
+}
+

@@ -95,7 +95,11 @@ def test_device_buffers_and_statuses(solver21):
     torch.cuda.synchronize()  # the library launches on its own stream: device-wide wait
     st_h = st.cpu().numpy()
     assert set(np.unique(st_h)).issubset({0, 1, 2, 3, 4})
-    assert (st_h == 0).mean() > 0.5
+    # the random sweep (v_z down to -6 m/s, body rates, lateral velocity) is much harder than the grid sweep:
+    # the CPU restatement converges on ~30 % of it within 400 iterations; the GPU must do what the CPU does
+    c = solve_cpu(21, drops.cpu().numpy(), default_options(max_iter=400))
+    assert (st_h == c["status"]).mean() >= 0.9
+    assert abs(int((st_h == 0).sum()) - int((c["status"] == 0).sum())) <= 3
     assert torch.isfinite(x[st == 0]).all()
 
 
