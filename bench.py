@@ -44,9 +44,30 @@ def iter_bytes(N):
 
 
 def iter_flops(N):
-    """Algorithmic FP64 flops of one iteration of one scenario (Riccati stage count)."""
-    per_stage = 2 * (12 * 12 * 36 + 36 * 36 * 12 + 36 * 12 * 12 + 24 ** 3 // 3 + 24 * 24 * 24 + 24 * 24 * 24) + 2 * 3100
-    return per_stage * (N - 1)
+    """Algorithmic FP64 flops of one iteration of one scenario with ONE Riccati factorisation:
+    per stage 2 x MACs of  T = Pxx G (12.12.36) + lower triangle of G'T (78 tiles x 9 x 12) + G'Pxc (36.12.12)
+    + partial Cholesky of the 48x48 stage matrix, 24 pivots (sum_j (48-j)(49-j)/2) + condensing (576 terms x 2)
+    + forward sweep (24.24 + 300 + 12.36 + 12.24), plus evaluation (3.1k flop / knot) and row passes."""
+    chol = sum((48 - j) * (49 - j) // 2 for j in range(24))
+    macs = 12 * 12 * 36 + 78 * 9 * 12 + 36 * 12 * 12 + chol + 2 * 576 + (24 * 24 + 300 + 12 * 36 + 12 * 24)
+    return (2 * macs + 3100 + 3000) * (N - 1)
+
+
+def scratch_bytes(N, slots):
+    K, nx, MR = N - 1, 36 * N - 24, 36 + 104 * (N - 1)
+    n = 3 * nx + 12 * MR + K * (388 + 192) + K * (1152 + 36) + (K + 1) * 312 + 144 + 128
+    return 8 * slots * ((n + 31) // 32 * 32)
+
+
+def ncu_traffic():
+    """DRAM bytes per launch of k_solve from the committed ncu --set full capture of this workload, or None."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path))
+        except Exception:
+            return None
+    return None
 
 
 class ClockSampler:
@@ -123,7 +144,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = max(cores, min(64, args.batch))
+    sample = args.cpu_sample or args.batch  # default: the whole sweep (about 10 s on 16 host threads)
     drops = workload(1, 0, args.batch)
     sub = drops[:: max(1, len(drops) // sample)][:sample]
     for _ in range(min(args.warmup, 1)):
@@ -269,6 +290,9 @@ def main():
         kernel_ms = ms / args.steps  # one launch per step; the all-gather (N>1) rides on the same stream
         local_iters = float(its.sum())
         achieved = iter_bytes(N) * local_iters / (kernel_ms * 1e-3) / 1e9
+        fp64_peak = solver.fp64_peak_tflops()
+        fp64_ach = iter_flops(N) * local_iters / (kernel_ms * 1e-3) / 1e12
+        tr = ncu_traffic()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -276,8 +300,8 @@ def main():
             "config": {"workload": "SRB landing sweep, %d grid drop conditions per GPU (height x pitch x roll x v_x, v_z=-3), N=%d knots"
                        % (B, N), "knots": N, "batch_per_gpu": B, "global_batch": B * world,
                        "parallelism": "scenario-sharded x%d, one all-gather of results" % world,
-                       "l2": "per-warp solver scratch (%.2f GB) exceeds the 126 MB L2; no flush needed"
-                       % (8e-9 * 148 * 7 * (3 * nx + 12 * (36 + 104 * (N - 1)) + (N - 1) * (385 + 189 + 1620) + N * 312)),
+                       "l2": "per-scenario solver scratch of the 296 resident CTAs (%.2f GB) exceeds the 126 MB L2 and "
+                             "every step rewrites all of it; no flush needed" % (1e-9 * scratch_bytes(N, 296)),
                        "options": "tol 1e-4, constr_viol_tol 1e-3, max_iter 3000 (generate_landingCtrller_IPOPT.m:232-236)"},
             "converged_per_step": conv_per_step, "scenarios_per_step": B * world,
             "kkt_iters_per_s": iters_per_step * args.steps / (ms * 1e-3),
@@ -286,15 +310,21 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 12 * 8,
                     "d2h_bytes_per_step": B * (nx + 2) * 8 + B * 8, "ms_per_step": ms_e2e / args.steps},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak,
+                         "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
+                         "peak_source": peak_src,
                          "kernel": "k_solve", "units_per_launch": local_iters,
-                         "bytes_per_unit": iter_bytes(N),
-                         "fp64_tflops_algorithmic": iter_flops(N) * local_iters / (kernel_ms * 1e-3) / 1e12,
-                         "note": "one launch per step = all interior-point iterations of the batch; unit = one KKT iteration of one scenario"},
+                         "bytes_per_unit": iter_bytes(N), "flops_per_unit": iter_flops(N),
+                         "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                                  "frac": fp64_ach / fp64_peak if fp64_peak else None,
+                                  "peak_source": "measured in this run (landing_fp64_peak: DFMA micro-kernel, CUDA events)"},
+                         "note": "one launch per step = all interior-point iterations of the batch; unit = one KKT "
+                                 "iteration of one scenario; the kernel is FP64-latency bound (DESIGN.md 2.3), the hbm "
+                                 "line uses the algorithmic bytes of SURVEY 8d-ii, the fp64 line the algorithmic flops"},
         }
         # CPU baseline on the host cores (bounded sample of the same workload)
         cores = os.cpu_count() or 1
-        ns = args.cpu_sample or max(cores, 32)
+        ns = args.cpu_sample or B  # default: the whole sweep of rank 0 (about 10 s on 16 host threads)
         sub = drops_h[:: max(1, B // ns)][:ns]
         r, dt = cpu_run(N, sub, cores)
         line["cpu_baseline"] = {

@@ -135,6 +135,10 @@ typedef struct landing_solve_io {
 int landing_solve_batch(landing_ctx *ctx, long long B, int memspace, const landing_problem *pb,
                         const landing_options *opt, const landing_solve_io *io);
 
+/* Measured FP64 FMA throughput of the context's device in TFLOP/s (a DFMA micro-kernel timed with CUDA
+ * events): the roofline denominator of the interior-point kernel, which is FP64-pipe bound by design. */
+int landing_fp64_peak(landing_ctx *ctx, double *tflops);
+
 /* number of kernel launches issued by this context so far (bench accounting) */
 long long landing_launch_count(const landing_ctx *ctx);
 /* CUDA stream (cudaStream_t) the context launches on; for event timing by the caller */

@@ -79,6 +79,7 @@ def load_library(path=LIB_PATH):
                                         ctypes.POINTER(SolveIO)]
     lib.landing_launch_count.restype = ctypes.c_longlong
     lib.landing_launch_count.argtypes = [ctypes.c_void_p]
+    lib.landing_fp64_peak.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
     lib.landing_stream.restype = ctypes.c_void_p
     lib.landing_stream.argtypes = [ctypes.c_void_p]
     lib.landing_dims_for.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
@@ -147,6 +148,12 @@ class LandingSolver:
     @property
     def launches(self):
         return self.lib.landing_launch_count(self.ctx)
+
+    def fp64_peak_tflops(self):
+        """Measured FP64 FMA throughput of this device (TFLOP/s)."""
+        v = ctypes.c_double()
+        self._check(self.lib.landing_fp64_peak(self.ctx, ctypes.byref(v)), "landing_fp64_peak")
+        return v.value
 
     @property
     def stream_ptr(self):

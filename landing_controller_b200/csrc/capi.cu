@@ -121,6 +121,16 @@ const long long* landing_sparsity(const landing_ctx* c, int which) {
 }
 
 long long landing_launch_count(const landing_ctx* c) { return c ? c->launches : 0; }
+
+int landing_fp64_peak(landing_ctx* c, double* tflops) {
+  if (!c || !tflops) return fail(LANDING_ERR_ARG, "landing_fp64_peak: null argument");
+  CU(cudaSetDevice(c->device));
+  std::string err;
+  const int rc = fp64_peak_run(c->stream, tflops, &err);
+  if (rc != LANDING_OK) return fail(rc, err);
+  c->launches += 4;
+  return LANDING_OK;
+}
 void* landing_stream(const landing_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 void landing_problem_default(landing_problem* pb) {

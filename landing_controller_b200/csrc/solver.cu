@@ -162,14 +162,6 @@ HostTables build_tables_host() {
 
 }  // namespace
 
-void solver_free(SolverWorkspace& ws) {
-  if (ws.scratch) cudaFree(ws.scratch);
-  if (ws.io) cudaFree(ws.io);
-  if (ws.counter) cudaFree(ws.counter);
-  if (ws.tab.dev) cudaFree(ws.tab.dev);
-  ws = SolverWorkspace{};
-}
-
 #define CUS(call)                                                            \
   do {                                                                       \
     cudaError_t e_ = (call);                                                 \
@@ -178,6 +170,61 @@ void solver_free(SolverWorkspace& ws) {
       return LANDING_ERR_CUDA;                                               \
     }                                                                        \
   } while (0)
+
+// ---------------------------------------------------------------- FP64 FMA peak (measured, for the roofline)
+namespace {
+__global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
+  // 16 independent DFMA chains per thread; 8 warps x 8 CTAs per SM keep the FP64 pipe full
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; i++) a[i] = 1.0 + 1e-9 * (threadIdx.x + i);
+  const double m = 1.0000001, c = 1e-9;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = fma(a[i], m, c);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) s += a[i];
+  if (s == 123.456) out[0] = s;  // never true; keeps the chains alive
+}
+}  // namespace
+
+int fp64_peak_run(cudaStream_t st, double* tflops, std::string* err) {
+  int dev = 0, n_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  double* d_out = nullptr;
+  CUS(cudaMalloc(&d_out, 8));
+  cudaEvent_t e0, e1;
+  CUS(cudaEventCreate(&e0));
+  CUS(cudaEventCreate(&e1));
+  const int grid = n_sm * 8, iters = 20000;
+  double best = 0;
+  for (int rep = 0; rep < 4; rep++) {
+    CUS(cudaEventRecord(e0, st));
+    k_fp64_peak<<<grid, 256, 0, st>>>(d_out, iters);
+    CUS(cudaEventRecord(e1, st));
+    CUS(cudaEventSynchronize(e1));
+    float ms = 0;
+    CUS(cudaEventElapsedTime(&ms, e0, e1));
+    const double tf = 2.0 * 16.0 * iters * 256.0 * grid / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d_out);
+  *tflops = best;
+  return LANDING_OK;
+}
+
+void solver_free(SolverWorkspace& ws) {
+  if (ws.scratch) cudaFree(ws.scratch);
+  if (ws.io) cudaFree(ws.io);
+  if (ws.counter) cudaFree(ws.counter);
+  if (ws.tab.dev) cudaFree(ws.tab.dev);
+  ws = SolverWorkspace{};
+}
 
 int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memspace,
                const landing_problem& pb, const landing_options& opt, const landing_solve_io& io,
@@ -275,10 +322,11 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
     for (int i = 0; i < PH_NBACK; i++)
       fprintf(stderr, "[landing prof]   %-11s %6.1f%%  %9.0f cycles per iteration\n", names[i], 100.0 * (double)h[i] / tot,
               (double)h[i] / (double)std::max(1ull, h[PH_NITER]));
-    static const char* bn[] = {"wait+sync", "P1 G,q", "P2 T=PG", "P3 tiles", "P4 targets", "P5 chol", "P6 store"};
-    for (int i = 0; i < 7; i++)
-      fprintf(stderr, "[landing prof]   backward %-10s %8.0f cycles per stage\n", bn[i],
-              (double)h[PH_B_WAIT + i] / (double)std::max(1ull, h[PH_B_STAGES]));
+    static const char* bn[] = {"wait+sync", "P1 G,q", "P2 T=PG", "P3 tiles", "P4 targets", "(unused)", "P6 store", "", "P5 chol diag+panel", "P5 chol trailing"};
+    for (int i = 0; i < 10; i++)
+      if (bn[i][0] && i != 5)
+        fprintf(stderr, "[landing prof]   backward %-18s %8.0f cycles per stage\n", bn[i],
+                (double)h[PH_B_WAIT + i] / (double)std::max(1ull, h[PH_B_STAGES]));
   }
   if (memspace == LANDING_HOST) {
     CUS(cudaMemcpyAsync(io.x_star, P.x_star, sizeof(double) * nx * B, cudaMemcpyDeviceToHost, st));

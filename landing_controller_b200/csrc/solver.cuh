@@ -34,6 +34,9 @@ struct SolverWorkspace {
 
 void solver_free(SolverWorkspace& ws);
 
+// FP64 FMA throughput of the device (roofline denominator of the interior-point kernel), TFLOP/s
+int fp64_peak_run(cudaStream_t st, double* tflops, std::string* err);
+
 int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memspace,
                const landing_problem& pb, const landing_options& opt, const landing_solve_io& io,
                cudaStream_t st, int* launches, std::string* err);

@@ -65,7 +65,7 @@ struct KParams {
 
 // phase ids of the optional cycle profile
 enum { PH_EVAL = 0, PH_ERR, PH_DUAL, PH_MU, PH_BACK, PH_FWD, PH_ROWS, PH_LS, PH_ACCEPT, PH_NBACK, PH_NITER,
-       PH_B_WAIT, PH_B_P1, PH_B_P2, PH_B_P3, PH_B_P4, PH_B_CHOL, PH_B_P6, PH_B_STAGES, PH_COUNT };
+       PH_B_WAIT, PH_B_P1, PH_B_P2, PH_B_P3, PH_B_P4, PH_B_CHOL, PH_B_P6, PH_B_STAGES, PH_C_DIAG, PH_C_TRAIL, PH_COUNT };
 struct Prof {
   unsigned long long* c;
   long long t;

@@ -10,21 +10,29 @@
 #pragma once
 // (textually included inside namespace srb { namespace { ... } } by solver_dev.cuh)
 
-// ---- static tile tables (built once per CTA in shared memory)
+// ---- static work tables (built once per CTA in shared memory)
 //   [0,78)    symmetric G'(Pxx G) tiles (ti >= tj), 3x3, G-column tile coordinates 0..11
 //   [78,126)  cross tiles G' Pxc: (ti 0..11, tc 0..3)
-//   [CH_OFF[b], CH_OFF[b+1])  trailing 2x2 tiles (tr >= tc) of block step b; tr == T_b is the gradient row
-constexpr int NB = 4;                         // pivot block size
-constexpr int NBLK = NS / NB;                 // 6 block steps
-__host__ __device__ constexpr int ch_T(int b) { return (NW - NB * (b + 1)) / 2; }          // tile rows of step b
-__host__ __device__ constexpr int ch_count(int b) { return ch_T(b) * (ch_T(b) + 1) / 2 + ch_T(b); }
+//   [ch_off(b), ch_off(b+1))  trailing items of block step b: (row r | column group g << 8), r in [i0, 48] (48 = the
+//             gradient row), columns i0 + 4g .. i0 + 4g + 3, only groups that reach the lower triangle (i0 + 4g <= r);
+//             ordered group by group so that a warp reads ONE column group (broadcast) and consecutive rows
+//             (row stride 49 doubles: conflict-free)
+constexpr int NB = 8;                         // pivot block size
+constexpr int NBLK = NS / NB;                 // 3 block steps
+__host__ __device__ constexpr int ch_count(int b) {
+  const int i0 = NB * (b + 1), ng = (NW - i0) / 4;
+  int n = 0;
+  for (int g = 0; g < ng; g++) n += (NW + 1) - (i0 + 4 * g);
+  return n;
+}
 __host__ __device__ constexpr int ch_off(int b) {
   int o = 126;
   for (int i = 0; i < b; i++) o += ch_count(i);
   return o;
 }
 constexpr int TL_COUNT = ch_off(NBLK);
-static_assert(TL_COUNT <= TL_WORDS * 4, "tile table does not fit its shared-memory region");
+static_assert(TL_COUNT <= TL_WORDS * 4, "work table does not fit its shared-memory region");
+static_assert(ch_count(0) <= NT, "one trailing item per thread");
 
 __device__ void build_tile_tables(unsigned short* tl) {
   const int tid = threadIdx.x;
@@ -35,13 +43,10 @@ __device__ void build_tile_tables(unsigned short* tl) {
     for (int ti = 0; ti < 12; ti++)
       for (int tc = 0; tc < 4; tc++) tl[n++] = (unsigned short)(ti | (tc << 8));
   } else if (tid <= NBLK) {
-    const int b = tid - 1, T = ch_T(b);
+    const int b = tid - 1, i0 = NB * (b + 1), ng = (NW - i0) / 4;
     int n = ch_off(b);
-    // gradient-row tiles first (cheap), then the triangle, longest rows last so that the strided
-    // assignment i = tid, tid + NT, ... mixes them
-    for (int tc = 0; tc < T; tc++) tl[n++] = (unsigned short)(T | (tc << 8));
-    for (int tr = 0; tr < T; tr++)
-      for (int tc = 0; tc <= tr; tc++) tl[n++] = (unsigned short)(tr | (tc << 8));
+    for (int g = 0; g < ng; g++)
+      for (int r = i0 + 4 * g; r <= NW; r++) tl[n++] = (unsigned short)(r | (g << 8));
   }
 }
 
@@ -69,79 +74,80 @@ __device__ __forceinline__ void prefetch_lists(const Ws& w, int k, double* lb) {
 __device__ __forceinline__ int rot_tile(int t) { return t < 8 ? t + 8 : t - 8; }
 
 // Blocked partial Cholesky of the lower-stored 48x48 matrix M (+ gradient row qh), 24 pivots.
-// Every thread computes the 4x4 diagonal factor redundantly (no broadcast needed); false -> a pivot
-// was not positive (wrong inertia).
-__device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const unsigned short* tl) {
+// Per block step: (1) warps 0-1 factor the NB x NB diagonal block in registers (right-looking, so every pivot
+// hangs on a chain of ~6 FP64 operations; the FP64 pipe is half rate, so the other warps do NOT repeat it) and,
+// fused with it column by column, solve their panel row (rows below the block; row 48 = gradient) against L_D^T;
+// (2) all threads update the trailing lower triangle, one (row, 4-column group) item each.
+// false -> a pivot was not positive (wrong inertia).
+__device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const unsigned short* tl, int* s_pd, Prof& pf) {
   const int tid = threadIdx.x;
 #pragma unroll 1
   for (int b = 0; b < NBLK; b++) {
     const int p0 = NB * b, i0 = p0 + NB;
-    const double* D = M + p0 * LDM + p0;
-    const double d00 = D[0];
-    const double d10 = D[LDM], d11 = D[LDM + 1];
-    const double d20 = D[2 * LDM], d21 = D[2 * LDM + 1], d22 = D[2 * LDM + 2];
-    const double d30 = D[3 * LDM], d31 = D[3 * LDM + 1], d32 = D[3 * LDM + 2], d33 = D[3 * LDM + 3];
-    if (!(d00 > 1e-14)) return false;
-    const double r0 = rsqrt(d00);
-    const double l10 = d10 * r0, l20 = d20 * r0, l30 = d30 * r0;
-    const double e11 = d11 - l10 * l10;
-    if (!(e11 > 1e-14)) return false;
-    const double r1 = rsqrt(e11);
-    const double l21 = (d21 - l20 * l10) * r1, l31 = (d31 - l30 * l10) * r1;
-    const double e22 = d22 - l20 * l20 - l21 * l21;
-    if (!(e22 > 1e-14)) return false;
-    const double r2 = rsqrt(e22);
-    const double l32 = (d32 - l30 * l20 - l31 * l21) * r2;
-    const double e33 = d33 - l30 * l30 - l31 * l31 - l32 * l32;
-    if (!(e33 > 1e-14)) return false;
-    const double r3 = rsqrt(e33);
-    // panel: rows below the block (row 48 = gradient) times L_D^-T
-    const int nrows = NW + 1 - i0;
-    if (tid < nrows) {
-      const int r = i0 + tid;
-      double* a = (r < NW) ? (M + r * LDM + p0) : (qh + p0);
-      const double x0 = a[0] * r0;
-      const double x1 = (a[1] - x0 * l10) * r1;
-      const double x2 = (a[2] - x0 * l20 - x1 * l21) * r2;
-      const double x3 = (a[3] - x0 * l30 - x1 * l31 - x2 * l32) * r3;
-      a[0] = x0; a[1] = x1; a[2] = x2; a[3] = x3;
-    }
-    __syncthreads();
-    if (tid == NT - 1) {  // the block's own factor; the diagonal keeps 1/l_jj (what the solves need)
-      double* Dw = M + p0 * LDM + p0;
-      Dw[0] = r0;
-      Dw[LDM] = l10; Dw[LDM + 1] = r1;
-      Dw[2 * LDM] = l20; Dw[2 * LDM + 1] = l21; Dw[2 * LDM + 2] = r2;
-      Dw[3 * LDM] = l30; Dw[3 * LDM + 1] = l31; Dw[3 * LDM + 2] = l32; Dw[3 * LDM + 3] = r3;
-    }
-    // trailing update, 2x2 tiles of the lower triangle (+ gradient row)
-    const int T = (NW - i0) / 2, cnt = T * (T + 1) / 2 + T;
-    const unsigned short* list = tl + ch_off(b);
-    for (int i = tid; i < cnt; i += NT) {
-      const int e = list[i], tr = e & 255, tc = e >> 8;
-      const int c0 = i0 + 2 * tc;
-      const double* xc0 = M + c0 * LDM + p0;
-      const double* xc1 = xc0 + LDM;
-      const double a0 = xc0[0], a1 = xc0[1], a2 = xc0[2], a3 = xc0[3];
-      const double b0 = xc1[0], b1 = xc1[1], b2 = xc1[2], b3 = xc1[3];
-      if (tr < T) {
-        const int rr = i0 + 2 * tr;
-        const double* xr0 = M + rr * LDM + p0;
-        const double* xr1 = xr0 + LDM;
-        const double u0 = xr0[0], u1 = xr0[1], u2 = xr0[2], u3 = xr0[3];
-        const double v0 = xr1[0], v1 = xr1[1], v2 = xr1[2], v3 = xr1[3];
-        double* o = M + rr * LDM + c0;
-        o[0] -= u0 * a0 + u1 * a1 + u2 * a2 + u3 * a3;
-        o[LDM] -= v0 * a0 + v1 * a1 + v2 * a2 + v3 * a3;
-        o[LDM + 1] -= v0 * b0 + v1 * b1 + v2 * b2 + v3 * b3;
-        if (tr > tc) o[1] -= u0 * b0 + u1 * b1 + u2 * b2 + u3 * b3;
-      } else {
-        const double u0 = qh[p0], u1 = qh[p0 + 1], u2 = qh[p0 + 2], u3 = qh[p0 + 3];
-        qh[c0] -= u0 * a0 + u1 * a1 + u2 * a2 + u3 * a3;
-        qh[c0 + 1] -= u0 * b0 + u1 * b1 + u2 * b2 + u3 * b3;
+    double L[NB][NB];
+    if (tid < 64) {
+      double x[NB];
+#pragma unroll
+      for (int i = 0; i < NB; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) L[i][j] = M[(p0 + i) * LDM + p0 + j];
+      const bool panel = tid < NW + 1 - i0;
+      double* arow = (i0 + tid < NW) ? (M + (i0 + tid) * LDM + p0) : (qh + p0);
+#pragma unroll
+      for (int j = 0; j < NB; j++) x[j] = panel ? arow[j] : 0.0;
+      bool pd = true;
+#pragma unroll
+      for (int j = 0; j < NB; j++) {
+        const double e = L[j][j];
+        pd = pd && (e > 1e-14);
+        const double r = rsqrt(e);
+        L[j][j] = r;  // the diagonal keeps 1/l_jj (what the solves need)
+        const double xj = x[j] * r;
+        x[j] = xj;
+#pragma unroll
+        for (int i = j + 1; i < NB; i++) L[i][j] *= r;
+#pragma unroll
+        for (int i = j + 1; i < NB; i++) {
+#pragma unroll
+          for (int l = j + 1; l <= i; l++) L[i][l] -= L[i][j] * L[l][j];
+          x[i] -= xj * L[i][j];
+        }
       }
+      if (panel) {
+#pragma unroll
+        for (int j = 0; j < NB; j++) arow[j] = x[j];
+      }
+      if (tid == 63) *s_pd = pd ? 1 : 0;
     }
     __syncthreads();
+    pf.lap(PH_C_DIAG);
+    if (!*s_pd) return false;
+    if (tid == 63) {  // the block's own factor (nobody reads the diagonal block during the trailing update)
+#pragma unroll
+      for (int i = 0; i < NB; i++)
+#pragma unroll
+        for (int j = 0; j <= i; j++) M[(p0 + i) * LDM + p0 + j] = L[i][j];
+    }
+    // trailing update: M[r][c] -= panel_r . panel_c for c in the item's column group, c <= r
+    const int cnt = ch_count(b);
+    if (tid < cnt) {
+      const int e = tl[ch_off(b) + tid], r = e & 255, c0 = i0 + 4 * (e >> 8);
+      const double* xr = (r < NW) ? (M + r * LDM + p0) : (qh + p0);
+      const double* xc = M + c0 * LDM + p0;
+      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        const double u = xr[q];
+        s0 += u * xc[q]; s1 += u * xc[LDM + q]; s2 += u * xc[2 * LDM + q]; s3 += u * xc[3 * LDM + q];
+      }
+      double* o = (r < NW) ? (M + r * LDM + c0) : (qh + c0);
+      o[0] -= s0;
+      if (c0 + 1 <= r) o[1] -= s1;
+      if (c0 + 2 <= r) o[2] -= s2;
+      if (c0 + 3 <= r) o[3] -= s3;
+    }
+    __syncthreads();
+    pf.lap(PH_C_TRAIL);
   }
   return true;
 }
@@ -158,6 +164,7 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
   const unsigned short* tl = reinterpret_cast<const unsigned short*>(smem + SM_TL);
   const int* tbl = reinterpret_cast<const int*>(smem + SM_TBL);
   const SolverTables& tb = P.tab;
+  __shared__ int s_ok;
   const int* t_g = tbl + tb.o_g;
   const int* t_qptr = tbl + tb.o_qptr;
   const int* t_qterms = tbl + tb.o_qterms;
@@ -325,12 +332,11 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
     __syncthreads();
     pf.lap(PH_B_P4);
     // P5. eliminate the controls
-    if (!partial_cholesky(M, V + V_QH, tl)) {
+    if (!partial_cholesky(M, V + V_QH, tl, &s_ok, pf)) {
       cp_async_wait_all();  // no prefetch may still be in flight when the sweep is retried
       __syncthreads();
       return false;
     }
-    pf.lap(PH_B_CHOL);
     // P6. P_k, p_k, yv and what the forward sweep needs
     for (int idx = tid; idx < NS * NS; idx += NT) {
       const int i = idx / NS, j = idx - i * NS, a = i < j ? j : i, b2 = i < j ? i : j;
@@ -353,7 +359,6 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
     pf.lap(PH_B_P6);
   }
   // free initial foot positions: Cholesky of P_0's (c,c) block (12 x 12) by warp 0, 1/l_ii on the diagonal
-  __shared__ int s_ok;
   __syncthreads();
   if (tid == 0) s_ok = 1;
   for (int idx = tid; idx < 144; idx += NT) M[(idx / 12) * LDM + (idx % 12)] = Pn[(12 + idx / 12) * LDP + 12 + (idx % 12)];
