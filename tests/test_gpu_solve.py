@@ -38,6 +38,20 @@ def test_iterates_match_cpu_restatement(solver21, iters):
     assert np.allclose(r["f"], c["f"], rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.parametrize("N", [30, 50])
+def test_iterates_match_cpu_restatement_other_knot_counts(N):
+    """BASELINE configs 1 (N = 30) and 2 (N = 50): same algorithm, iterate for iterate."""
+    drops = lc.grid_sweep(1024)[::171][:6]
+    s = lc.LandingSolver(N=N)
+    s.options.max_iter = 4
+    r = s.solve(drops)
+    c = solve_cpu(N, drops, default_options(max_iter=4))
+    s.close()
+    assert np.array_equal(r["iters"], c["iters"])
+    assert np.max(np.abs(r["x"] - c["x"])) < 1e-9
+    assert np.allclose(r["f"], c["f"], rtol=1e-9, atol=1e-12)
+
+
 def _kkt_certificate(o, pb, drop, x, lam):
     """Feasibility / stationarity of (x, lam) according to the ORACLE's functions."""
     p, _ = o.build_p_x0(pb, drop[:6], drop[6:])
