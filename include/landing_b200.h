@@ -114,7 +114,13 @@ typedef struct landing_options {
   double bound_frac;         /* 0.5 */
   double bound_relax_factor; /* 1e-6 */
   int max_soc;               /* 4 */
-  int reserved[7];
+  /* Jamming watchdog (this library's substitute for IPOPT's restoration phase, which the restatement does not
+   * have): when the accepted primal step length stays below jam_alpha for jam_iters consecutive iterations the
+   * iterate is re-centred exactly as after a failed line search (slacks pushed back inside their bounds,
+   * multipliers reset, mu = mu_init).  jam_iters = 0 switches it off. */
+  int jam_iters;             /* 5 */
+  double jam_alpha;          /* 0.02 */
+  int reserved[6];
 } landing_options;
 
 void landing_options_default(landing_options *opt);

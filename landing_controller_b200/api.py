@@ -49,7 +49,8 @@ class Options(ctypes.Structure):
                 ("dual_inf_tol", ctypes.c_double), ("compl_inf_tol", ctypes.c_double),
                 ("mu_init", ctypes.c_double), ("bound_push", ctypes.c_double),
                 ("bound_frac", ctypes.c_double), ("bound_relax_factor", ctypes.c_double),
-                ("max_soc", ctypes.c_int), ("reserved", ctypes.c_int * 7)]
+                ("max_soc", ctypes.c_int), ("jam_iters", ctypes.c_int), ("jam_alpha", ctypes.c_double),
+                ("reserved", ctypes.c_int * 6)]
 
 
 class SolveIO(ctypes.Structure):
@@ -79,7 +80,8 @@ def load_library(path=LIB_PATH):
                                         ctypes.POINTER(SolveIO)]
     lib.landing_launch_count.restype = ctypes.c_longlong
     lib.landing_launch_count.argtypes = [ctypes.c_void_p]
-    lib.landing_fp64_peak.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
+    if hasattr(lib, "landing_fp64_peak"):
+        lib.landing_fp64_peak.argtypes = [ctypes.c_void_p, ctypes.POINTER(ctypes.c_double)]
     lib.landing_stream.restype = ctypes.c_void_p
     lib.landing_stream.argtypes = [ctypes.c_void_p]
     lib.landing_dims_for.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]

@@ -173,6 +173,8 @@ void landing_options_default(landing_options* o) {
   o->bound_frac = 0.5;
   o->bound_relax_factor = 1e-6;
   o->max_soc = 4;
+  o->jam_iters = 5;
+  o->jam_alpha = 0.02;
 }
 
 int landing_eval_batch(landing_ctx* c, long long B, int memspace, int layout, const landing_eval_io* io) {

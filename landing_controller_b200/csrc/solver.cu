@@ -296,7 +296,11 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
     P.drops = io.drops; P.x0 = io.x0; P.x_star = io.x_star; P.f_star = io.f_star; P.lam_g = io.lam_g;
     P.viol = io.viol; P.status = io.status; P.iters = io.iters;
   }
+#ifdef SRB_PROF
   static const bool want_prof = getenv("LANDING_PROF") != nullptr;
+#else
+  static const bool want_prof = false;
+#endif
   unsigned long long* d_prof = nullptr;
   if (want_prof) {
     CUS(cudaMalloc(&d_prof, sizeof(unsigned long long) * PH_COUNT));

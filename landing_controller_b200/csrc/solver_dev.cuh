@@ -69,11 +69,17 @@ enum { PH_EVAL = 0, PH_ERR, PH_DUAL, PH_MU, PH_BACK, PH_FWD, PH_ROWS, PH_LS, PH_
 struct Prof {
   unsigned long long* c;
   long long t;
+#ifndef SRB_PROF  // build with make EXTRA=-DSRB_PROF for the per-phase cycle profile (costs ~4 %)
+  __device__ __forceinline__ void start() {}
+  __device__ __forceinline__ void lap(int) {}
+  __device__ __forceinline__ void count(int) {}
+#else
   __device__ __forceinline__ void start() { if (c && threadIdx.x == 0) t = clock64(); }
   __device__ __forceinline__ void lap(int ph) {
     if (c && threadIdx.x == 0) { const long long n = clock64(); atomicAdd(c + ph, (unsigned long long)(n - t)); t = n; }
   }
   __device__ __forceinline__ void count(int ph) { if (c && threadIdx.x == 0) atomicAdd(c + ph, 1ull); }
+#endif
 };
 
 struct Ws {  // pointers into one CTA's scratch slot
@@ -634,7 +640,7 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long
   double mu = opt.mu_init;
   init_slacks(P, w, tab, mu);
 
-  int nfilt = 0, restarts = 0, status = LANDING_ST_MAX_ITER, it = 0;
+  int nfilt = 0, restarts = 0, status = LANDING_ST_MAX_ITER, it = 0, tiny = 0;
   double theta0 = -1.0, dw_last = 0.0, viol = 0.0;
   Prof pf{P.prof, 0};
   for (it = 0; it <= opt.max_iter; it++) {
@@ -739,7 +745,12 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long
       ls++;
     }
     pf.lap(PH_LS);
+    // watchdog against jamming at the fraction-to-the-boundary rule: a run of tiny accepted steps is treated like a
+    // failed line search (ip_ref.c)
+    if (accepted) tiny = (alpha < opt.jam_alpha) ? tiny + 1 : 0;
+    if (accepted && opt.jam_iters > 0 && tiny >= opt.jam_iters && restarts < 20) accepted = false;
     if (!accepted) {
+      tiny = 0;
       if (restarts < 20) {  // re-centre: slacks back inside their bounds, multipliers reset, mu = mu_init
         restarts++;
         mu = opt.mu_init;

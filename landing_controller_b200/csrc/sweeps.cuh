@@ -13,18 +13,31 @@
 // ---- static work tables (built once per CTA in shared memory)
 //   [0,78)    symmetric G'(Pxx G) tiles (ti >= tj), 3x3, G-column tile coordinates 0..11
 //   [78,126)  cross tiles G' Pxc: (ti 0..11, tc 0..3)
-//   [ch_off(b), ch_off(b+1))  trailing items of block step b: (row r | column group g << 8), r in [i0, 48] (48 = the
-//             gradient row), columns i0 + 4g .. i0 + 4g + 3, only groups that reach the lower triangle (i0 + 4g <= r);
-//             ordered group by group so that a warp reads ONE column group (broadcast) and consecutive rows
-//             (row stride 49 doubles: conflict-free)
-constexpr int NB = 8;                         // pivot block size
-constexpr int NBLK = NS / NB;                 // 3 block steps
+//   [ch_off(b), ch_off(b+1))  trailing work items of block step b (see partial_cholesky)
+#ifndef SRB_TRAIL
+#define SRB_TRAIL 1
+#endif
+#ifndef SRB_NB
+#define SRB_NB 4
+#endif
+constexpr int NB = SRB_NB;                    // pivot block size
+constexpr int NBLK = NS / NB;                 // block steps
+#if SRB_TRAIL == 0
+// 2x2 tiles (tr >= tc) of the trailing lower triangle; tr == T is the gradient row
+__host__ __device__ constexpr int ch_count(int b) {
+  const int T = (NW - NB * (b + 1)) / 2;
+  return T * (T + 1) / 2 + T;
+}
+#else
+// (row r | column group g << 8): r in [i0, 48] (48 = gradient row), columns i0 + 4g .. i0 + 4g + 3, i0 + 4g <= r;
+// ordered group by group: a warp reads ONE column group (broadcast) and consecutive rows (conflict-free)
 __host__ __device__ constexpr int ch_count(int b) {
   const int i0 = NB * (b + 1), ng = (NW - i0) / 4;
   int n = 0;
   for (int g = 0; g < ng; g++) n += (NW + 1) - (i0 + 4 * g);
   return n;
 }
+#endif
 __host__ __device__ constexpr int ch_off(int b) {
   int o = 126;
   for (int i = 0; i < b; i++) o += ch_count(i);
@@ -32,7 +45,6 @@ __host__ __device__ constexpr int ch_off(int b) {
 }
 constexpr int TL_COUNT = ch_off(NBLK);
 static_assert(TL_COUNT <= TL_WORDS * 4, "work table does not fit its shared-memory region");
-static_assert(ch_count(0) <= NT, "one trailing item per thread");
 
 __device__ void build_tile_tables(unsigned short* tl) {
   const int tid = threadIdx.x;
@@ -43,10 +55,18 @@ __device__ void build_tile_tables(unsigned short* tl) {
     for (int ti = 0; ti < 12; ti++)
       for (int tc = 0; tc < 4; tc++) tl[n++] = (unsigned short)(ti | (tc << 8));
   } else if (tid <= NBLK) {
-    const int b = tid - 1, i0 = NB * (b + 1), ng = (NW - i0) / 4;
+    const int b = tid - 1, i0 = NB * (b + 1);
     int n = ch_off(b);
+#if SRB_TRAIL == 0
+    const int T = (NW - i0) / 2;
+    for (int tc = 0; tc < T; tc++) tl[n++] = (unsigned short)(T | (tc << 8));
+    for (int tr = 0; tr < T; tr++)
+      for (int tc = 0; tc <= tr; tc++) tl[n++] = (unsigned short)(tr | (tc << 8));
+#else
+    const int ng = (NW - i0) / 4;
     for (int g = 0; g < ng; g++)
       for (int r = i0 + 4 * g; r <= NW; r++) tl[n++] = (unsigned short)(r | (g << 8));
+#endif
   }
 }
 
@@ -74,18 +94,17 @@ __device__ __forceinline__ void prefetch_lists(const Ws& w, int k, double* lb) {
 __device__ __forceinline__ int rot_tile(int t) { return t < 8 ? t + 8 : t - 8; }
 
 // Blocked partial Cholesky of the lower-stored 48x48 matrix M (+ gradient row qh), 24 pivots.
-// Per block step: (1) warps 0-1 factor the NB x NB diagonal block in registers (right-looking, so every pivot
-// hangs on a chain of ~6 FP64 operations; the FP64 pipe is half rate, so the other warps do NOT repeat it) and,
-// fused with it column by column, solve their panel row (rows below the block; row 48 = gradient) against L_D^T;
-// (2) all threads update the trailing lower triangle, one (row, 4-column group) item each.
+// Per block step: (1) the NB x NB diagonal block is factored in registers (right-looking: every pivot hangs on a
+// chain of ~6 FP64 operations) and, fused with it column by column, each panel row (rows below the block; row 48 =
+// gradient) is solved against L_D^T; (2) all threads update the trailing lower triangle.
 // false -> a pivot was not positive (wrong inertia).
-__device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const unsigned short* tl, int* s_pd, Prof& pf) {
+__device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const unsigned short* tl, Prof& pf) {
   const int tid = threadIdx.x;
 #pragma unroll 1
   for (int b = 0; b < NBLK; b++) {
     const int p0 = NB * b, i0 = p0 + NB;
     double L[NB][NB];
-    if (tid < 64) {
+    {  // every thread repeats the small factorisation: cheaper than a broadcast through shared memory + barrier
       double x[NB];
 #pragma unroll
       for (int i = 0; i < NB; i++)
@@ -117,21 +136,50 @@ __device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const un
 #pragma unroll
         for (int j = 0; j < NB; j++) arow[j] = x[j];
       }
-      if (tid == 63) *s_pd = pd ? 1 : 0;
+      if (!pd) return false;  // every thread holds the same factor
     }
     __syncthreads();
     pf.lap(PH_C_DIAG);
-    if (!*s_pd) return false;
     if (tid == 63) {  // the block's own factor (nobody reads the diagonal block during the trailing update)
 #pragma unroll
       for (int i = 0; i < NB; i++)
 #pragma unroll
         for (int j = 0; j <= i; j++) M[(p0 + i) * LDM + p0 + j] = L[i][j];
     }
-    // trailing update: M[r][c] -= panel_r . panel_c for c in the item's column group, c <= r
     const int cnt = ch_count(b);
-    if (tid < cnt) {
-      const int e = tl[ch_off(b) + tid], r = e & 255, c0 = i0 + 4 * (e >> 8);
+    const unsigned short* list = tl + ch_off(b);
+#if SRB_TRAIL == 0
+    const int T = (NW - i0) / 2;
+    for (int i = tid; i < cnt; i += NT) {
+      const int e = list[i], tr = e & 255, tc = e >> 8;
+      const int c0 = i0 + 2 * tc;
+      const double* xc0 = M + c0 * LDM + p0;
+      const double* xc1 = xc0 + LDM;
+      const bool grad = !(tr < T);
+      const int rr = i0 + 2 * tr;
+      const double* xr0 = grad ? (qh + p0) : (M + rr * LDM + p0);
+      const double* xr1 = grad ? xr0 : xr0 + LDM;
+      double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+#pragma unroll
+      for (int q = 0; q < NB; q++) {
+        const double a = xc0[q], bq = xc1[q], u = xr0[q], v = xr1[q];
+        s00 += u * a; s01 += u * bq; s10 += v * a; s11 += v * bq;
+      }
+      if (!grad) {
+        double* o = M + rr * LDM + c0;
+        o[0] -= s00;
+        o[LDM] -= s10;
+        o[LDM + 1] -= s11;
+        if (tr > tc) o[1] -= s01;
+      } else {
+        qh[c0] -= s00;
+        qh[c0 + 1] -= s01;
+      }
+    }
+#else
+    // M[r][c] -= panel_r . panel_c for c in the item's column group, c <= r
+    for (int i = tid; i < cnt; i += NT) {
+      const int e = list[i], r = e & 255, c0 = i0 + 4 * (e >> 8);
       const double* xr = (r < NW) ? (M + r * LDM + p0) : (qh + p0);
       const double* xc = M + c0 * LDM + p0;
       double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
@@ -146,6 +194,7 @@ __device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const un
       if (c0 + 2 <= r) o[2] -= s2;
       if (c0 + 3 <= r) o[3] -= s3;
     }
+#endif
     __syncthreads();
     pf.lap(PH_C_TRAIL);
   }
@@ -332,7 +381,7 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
     __syncthreads();
     pf.lap(PH_B_P4);
     // P5. eliminate the controls
-    if (!partial_cholesky(M, V + V_QH, tl, &s_ok, pf)) {
+    if (!partial_cholesky(M, V + V_QH, tl, pf)) {
       cp_async_wait_all();  // no prefetch may still be in flight when the sweep is retried
       __syncthreads();
       return false;

@@ -39,6 +39,8 @@ void ip_options_default(ip_options *o) {
   o->bound_relax_factor = 1e-6;
   o->max_soc = 4;
   o->verbose = 0;
+  o->jam_alpha = 0.02;
+  o->jam_iters = 5;
 }
 
 typedef struct {
@@ -534,7 +536,7 @@ static int ip_solve_ws(ipws *w, const double *p, const double *x0, const ip_opti
   init_slacks(w, opt, mu);
   w->nfilt = 0;
   double theta0 = -1, dw_last = 0;
-  int status = 1, it = 0, restarts = 0;
+  int status = 1, it = 0, restarts = 0, tiny = 0;
   for (it = 0; it <= opt->max_iter; it++) {
     double err[3], cmu, ysum, zsum;
     int nzb;
@@ -652,7 +654,12 @@ static int ip_solve_ws(ipws *w, const double *p, const double *x0, const ip_opti
       alpha *= 0.5;
       ls++;
     }
+    /* watchdog against jamming at the fraction-to-the-boundary rule: a run of tiny accepted steps is treated like
+     * a failed line search (IPOPT would leave such a phase through its restoration phase) */
+    if (accepted) tiny = (alpha < opt->jam_alpha) ? tiny + 1 : 0;
+    if (accepted && opt->jam_iters > 0 && tiny >= opt->jam_iters && restarts < 20) { accepted = 0; }
     if (!accepted) {
+      tiny = 0;
       /* no restoration phase: re-centre instead -- slacks pushed back inside their bounds at the
        * current x, multipliers reset, barrier parameter back to mu_init, filter cleared */
       if (restarts < 20) {

@@ -26,6 +26,8 @@ typedef struct ip_options {
   double mu_init, bound_push, bound_frac, bound_relax_factor;
   int max_soc;
   int verbose;
+  double jam_alpha; /* watchdog: accepted primal step below this ... */
+  int jam_iters;    /* ... for this many consecutive iterations -> re-centre (0 = off) */
 } ip_options;
 
 typedef struct ip_result {

@@ -11,7 +11,8 @@ class IpOptions(ctypes.Structure):
     _fields_ = [("max_iter", ctypes.c_int), ("tol", ctypes.c_double), ("constr_viol_tol", ctypes.c_double),
                 ("dual_inf_tol", ctypes.c_double), ("compl_inf_tol", ctypes.c_double),
                 ("mu_init", ctypes.c_double), ("bound_push", ctypes.c_double), ("bound_frac", ctypes.c_double),
-                ("bound_relax_factor", ctypes.c_double), ("max_soc", ctypes.c_int), ("verbose", ctypes.c_int)]
+                ("bound_relax_factor", ctypes.c_double), ("max_soc", ctypes.c_int), ("verbose", ctypes.c_int),
+                ("jam_alpha", ctypes.c_double), ("jam_iters", ctypes.c_int)]
 
 
 class IpResult(ctypes.Structure):
