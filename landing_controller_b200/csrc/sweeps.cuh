@@ -98,13 +98,16 @@ __device__ __forceinline__ int rot_tile(int t) { return t < 8 ? t + 8 : t - 8; }
 // chain of ~6 FP64 operations) and, fused with it column by column, each panel row (rows below the block; row 48 =
 // gradient) is solved against L_D^T; (2) all threads update the trailing lower triangle.
 // false -> a pivot was not positive (wrong inertia).
-__device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const unsigned short* tl, Prof& pf) {
+__device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const unsigned short* tl, int* s_pd, Prof& pf) {
   const int tid = threadIdx.x;
-#pragma unroll 1
-  for (int b = 0; b < NBLK; b++) {
+#pragma unroll
+  for (int b = 0; b < NBLK; b++) {  // unrolled: the work-table offsets are compile-time constants
     const int p0 = NB * b, i0 = p0 + NB;
     double L[NB][NB];
-    {  // every thread repeats the small factorisation: cheaper than a broadcast through shared memory + barrier
+#ifdef SRB_DIAG01
+    if (tid < 64)  // only warps 0-1 own panel rows
+#endif
+    {  // every panel thread repeats the small factorisation: cheaper than a broadcast through shared memory
       double x[NB];
 #pragma unroll
       for (int i = 0; i < NB; i++)
@@ -136,10 +139,17 @@ __device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const un
 #pragma unroll
         for (int j = 0; j < NB; j++) arow[j] = x[j];
       }
+#ifdef SRB_DIAG01
+      if (tid == 63) *s_pd = pd ? 1 : 0;
+#else
       if (!pd) return false;  // every thread holds the same factor
+#endif
     }
     __syncthreads();
     pf.lap(PH_C_DIAG);
+#ifdef SRB_DIAG01
+    if (!*s_pd) return false;
+#endif
     if (tid == 63) {  // the block's own factor (nobody reads the diagonal block during the trailing update)
 #pragma unroll
       for (int i = 0; i < NB; i++)
@@ -381,7 +391,7 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
     __syncthreads();
     pf.lap(PH_B_P4);
     // P5. eliminate the controls
-    if (!partial_cholesky(M, V + V_QH, tl, pf)) {
+    if (!partial_cholesky(M, V + V_QH, tl, &s_ok, pf)) {
       cp_async_wait_all();  // no prefetch may still be in flight when the sweep is retried
       __syncthreads();
       return false;
