@@ -309,7 +309,9 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
   P.prof = d_prof;
   CUS(cudaMemsetAsync(ws.counter, 0, sizeof(int), st));
   if (P.lam_g) CUS(cudaMemsetAsync(P.lam_g, 0, sizeof(double) * m * B, st));
-  const int grid = (int)std::min<long long>(nslots, B);
+  long long gcap = nslots;
+  if (const char* e = getenv("LANDING_GRID")) gcap = std::max(1LL, std::min<long long>(nslots, atoll(e)));  // experiments
+  const int grid = (int)std::min<long long>(gcap, B);
   k_solve<<<grid, NT, SM_TOTAL * sizeof(double), st>>>(P);
   *launches += 1;
   CUS(cudaGetLastError());

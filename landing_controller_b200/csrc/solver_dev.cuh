@@ -19,7 +19,10 @@ namespace {
 constexpr unsigned FULL = 0xffffffffu;
 constexpr int NT = 256;          // threads per CTA (= per scenario)
 constexpr int NWARP = NT / 32;
-constexpr int CTAS_PER_SM = 2;
+#ifndef SRB_CTAS
+#define SRB_CTAS 2
+#endif
+constexpr int CTAS_PER_SM = SRB_CTAS;
 constexpr int NS = 24;           // stage state / control size
 constexpr int NW = 48;           // stage variables X(12) c(12) f(12) c+(12)
 constexpr int LDM = 49, LDP = 25, LDG = 37;  // leading dimensions (padding against bank conflicts)
@@ -27,6 +30,9 @@ constexpr int MAXFILTER = 64;
 constexpr int RK = 104;          // rows per knot (interior numbering)
 constexpr int NROWTAB = 36 + RK;
 constexpr int NJ_PAD = 388, NH_PAD = 192;  // strides of the per-knot entry lists in the scratch (16-byte chunks; padding = 0)
+
+// condensed stage data: 278 target sums | 48 stage-gradient entries | 137 G values | 12 dynamics defects
+constexpr int CT_Q = 280, CT_G = 328, CT_R = 468, CT_STRIDE = 480;
 
 // ---- shared memory carve-up (doubles) per CTA
 constexpr int SM_M = 0;                        // 48 x 49 stage matrix (lower triangle, elimination order)
@@ -36,7 +42,8 @@ constexpr int SM_T = SM_G + 12 * LDG;          // 12 x 37   Pxx*G
 // stage list buffers (double-buffered, filled by cp.async): J | H | sigma | yhat | dynamics defects
 constexpr int LB_J = 0, LB_H = 388, LB_SIG = 580, LB_YH = 684, LB_GD = 788, LB_SIZE = 800;
 constexpr int SM_LB0 = SM_T + 12 * LDG;
-constexpr int SM_V = SM_LB0 + 2 * LB_SIZE;     // vectors
+constexpr int LB_REGION = 2 * CT_STRIDE;       // two condensed-stage buffers (backward) / one list buffer (pre-pass)
+constexpr int SM_V = SM_LB0 + LB_REGION;       // vectors
 constexpr int V_Q = 0, V_QH = 48, V_R = 96, V_T = 108, V_YV = 120, V_PN = 144, V_XI = 168, V_U = 192, V_END = 216;
 constexpr int SM_RED = SM_V + V_END;           // block-reduction scratch NWARP x 8
 constexpr int SM_TAB = SM_RED + NWARP * 8;     // lb[140] ub[140] lbo[140] ubo[140]
@@ -86,13 +93,14 @@ struct Ws {  // pointers into one CTA's scratch slot
   double *x, *xt, *dx;
   double *S, *Y, *ZL, *ZU, *G, *GT, *DS, *YN, *DZL, *DZU, *SIG, *YH;
   double *JL, *HL;
+  double *CT;  // condensed stage data [K][CT_STRIDE], see sweeps.cuh:condense_all
   double *FY, *rf, *yvf, *PX, *PV, *L0;  // FY: per stage [48][24] = L (rows 0-23) | Yt (rows 24-47)
   double *FT, *FP;
 };
 
 __host__ __device__ inline long long slot_doubles(int N) {
   const long long K = N - 1, nx = 36LL * N - 24, MR = 36 + RK * K;
-  const long long n = 3 * nx + 12 * MR + K * (NJ_PAD + NH_PAD) + K * (1152 + 12 + 24) + (K + 1) * (288 + 24) + 144 +
+  const long long n = 3 * nx + 12 * MR + K * (NJ_PAD + NH_PAD + CT_STRIDE) + K * (1152 + 12 + 24) + (K + 1) * (288 + 24) + 144 +
                       2 * MAXFILTER;
   return (n + 31) / 32 * 32;
 }
@@ -106,6 +114,7 @@ __device__ inline Ws carve(double* base, int N) {
   w.GT = p; p += MR; w.DS = p; p += MR; w.YN = p; p += MR; w.DZL = p; p += MR; w.DZU = p; p += MR;
   w.SIG = p; p += MR; w.YH = p; p += MR;
   w.JL = p; p += K * NJ_PAD; w.HL = p; p += K * NH_PAD;
+  w.CT = p; p += K * CT_STRIDE;
   w.FY = p; p += K * 1152; w.rf = p; p += K * 12;
   w.yvf = p; p += K * 24; w.PX = p; p += (K + 1) * 288; w.PV = p; p += (K + 1) * 24;
   w.L0 = p; p += 144; w.FT = p; p += MAXFILTER; w.FP = p; p += MAXFILTER;
@@ -333,32 +342,114 @@ __device__ __forceinline__ int stage_var(int N, int k, int sv) {
   return 12 * N + 24 * (k + 1) + (sv - 36);
 }
 
-// ds = J_row . dx + (g - s), new multipliers, dz, fraction-to-the-boundary limits, merit pieces: all rows in parallel
-__device__ __noinline__ void row_steps(const KParams& P, const Ws& w, const double* tab, const double* drop,
+// row buffer of one knot for row_steps (doubles): J list | s | g | sigma | zL | zU | dx of the 48 stage variables
+constexpr int RB_J = 0, RB_S = NJ_PAD, RB_G = RB_S + RK, RB_SIG = RB_G + RK, RB_ZL = RB_SIG + RK, RB_ZU = RB_ZL + RK,
+              RB_DX = RB_ZU + RK, RB_SIZE = RB_DX + NW + 4;
+static_assert(RB_SIZE % 2 == 0 && 2 * RB_SIZE <= NW * LDM && RB_SIZE <= LB_REGION && RB_SIZE <= NS * LDP + 2 * 12 * LDG,
+              "row buffers alias the sweep regions");
+
+__device__ __forceinline__ void prefetch_rows(const Ws& w, int N, int K, int k, double* rb) {
+  // called by 128 threads (t = threadIdx.x & 127) for knot k
+  const int t = threadIdx.x & 127, r0 = 36 + RK * k;
+  const double* Jk = w.JL + (long long)k * NJ_PAD;
+  for (int i = t; i < NJ_PAD / 2; i += 128) cp_async16(rb + RB_J + 2 * i, Jk + 2 * i);
+  if (t < RK / 2) {
+    cp_async16(rb + RB_S + 2 * t, w.S + r0 + 2 * t);
+    cp_async16(rb + RB_G + 2 * t, w.G + r0 + 2 * t);
+    cp_async16(rb + RB_SIG + 2 * t, w.SIG + r0 + 2 * t);
+  } else if (t < RK) {
+    const int i = t - RK / 2;
+    cp_async16(rb + RB_ZL + 2 * i, w.ZL + r0 + 2 * i);
+    cp_async16(rb + RB_ZU + 2 * i, w.ZU + r0 + 2 * i);
+  } else if (t < RK + 6) {
+    const int i = t - RK;
+    cp_async16(rb + RB_DX + 2 * i, w.dx + 12 * k + 2 * i);                    // dX_k
+  } else if (t < RK + 18) {
+    const int i = t - RK - 6;
+    cp_async16(rb + RB_DX + 12 + 2 * i, w.dx + 12 * N + 24 * k + 2 * i);      // dc_k, df_k
+  } else if (t < RK + 24) {
+    const int i = t - RK - 18;
+    if (k + 1 < K) cp_async16(rb + RB_DX + 36 + 2 * i, w.dx + 12 * N + 24 * (k + 1) + 2 * i);  // dc_{k+1}
+    else { rb[RB_DX + 36 + 2 * i] = 0.0; rb[RB_DX + 37 + 2 * i] = 0.0; }
+  }
+}
+
+// per-row step recovery from shared-memory copies of the row data
+__device__ __forceinline__ void row_step_sm(const Ws& w, int idx, const double* rb, int rho, double lb, double ub,
+                                            double jdx, double mu, double tau, StepInfo& si) {
+  const double s = rb[RB_S + rho], rd = rb[RB_G + rho] - s;
+  const double ds = jdx + rd;
+  double yn = rb[RB_SIG + rho] * ds, dzl = 0.0, dzu = 0.0;
+  si.theta += fabs(rd);
+  if (isfinite(lb)) {
+    const double d = s - lb, z = rb[RB_ZL + rho];
+    yn -= mu / d;
+    dzl = mu / d - z - z / d * ds;
+    if (ds < 0) si.a_pr = fmin(si.a_pr, -tau * d / ds);
+    if (dzl < 0) si.a_du = fmin(si.a_du, -tau * z / dzl);
+    si.dphi_bar -= mu * ds / d;
+    si.phi_bar -= mu * log(d);
+  }
+  if (isfinite(ub)) {
+    const double d = ub - s, z = rb[RB_ZU + rho];
+    yn += mu / d;
+    dzu = mu / d - z + z / d * ds;
+    if (ds > 0) si.a_pr = fmin(si.a_pr, tau * d / ds);
+    if (dzu < 0) si.a_du = fmin(si.a_du, -tau * z / dzu);
+    si.dphi_bar += mu * ds / d;
+    si.phi_bar -= mu * log(d);
+  }
+  w.DS[idx] = ds;
+  w.YN[idx] = yn;
+  w.DZL[idx] = dzl;
+  w.DZU[idx] = dzu;
+}
+
+// ds = J_row . dx + (g - s), new multipliers, dz, fraction-to-the-boundary limits, merit pieces.
+// Two knots per round (threads 0-127 / 128-255, one row per thread); the knots' J lists, row data and steps arrive in
+// shared memory through a 4-buffer cp.async ring, so no thread waits on a chain of dependent L2 round trips.
+__device__ __noinline__ void row_steps(const KParams& P, const Ws& w, double* smem, const double* tab, const double* drop,
                                        double* red, double mu, double tau, StepInfo& si) {
-  const int N = P.N, K = P.K, MR = P.MR, tid = threadIdx.x;
+  const int N = P.N, K = P.K, tid = threadIdx.x, half = tid >> 7, t = tid & 127;
   const SolverTables& tb = P.tab;
   si.a_pr = 1.0; si.a_du = 1.0; si.dphi_bar = 0.0; si.phi_bar = 0.0; si.theta = 0.0;
-  for (int idx = tid; idx < MR; idx += NT) {
-    if (idx < 12) { si.theta += fabs(w.G[idx] - drop[idx]); continue; }
-    if (idx < 36) {
-      const int j = idx - 12, i = (j < 12 ? j % 6 : 6 + (j - 12) % 6);
-      row_step(w, idx, tab[idx], tab[NROWTAB + idx], w.dx[12 * (N - 1) + i], mu, tau, si);
-      continue;
-    }
-    const int k = (idx - 36) / RK, rho = (idx - 36) - k * RK;
-    if (rho < 12) { si.theta += fabs(w.G[idx]); continue; }
-    if (k == K - 1 && is_noslip(rho)) continue;
-    const double* Jk = w.JL + (long long)k * NJ_PAD;
-    double jdx = 0.0;
-    const int p0 = __ldg(tb.r_ptr + rho), p1 = __ldg(tb.r_ptr + rho + 1);
-    for (int p = p0; p < p1; p++) {
-      const int term = __ldg(tb.r_terms + p), sv = term >> 10;
-      if (k == K - 1 && sv >= 36) continue;  // no c+ at the last knot
-      jdx += Jk[term & 1023] * w.dx[stage_var(N, k, sv)];
-    }
-    row_step(w, idx, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
+  auto ring = [&](int k) {
+    const int j = k & 3;
+    return smem + (j == 0 ? SM_LB0 : (j == 1 ? SM_M : (j == 2 ? SM_M + RB_SIZE : SM_P)));
+  };
+  const int rounds = (K + 1) / 2;
+  if (half < K) prefetch_rows(w, N, K, half, ring(half));
+  cp_async_commit();
+  // boundary rows meanwhile (initial-state rows, terminal inequality rows)
+  if (tid < 12) si.theta += fabs(w.G[tid] - drop[tid]);
+  else if (tid < 36) {
+    const int j = tid - 12, i = (j < 12 ? j % 6 : 6 + (j - 12) % 6);
+    row_step(w, tid, tab[tid], tab[NROWTAB + tid], w.dx[12 * (N - 1) + i], mu, tau, si);
   }
+  for (int r = 0; r < rounds; r++) {
+    const int k = 2 * r + half, kn = k + 2;
+    if (kn < K) prefetch_rows(w, N, K, kn, ring(kn));
+    cp_async_commit();
+    cp_async_wait_group<1>();
+    __syncthreads();
+    if (k < K && t < RK) {
+      const double* rb = ring(k);
+      const int rho = t, idx = 36 + RK * k + rho;
+      if (rho < 12) {
+        si.theta += fabs(rb[RB_G + rho]);
+      } else if (!(k == K - 1 && is_noslip(rho))) {
+        double jdx = 0.0;
+        const int p0 = __ldg(tb.r_ptr + rho), p1 = __ldg(tb.r_ptr + rho + 1);
+        for (int p = p0; p < p1; p++) {
+          const int term = __ldg(tb.r_terms + p);
+          jdx += rb[RB_J + (term & 1023)] * rb[RB_DX + (term >> 10)];  // dc+ is zero at the last knot
+        }
+        row_step_sm(w, idx, rb, rho, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
+      }
+    }
+    __syncthreads();
+  }
+  cp_async_wait_group<0>();
   double v[5] = {si.a_pr, si.a_du, si.dphi_bar, si.phi_bar, si.theta};
   const int op[5] = {R_MIN, R_MIN, R_SUM, R_SUM, R_SUM};
   block_reduce<5>(red, v, op);
@@ -678,6 +769,7 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long
     }
     row_yhat(P, w, tab, mu);
     __syncthreads();
+    condense_all(P, w, smem);
     pf.lap(PH_MU);
     const double tau = fmax(tau_min, 1.0 - mu);
     // factorise with inertia correction (IPOPT's delta_w schedule)
@@ -702,7 +794,7 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long
     costates(P, w);
     pf.lap(PH_FWD);
     StepInfo si;
-    row_steps(P, w, tab, drop, red, mu, tau, si);
+    row_steps(P, w, smem, tab, drop, red, mu, tau, si);
     pf.lap(PH_ROWS);
     // filter line search
     const double theta = si.theta, phi = f + si.phi_bar;

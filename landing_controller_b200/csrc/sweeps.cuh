@@ -211,6 +211,87 @@ __device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const un
   return true;
 }
 
+// ---------------------------------------------------------------- condensing pre-pass (parallel over stages)
+// Everything of a stage that does not depend on P_{k+1}: the lower-triangle sums H + J_I' Sigma J_I per target, the stage
+// gradient q = J_I' yhat, the structural entries of G and the defects r.  Done once per iteration for all stages with all
+// 256 threads busy (4-deep cp.async ring over the stage lists), instead of inside the sequential sweep (and its retries).
+template <int PENDING> __device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory");
+}
+
+__device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double* smem) {
+  const int K = P.K, tid = threadIdx.x;
+  const int* tbl = reinterpret_cast<const int*>(smem + SM_TBL);
+  const SolverTables& tb = P.tab;
+  const int* t_g = tbl + tb.o_g;
+  const int* t_qptr = tbl + tb.o_qptr;
+  const int* t_qterms = tbl + tb.o_qterms;
+  const int* t_uabh = tbl + tb.o_uabh;
+  const int* t_uptr = tbl + tb.o_uptr;
+  const int* t_uterms = tbl + tb.o_uterms;
+  // 4-deep ring of list buffers over regions that are idle before the sweeps: list region | stage matrix (2) | P,G,T
+  auto ring = [&](int k) {
+    const int j = k & 3;
+    return smem + (j == 0 ? SM_LB0 : (j == 1 ? SM_M : (j == 2 ? SM_M + LB_SIZE : SM_P)));
+  };
+  static_assert(2 * LB_SIZE <= NW * LDM && LB_SIZE <= LB_REGION && LB_SIZE <= NS * LDP + 2 * 12 * LDG, "ring buffers fit");
+  for (int k = 0; k < 3; k++) {
+    if (k < K) prefetch_lists(w, k, ring(k)); else cp_async_commit();
+  }
+  for (int k = 0; k < K; k++) {
+    if (k + 3 < K) prefetch_lists(w, k + 3, ring(k + 3)); else cp_async_commit();
+    cp_async_wait_group<3>();
+    __syncthreads();
+    const double* lb = ring(k);
+    const double* Js = lb + LB_J;
+    const double* Hs = lb + LB_H;
+    const double* SIGs = lb + LB_SIG;
+    const double* YHs = lb + LB_YH;
+    double* ct = w.CT + (long long)k * CT_STRIDE;
+#pragma unroll
+    for (int rnd = 0; rnd < 2; rnd++) {
+      // second round in reverse thread order: the threads that had the long targets get the trivial items
+      const int it = rnd == 0 ? tid : 2 * NT - 1 - tid;
+      if (it < tb.n_u) {
+        const int abh = t_uabh[it], h = abh >> 12;
+        double a0 = h ? Hs[h - 1] : 0.0, a1 = 0.0;
+        const int p0 = t_uptr[it], p1 = t_uptr[it + 1];
+        for (int p = p0; p < p1; p += 2) {
+          const int u0 = t_uterms[p], u1 = t_uterms[p + 1];
+          a0 += SIGs[u0 >> 20] * Js[(u0 >> 10) & 1023] * Js[u0 & 1023];
+          a1 += SIGs[u1 >> 20] * Js[(u1 >> 10) & 1023] * Js[u1 & 1023];
+        }
+        ct[it] = a0 + a1;
+      } else if (it < tb.n_u + NW) {
+        const int m = it - tb.n_u;
+        double a0 = 0.0, a1 = 0.0;
+        const int p0 = t_qptr[m], p1 = t_qptr[m + 1];
+        for (int p = p0; p < p1; p += 2) {
+          const int u0 = t_qterms[p], u1 = t_qterms[p + 1];
+          a0 += YHs[u0 >> 10] * Js[u0 & 1023];
+          a1 += YHs[u1 >> 10] * Js[u1 & 1023];
+        }
+        ct[CT_Q + m] = a0 + a1;
+      } else if (it < tb.n_u + NW + tb.n_g) {
+        const int n = it - tb.n_u - NW;
+        ct[CT_G + n] = -Js[t_g[n] & 1023];
+      } else if (it < tb.n_u + NW + tb.n_g + 12) {
+        const int i = it - tb.n_u - NW - tb.n_g;
+        ct[CT_R + dyn_state(i)] = -lb[LB_GD + i];
+      }
+    }
+    __syncthreads();  // the buffer is refilled three stages later
+  }
+  cp_async_wait_group<0>();
+}
+
+// condensed data of stage k -> shared memory (asynchronously, 16-byte chunks)
+__device__ __forceinline__ void prefetch_ct(const Ws& w, int k, double* cb) {
+  const int tid = threadIdx.x;
+  if (tid < CT_STRIDE / 2) cp_async16(cb + 2 * tid, w.CT + (long long)k * CT_STRIDE + 2 * tid);
+  cp_async_commit();
+}
+
 // ---------------------------------------------------------------- backward sweep
 // Condenses every stage from the entry lists, factors it and propagates P, p.  false -> not PD.
 __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, double* smem, double dwreg) {
@@ -225,15 +306,11 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
   const SolverTables& tb = P.tab;
   __shared__ int s_ok;
   const int* t_g = tbl + tb.o_g;
-  const int* t_qptr = tbl + tb.o_qptr;
-  const int* t_qterms = tbl + tb.o_qterms;
   const int* t_uabh = tbl + tb.o_uabh;
-  const int* t_uptr = tbl + tb.o_uptr;
-  const int* t_uterms = tbl + tb.o_uterms;
   // this thread's GEMM tile
   int g_ti = 0, g_tj = 0;
   if (tid < 126) { const int e = tl[tid]; g_ti = e & 255; g_tj = e >> 8; }
-  prefetch_lists(w, K - 1, smem + SM_LB0 + ((K - 1) & 1) * LB_SIZE);
+  prefetch_ct(w, K - 1, smem + SM_LB0 + ((K - 1) & 1) * CT_STRIDE);
   // terminal block P_K, p_K; G's zero pattern is set once (only its structural entries change)
   for (int i = tid; i < NS * LDP; i += NT) Pn[i] = 0.0;
   for (int i = tid; i < 12 * LDG; i += NT) Gs[i] = 0.0;
@@ -254,73 +331,38 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
   pf.start();
   for (int k = K - 1; k >= 0; k--) {
     pf.count(PH_B_STAGES);
-    const double* lb = smem + SM_LB0 + (k & 1) * LB_SIZE;
-    const double* Js = lb + LB_J;
-    const double* Hs = lb + LB_H;
-    const double* SIGs = lb + LB_SIG;
-    const double* YHs = lb + LB_YH;
+    const double* cb = smem + SM_LB0 + (k & 1) * CT_STRIDE;  // condensed data of this stage (condense_all)
     cp_async_wait_all();
-    __syncthreads();  // lists of stage k are in shared memory; P_{k+1}, p_{k+1} complete
+    __syncthreads();  // condensed data of stage k is in shared memory; P_{k+1}, p_{k+1} complete
     pf.lap(PH_B_WAIT);
-    if (k > 0) prefetch_lists(w, k - 1, smem + SM_LB0 + ((k - 1) & 1) * LB_SIZE);
-    // P1. dynamics Jacobian G | stage gradient q (elimination order) | defects r
+    if (k > 0) prefetch_ct(w, k - 1, smem + SM_LB0 + ((k - 1) & 1) * CT_STRIDE);
+    // P1. dynamics Jacobian G (structural entries), defects r
     if (tid < tb.n_g) {
-      const int e = t_g[tid], t = e >> 10;
-      Gs[(t / 36) * LDG + (t % 36)] = -Js[e & 1023];
-    } else if (tid >= 160 && tid < 208) {
-      const int m = tid - 160;
-      double a0 = 0.0, a1 = 0.0;
-      const int p0 = t_qptr[m], p1 = t_qptr[m + 1];
-      for (int p = p0; p < p1; p += 2) {
-        const int u0 = t_qterms[p], u1 = t_qterms[p + 1];
-        a0 += YHs[u0 >> 10] * Js[u0 & 1023];
-        a1 += YHs[u1 >> 10] * Js[u1 & 1023];
-      }
-      V[V_Q + m] = a0 + a1;
+      const int t = t_g[tid] >> 10;
+      Gs[(t / 36) * LDG + (t % 36)] = cb[CT_G + tid];
     } else if (tid >= 224 && tid < 236) {
-      V[V_R + dyn_state(tid - 224)] = -lb[LB_GD + tid - 224];
+      V[V_R + tid - 224] = cb[CT_R + tid - 224];
     }
     __syncthreads();
     pf.lap(PH_B_P1);
-    // P2. T = Pxx G (12 x 36; thread = 1 x 4 strip), t = Pxx r + p_x  |  condensing sums (threads 128..255)
-    double cacc[3] = {0.0, 0.0, 0.0};
+    // P2. T = Pxx G (12 x 36; thread (i, jj) -> columns jj, jj+9, jj+18, jj+27: conflict free), t = Pxx r + p_x
     if (tid < 108) {
-      const int i = tid / 9, j0 = (tid - i * 9) * 4;
+      const int i = tid / 9, jj = tid - i * 9;
       double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
 #pragma unroll
       for (int l = 0; l < 12; l++) {
         const double pv = Pn[i * LDP + l];
-        const double* g = Gs + l * LDG + j0;
-        s0 += pv * g[0]; s1 += pv * g[1]; s2 += pv * g[2]; s3 += pv * g[3];
+        const double* g = Gs + l * LDG + jj;
+        s0 += pv * g[0]; s1 += pv * g[9]; s2 += pv * g[18]; s3 += pv * g[27];
       }
-      double* t = Ts + i * LDG + j0;
-      t[0] = s0; t[1] = s1; t[2] = s2; t[3] = s3;
+      double* t = Ts + i * LDG + jj;
+      t[0] = s0; t[9] = s1; t[18] = s2; t[27] = s3;
     } else if (tid < 120) {
       const int i = tid - 108;
       double s = V[V_PN + i];
 #pragma unroll
       for (int l = 0; l < 12; l++) s += Pn[i * LDP + l] * V[V_R + l];
       V[V_T + i] = s;
-    } else if (tid >= 128) {
-      // Hessian entry + sigma-weighted outer products of the inequality rows (+ delta_w) per target
-#pragma unroll
-      for (int j = 0; j < 3; j++) {
-        const int t = tid - 128 + 128 * j;
-        if (t < tb.n_u) {
-          const int abh = t_uabh[t], h = abh >> 12;
-          double a0 = h ? Hs[h - 1] : 0.0, a1 = 0.0;
-          const int p0 = t_uptr[t], p1 = t_uptr[t + 1];
-          for (int p = p0; p < p1; p += 2) {
-            const int u0 = t_uterms[p], u1 = t_uterms[p + 1];
-            a0 += SIGs[u0 >> 20] * Js[(u0 >> 10) & 1023] * Js[u0 & 1023];
-            a1 += SIGs[u1 >> 20] * Js[(u1 >> 10) & 1023] * Js[u1 & 1023];
-          }
-          const int ab = abh & 4095, a = ab / NW, b2 = ab - a * NW;
-          double acc = a0 + a1;
-          if (a == b2) acc += (a >= 12 && a < 24) ? (k == K - 1 ? 1.0 : 0.0) : dwreg;  // dummy c+ of the last stage
-          cacc[j] = acc;
-        }
-      }
     }
     __syncthreads();
     pf.lap(PH_B_P2);
@@ -362,7 +404,7 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
       M[(12 + i) * LDM + 12 + rem] = Pn[(12 + i) * LDP + 12 + rem];
     } else if (tid >= 208) {
       const int m = tid - 208;  // elimination-order index
-      double s = V[V_Q + m];
+      double s = cb[CT_Q + m];
       if (m >= 12 && m < 24) {
         const int j = m - 12;
         s += V[V_PN + 12 + j];
@@ -377,15 +419,15 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
     }
     __syncthreads();
     pf.lap(PH_B_P3);
-    // P4. add the condensing sums
-    if (tid >= 128) {
+    // P4. add the condensed sums (+ delta_w on the (f, X, c) diagonal, dummy c+ of the last stage)
 #pragma unroll
-      for (int j = 0; j < 3; j++) {
-        const int t = tid - 128 + 128 * j;
-        if (t < tb.n_u) {
-          const int ab = t_uabh[t] & 4095, a = ab / NW, b2 = ab - a * NW;
-          M[a * LDM + b2] += cacc[j];
-        }
+    for (int rnd = 0; rnd < 2; rnd++) {
+      const int t = tid + NT * rnd;
+      if (t < tb.n_u) {
+        const int ab = t_uabh[t] & 4095, a = ab / NW, b2 = ab - a * NW;
+        double acc = cb[t];
+        if (a == b2) acc += (a >= 12 && a < 24) ? (k == K - 1 ? 1.0 : 0.0) : dwreg;
+        M[a * LDM + b2] += acc;
       }
     }
     __syncthreads();
@@ -450,7 +492,7 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
 // ---------------------------------------------------------------- forward sweep
 // forward-stage buffer (doubles): FY 48x24 (L | Yt) | J list 388 | yv 24 | r 12 ; G (12x37) is rebuilt per stage
 constexpr int FB_FY = 0, FB_J = 1152, FB_YV = FB_J + NJ_PAD, FB_R = FB_YV + NS, FB_SIZE = FB_R + 12;
-static_assert(FB_SIZE <= NW * LDM && FB_SIZE <= 2 * 12 * LDG + 2 * LB_SIZE, "forward buffers alias the backward regions");
+static_assert(FB_SIZE <= NW * LDM && FB_SIZE <= 2 * 12 * LDG + LB_REGION, "forward buffers alias the backward regions");
 
 __device__ __forceinline__ void prefetch_factors(const Ws& w, int k, double* fb) {
   const int tid = threadIdx.x;
