@@ -43,7 +43,7 @@ struct HostTables {
   std::vector<int> all;
   size_t o_jl, o_hl, o_rptr, o_rterms, o_cptr, o_cterms, o_sm;
   std::vector<int> sm;  // shared-memory tables
-  int o_g, n_g, o_qptr, o_qterms, o_uabh, o_uptr, o_uterms, n_u;
+  int o_g, n_g, o_qptr, o_qterms, o_uabh, o_uptr, o_uterms, n_u, s_rptr, s_rterms, s_cptr, s_cterms;
 };
 
 int sidx_host(int v) { return v < 36 ? v : (v >= 48 ? v - 12 : -1); }
@@ -147,6 +147,8 @@ HostTables build_tables_host() {
   }
   T.o_rptr = push(rptr);
   T.o_rterms = push(rterms);
+  T.s_rptr = pushs(rptr);
+  T.s_rterms = pushs(rterms);
   // column schedule: per local variable (60), (rho, e)
   std::vector<int> cptr{0}, cterms;
   for (int v = 0; v < 60; v++) {
@@ -156,6 +158,8 @@ HostTables build_tables_host() {
   }
   T.o_cptr = push(cptr);
   T.o_cterms = push(cterms);
+  T.s_cptr = pushs(cptr);
+  T.s_cterms = pushs(cterms);
   T.o_sm = push(T.sm);
   return T;
 }
@@ -247,6 +251,7 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
     if (ws.tab.sm_count > TBL_INTS) { *err = "landing_solve_batch: shared-memory tables exceed their region"; return LANDING_ERR_ARG; }
     ws.tab.o_g = T.o_g; ws.tab.n_g = T.n_g; ws.tab.o_qptr = T.o_qptr; ws.tab.o_qterms = T.o_qterms;
     ws.tab.o_uabh = T.o_uabh; ws.tab.o_uptr = T.o_uptr; ws.tab.o_uterms = T.o_uterms; ws.tab.n_u = T.n_u;
+    ws.tab.o_rptr = T.s_rptr; ws.tab.o_rterms = T.s_rterms; ws.tab.o_cptr = T.s_cptr; ws.tab.o_cterms = T.s_cterms;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&ws.n_sm, cudaDevAttrMultiProcessorCount, dev);

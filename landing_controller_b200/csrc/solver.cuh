@@ -20,6 +20,7 @@ struct SolverTables {
   // condensing targets of the stage matrix (lower triangle, elimination order m = (s+24) mod 48):
   //   M[a][b] += H[h] (if any) + sum sigma_rho J_ea J_eb over terms (rho<<20 | ea<<10 | eb), padded to pairs
   int o_uabh, o_uptr, o_uterms, n_u;   // uabh = (a*48+b) | (h+1) << 12
+  int o_rptr, o_rterms, o_cptr, o_cterms;  // shared-memory copies of the row / column schedules
 };
 
 struct SolverWorkspace {

@@ -49,7 +49,7 @@ constexpr int SM_RED = SM_V + V_END;           // block-reduction scratch NWARP 
 constexpr int SM_TAB = SM_RED + NWARP * 8;     // lb[140] ub[140] lbo[140] ubo[140]
 constexpr int TL_WORDS = 296;                  // static tile tables (unsigned short), see sweeps.cuh
 constexpr int SM_TL = SM_TAB + 4 * NROWTAB;
-constexpr int TBL_INTS = 1700;                 // index tables of the sweeps (SolverTables::sm_src)
+constexpr int TBL_INTS = 2560;                 // index tables of the sweeps (SolverTables::sm_src)
 constexpr int SM_TBL = SM_TL + TL_WORDS;
 constexpr int SM_TOTAL = SM_TBL + TBL_INTS / 2;
 static_assert(CTAS_PER_SM * (SM_TOTAL * 8 + 1024) <= 232448, "shared memory budget (227 KB per SM)");
@@ -411,7 +411,8 @@ __device__ __forceinline__ void row_step_sm(const Ws& w, int idx, const double* 
 __device__ __noinline__ void row_steps(const KParams& P, const Ws& w, double* smem, const double* tab, const double* drop,
                                        double* red, double mu, double tau, StepInfo& si) {
   const int N = P.N, K = P.K, tid = threadIdx.x, half = tid >> 7, t = tid & 127;
-  const SolverTables& tb = P.tab;
+  const int* t_rptr = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_rptr;
+  const int* t_rterms = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_rterms;
   si.a_pr = 1.0; si.a_du = 1.0; si.dphi_bar = 0.0; si.phi_bar = 0.0; si.theta = 0.0;
   auto ring = [&](int k) {
     const int j = k & 3;
@@ -439,9 +440,9 @@ __device__ __noinline__ void row_steps(const KParams& P, const Ws& w, double* sm
         si.theta += fabs(rb[RB_G + rho]);
       } else if (!(k == K - 1 && is_noslip(rho))) {
         double jdx = 0.0;
-        const int p0 = __ldg(tb.r_ptr + rho), p1 = __ldg(tb.r_ptr + rho + 1);
+        const int p0 = t_rptr[rho], p1 = t_rptr[rho + 1];
         for (int p = p0; p < p1; p++) {
-          const int term = __ldg(tb.r_terms + p);
+          const int term = t_rterms[p];
           jdx += rb[RB_J + (term & 1023)] * rb[RB_DX + (term >> 10)];  // dc+ is zero at the last knot
         }
         row_step_sm(w, idx, rb, rho, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
@@ -566,9 +567,10 @@ __device__ __forceinline__ void row_yhat(const KParams& P, const Ws& w, const do
 }
 
 // max |grad f + J' y| (gradient of the Lagrangian w.r.t. x): one (knot, variable) item per thread
-__device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, double* red) {
+__device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const double* smem, double* red) {
   const int N = P.N, K = P.K, tid = threadIdx.x;
-  const SolverTables& tb = P.tab;
+  const int* t_cptr = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_cptr;
+  const int* t_cterms = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_cterms;
   double dmax = 0.0;
   for (int item = tid; item < K * 36; item += NT) {
     const int k = item / 36, v = item - k * 36;
@@ -576,9 +578,9 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, double*
     const double* yk = w.Y + 36 + RK * k;
     double a = 0.0;
     {
-      const int p0 = __ldg(tb.c_ptr + v), p1 = __ldg(tb.c_ptr + v + 1);
+      const int p0 = t_cptr[v], p1 = t_cptr[v + 1];
       for (int p = p0; p < p1; p++) {
-        const int term = __ldg(tb.c_terms + p);
+        const int term = t_cterms[p];
         a += Jk[term & 1023] * yk[term >> 10];
       }
     }
@@ -586,9 +588,9 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, double*
       if (k > 0) {  // what knot k-1 contributes to (X_k, c_k) through its X+ / c+ columns
         const double* Jp = Jk - NJ_PAD;
         const double* yp = yk - RK;
-        const int p0 = __ldg(tb.c_ptr + 36 + v), p1 = __ldg(tb.c_ptr + 36 + v + 1);
+        const int p0 = t_cptr[36 + v], p1 = t_cptr[36 + v + 1];
         for (int p = p0; p < p1; p++) {
-          const int term = __ldg(tb.c_terms + p);
+          const int term = t_cterms[p];
           a += Jp[term & 1023] * yp[term >> 10];
         }
       } else if (v < 12) {
@@ -601,9 +603,9 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, double*
     const double* Jk = w.JL + (long long)(K - 1) * NJ_PAD;
     const double* yk = w.Y + 36 + RK * (K - 1);
     double a = 0.0;
-    const int p0 = __ldg(tb.c_ptr + 36 + tid), p1 = __ldg(tb.c_ptr + 36 + tid + 1);
+    const int p0 = t_cptr[36 + tid], p1 = t_cptr[36 + tid + 1];
     for (int p = p0; p < p1; p++) {
-      const int term = __ldg(tb.c_terms + p);
+      const int term = t_cterms[p];
       a += Jk[term & 1023] * yk[term >> 10];
     }
     const int r1 = tid < 6 ? 12 + tid : 24 + (tid - 6);
@@ -741,7 +743,7 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long
     Errs er;
     row_errors(P, w, tab, drop, red, mu, er);
     pf.lap(PH_ERR);
-    const double dual = fmax(er.dual, dual_inf_x(P, w, red));
+    const double dual = fmax(er.dual, dual_inf_x(P, w, smem, red));
     pf.lap(PH_DUAL);
     pf.count(PH_NITER);
     const double s_d = fmax(s_max, (er.ysum + er.zsum) / (double)(P.opt.reserved[0] + er.nzb)) / s_max;
