@@ -173,14 +173,17 @@ def run_reference(args):
 
 
 def main():
+    global KNOTS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--batch", type=int, default=BATCH)
+    ap.add_argument("--knots", type=int, default=KNOTS, help="knots per trajectory (BASELINE configs: 30; 50 for the 16k sweep)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios in the cpu_baseline sample (0 = auto)")
     args = ap.parse_args()
+    KNOTS = args.knots
     if args.impl == "reference":
         run_reference(args)
         return

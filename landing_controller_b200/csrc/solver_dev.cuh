@@ -458,7 +458,7 @@ __device__ __noinline__ void row_steps(const KParams& P, const Ws& w, double* sm
 }
 
 // merit function pieces at the trial point (x + a dx, s + a ds) with g(trial) in GT
-__device__ __forceinline__ void merit_trial(const KParams& P, const Ws& w, const double* tab, const double* drop,
+__device__ __noinline__ void merit_trial(const KParams& P, const Ws& w, const double* tab, const double* drop,
                                             double* red, double alpha, double mu, double& phi_bar, double& theta) {
   const int K = P.K, MR = P.MR;
   double ph = 0.0, th = 0.0;
@@ -489,7 +489,7 @@ struct Errs {
 };
 
 // sigma per row and the pieces of the optimality error (oracle/ip_ref.c: assemble)
-__device__ __forceinline__ void row_errors(const KParams& P, const Ws& w, const double* tab, const double* drop,
+__device__ __noinline__ void row_errors(const KParams& P, const Ws& w, const double* tab, const double* drop,
                                            double* red, double mu, Errs& e) {
   const int K = P.K, MR = P.MR;
   double dual = 0, prim = 0, c0 = 0, cmu = 0, ys = 0, zs = 0, viol = 0, nb = 0;
@@ -539,7 +539,7 @@ __device__ __forceinline__ void row_errors(const KParams& P, const Ws& w, const 
   e.nzb = (int)(v[7] + 0.5);
 }
 
-__device__ __forceinline__ double compl_at(const KParams& P, const Ws& w, const double* tab, double* red, double mu) {
+__device__ __noinline__ double compl_at(const KParams& P, const Ws& w, const double* tab, double* red, double mu) {
   const int K = P.K, MR = P.MR;
   double cmu = 0;
   for (int idx = threadIdx.x; idx < MR; idx += NT) {
@@ -553,7 +553,7 @@ __device__ __forceinline__ double compl_at(const KParams& P, const Ws& w, const 
 }
 
 // yhat = sigma (g - s) - mu/(s-lb) + mu/(ub-s)
-__device__ __forceinline__ void row_yhat(const KParams& P, const Ws& w, const double* tab, double mu) {
+__device__ __noinline__ void row_yhat(const KParams& P, const Ws& w, const double* tab, double mu) {
   const int K = P.K, MR = P.MR;
   for (int idx = threadIdx.x; idx < MR; idx += NT) {
     if (row_kind(idx, K) != ROW_INEQ) { w.YH[idx] = 0.0; continue; }
@@ -617,7 +617,7 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
 }
 
 // slacks pushed inside their bounds at the current g; mu-based bound multipliers (ip_ref.c: init_slacks)
-__device__ __forceinline__ void init_slacks(const KParams& P, const Ws& w, const double* tab, double mu) {
+__device__ __noinline__ void init_slacks(const KParams& P, const Ws& w, const double* tab, double mu) {
   const int K = P.K, MR = P.MR;
   const double bp = P.opt.bound_push, bf = P.opt.bound_frac;
   for (int idx = threadIdx.x; idx < MR; idx += NT) {

@@ -14,21 +14,11 @@
 //   [0,78)    symmetric G'(Pxx G) tiles (ti >= tj), 3x3, G-column tile coordinates 0..11
 //   [78,126)  cross tiles G' Pxc: (ti 0..11, tc 0..3)
 //   [ch_off(b), ch_off(b+1))  trailing work items of block step b (see partial_cholesky)
-#ifndef SRB_TRAIL
-#define SRB_TRAIL 1
-#endif
 #ifndef SRB_NB
 #define SRB_NB 4
 #endif
 constexpr int NB = SRB_NB;                    // pivot block size
 constexpr int NBLK = NS / NB;                 // block steps
-#if SRB_TRAIL == 0
-// 2x2 tiles (tr >= tc) of the trailing lower triangle; tr == T is the gradient row
-__host__ __device__ constexpr int ch_count(int b) {
-  const int T = (NW - NB * (b + 1)) / 2;
-  return T * (T + 1) / 2 + T;
-}
-#else
 // (row r | column group g << 8): r in [i0, 48] (48 = gradient row), columns i0 + 4g .. i0 + 4g + 3, i0 + 4g <= r;
 // ordered group by group: a warp reads ONE column group (broadcast) and consecutive rows (conflict-free)
 __host__ __device__ constexpr int ch_count(int b) {
@@ -37,7 +27,6 @@ __host__ __device__ constexpr int ch_count(int b) {
   for (int g = 0; g < ng; g++) n += (NW + 1) - (i0 + 4 * g);
   return n;
 }
-#endif
 __host__ __device__ constexpr int ch_off(int b) {
   int o = 126;
   for (int i = 0; i < b; i++) o += ch_count(i);
@@ -57,16 +46,9 @@ __device__ void build_tile_tables(unsigned short* tl) {
   } else if (tid <= NBLK) {
     const int b = tid - 1, i0 = NB * (b + 1);
     int n = ch_off(b);
-#if SRB_TRAIL == 0
-    const int T = (NW - i0) / 2;
-    for (int tc = 0; tc < T; tc++) tl[n++] = (unsigned short)(T | (tc << 8));
-    for (int tr = 0; tr < T; tr++)
-      for (int tc = 0; tc <= tr; tc++) tl[n++] = (unsigned short)(tr | (tc << 8));
-#else
     const int ng = (NW - i0) / 4;
     for (int g = 0; g < ng; g++)
       for (int r = i0 + 4 * g; r <= NW; r++) tl[n++] = (unsigned short)(r | (g << 8));
-#endif
   }
 }
 
@@ -98,15 +80,12 @@ __device__ __forceinline__ int rot_tile(int t) { return t < 8 ? t + 8 : t - 8; }
 // chain of ~6 FP64 operations) and, fused with it column by column, each panel row (rows below the block; row 48 =
 // gradient) is solved against L_D^T; (2) all threads update the trailing lower triangle.
 // false -> a pivot was not positive (wrong inertia).
-__device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const unsigned short* tl, int* s_pd, Prof& pf) {
+__device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const unsigned short* tl, Prof& pf) {
   const int tid = threadIdx.x;
 #pragma unroll
   for (int b = 0; b < NBLK; b++) {  // unrolled: the work-table offsets are compile-time constants
     const int p0 = NB * b, i0 = p0 + NB;
     double L[NB][NB];
-#ifdef SRB_DIAG01
-    if (tid < 64)  // only warps 0-1 own panel rows
-#endif
     {  // every panel thread repeats the small factorisation: cheaper than a broadcast through shared memory
       double x[NB];
 #pragma unroll
@@ -139,17 +118,10 @@ __device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const un
 #pragma unroll
         for (int j = 0; j < NB; j++) arow[j] = x[j];
       }
-#ifdef SRB_DIAG01
-      if (tid == 63) *s_pd = pd ? 1 : 0;
-#else
       if (!pd) return false;  // every thread holds the same factor
-#endif
     }
     __syncthreads();
     pf.lap(PH_C_DIAG);
-#ifdef SRB_DIAG01
-    if (!*s_pd) return false;
-#endif
     if (tid == 63) {  // the block's own factor (nobody reads the diagonal block during the trailing update)
 #pragma unroll
       for (int i = 0; i < NB; i++)
@@ -158,35 +130,6 @@ __device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const un
     }
     const int cnt = ch_count(b);
     const unsigned short* list = tl + ch_off(b);
-#if SRB_TRAIL == 0
-    const int T = (NW - i0) / 2;
-    for (int i = tid; i < cnt; i += NT) {
-      const int e = list[i], tr = e & 255, tc = e >> 8;
-      const int c0 = i0 + 2 * tc;
-      const double* xc0 = M + c0 * LDM + p0;
-      const double* xc1 = xc0 + LDM;
-      const bool grad = !(tr < T);
-      const int rr = i0 + 2 * tr;
-      const double* xr0 = grad ? (qh + p0) : (M + rr * LDM + p0);
-      const double* xr1 = grad ? xr0 : xr0 + LDM;
-      double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-#pragma unroll
-      for (int q = 0; q < NB; q++) {
-        const double a = xc0[q], bq = xc1[q], u = xr0[q], v = xr1[q];
-        s00 += u * a; s01 += u * bq; s10 += v * a; s11 += v * bq;
-      }
-      if (!grad) {
-        double* o = M + rr * LDM + c0;
-        o[0] -= s00;
-        o[LDM] -= s10;
-        o[LDM + 1] -= s11;
-        if (tr > tc) o[1] -= s01;
-      } else {
-        qh[c0] -= s00;
-        qh[c0 + 1] -= s01;
-      }
-    }
-#else
     // M[r][c] -= panel_r . panel_c for c in the item's column group, c <= r
     for (int i = tid; i < cnt; i += NT) {
       const int e = list[i], r = e & 255, c0 = i0 + 4 * (e >> 8);
@@ -204,7 +147,6 @@ __device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const un
       if (c0 + 2 <= r) o[2] -= s2;
       if (c0 + 3 <= r) o[3] -= s3;
     }
-#endif
     __syncthreads();
     pf.lap(PH_C_TRAIL);
   }
@@ -433,7 +375,7 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
     __syncthreads();
     pf.lap(PH_B_P4);
     // P5. eliminate the controls
-    if (!partial_cholesky(M, V + V_QH, tl, &s_ok, pf)) {
+    if (!partial_cholesky(M, V + V_QH, tl, pf)) {
       cp_async_wait_all();  // no prefetch may still be in flight when the sweep is retried
       __syncthreads();
       return false;
