@@ -204,8 +204,13 @@ class LandingSolver:
         return p, x0
 
     # ---- the solve: one NLP per drop condition ----------------------------------------------
-    def solve(self, drops, x0=None, want_lam=False):
-        """drops: host numpy [B,12] (q_init[6], qd_init[6]). Returns dict of host arrays."""
+    def solve(self, drops, x0=None, want_lam=False, want_lam_p=False):
+        """drops: host numpy [B,12] (q_init[6], qd_init[6]). Returns dict of host arrays.
+
+        want_lam: also return lam_g [B,m].  want_lam_p: also return lam_x [B,nx] and lam_p [B,np], obtained as CasADi's
+        Nlpsol does after the solve (nlpsol.cpp:609-625): one nlp_grad evaluation at (x*, lam_f = 1, lam_g*);
+        lam_x = -grad_gamma_x is ~0 here (the reference passes no variable bounds), lam_p = -grad_gamma_p."""
+        want_lam = want_lam or want_lam_p
         drops = np.ascontiguousarray(drops, dtype=np.float64)
         B = drops.shape[0]
         d = self.dims
@@ -219,6 +224,10 @@ class LandingSolver:
         self._check(self.lib.landing_solve_batch(self.ctx, B, HOST, ctypes.byref(self.problem),
                                                  ctypes.byref(self.options), ctypes.byref(io)),
                     "landing_solve_batch")
+        if want_lam_p:
+            p, _ = self.build_host(drops)
+            g = self.eval_host(out["x"], p, lam_f=np.ones(B), lam_g=out["lam_g"], want=("grad_x", "grad_p"))
+            out["lam_x"], out["lam_p"] = -g["grad_x"], -g["grad_p"]
         return out
 
     def solve_device(self, drops, x_star, f_star, status, iters, viol=None, lam_g=None, x0=None):

@@ -94,6 +94,21 @@ def test_converged_points_are_kkt_points_of_the_reference_functions(solver21):
     assert frac >= 0.2
 
 
+def test_multipliers_of_the_parameters_follow_nlp_grad(solver21):
+    """lam_x / lam_p as CasADi's Nlpsol computes them after the solve (nlpsol.cpp:609-625), checked with the oracle."""
+    drops = lc.grid_sweep(1024)[::301][:3]
+    solver21.options.max_iter = 3000
+    r = solver21.solve(drops, want_lam_p=True)
+    o = Oracle(21)
+    pb = o.default_problem()
+    for b in range(len(drops)):
+        p, _ = o.build_p_x0(pb, drops[b, :6], drops[b, 6:])
+        _, _, _, gx, gp = o.grad(r["x"][b], p, 1.0, r["lam_g"][b])
+        assert np.max(np.abs(r["lam_p"][b] + gp) / np.maximum(1.0, np.abs(gp))) < 1e-10
+        assert np.max(np.abs(r["lam_x"][b] + gx)) < 1e-9
+        assert np.max(np.abs(r["lam_x"][b])) < 1e-2  # stationarity: no variable bounds => lam_x ~ 0
+
+
 def test_device_buffers_and_statuses(solver21):
     import torch
     B = 64
