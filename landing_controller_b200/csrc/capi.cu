@@ -178,7 +178,8 @@ void landing_options_default(landing_options* o) {
 }
 
 int landing_eval_batch(landing_ctx* c, long long B, int memspace, int layout, const landing_eval_io* io) {
-  if (!c || !io || B <= 0) return fail(LANDING_ERR_ARG, "landing_eval_batch: bad arguments");
+  if (!c || !io || B < 0) return fail(LANDING_ERR_ARG, "landing_eval_batch: bad arguments");
+  if (B == 0) return LANDING_OK;
   CU(cudaSetDevice(c->device));
   const DevicePlan& pl = c->dpl;
   const long long nx = pl.nx, np = pl.np, m = pl.m, nj = pl.nnzJ, nh = pl.nnzH;
@@ -299,7 +300,9 @@ int landing_build_batch(landing_ctx* c, long long B, int memspace, int layout, c
 
 int landing_solve_batch(landing_ctx* c, long long B, int memspace, const landing_problem* pb,
                         const landing_options* opt, const landing_solve_io* io) {
-  if (!c || !pb || !io || !io->drops || B <= 0) return fail(LANDING_ERR_ARG, "landing_solve_batch: bad arguments");
+  if (!c || !pb || !io || B < 0) return fail(LANDING_ERR_ARG, "landing_solve_batch: bad arguments");
+  if (B == 0) return LANDING_OK;  // an empty sweep is a no-op (the reference's sweep loops simply do not iterate)
+  if (!io->drops) return fail(LANDING_ERR_ARG, "landing_solve_batch: drops is NULL");
   CU(cudaSetDevice(c->device));
   landing_options o;
   if (opt) o = *opt; else landing_options_default(&o);

@@ -109,6 +109,61 @@ def test_multipliers_of_the_parameters_follow_nlp_grad(solver21):
         assert np.max(np.abs(r["lam_x"][b])) < 1e-2  # stationarity: no variable bounds => lam_x ~ 0
 
 
+def test_baseline_config0_single_drop_n30():
+    """BASELINE configs[0]: one drop condition (0.5 m, level, 1 m/s forward), N = 30 knots, solved to convergence on
+    the GPU and by the CPU restatement: both converge, same optimal cost, the GPU point is a KKT point of the oracle."""
+    N = 30
+    d = lc.single_drop()
+    s = lc.LandingSolver(N=N)
+    r = s.solve(d, want_lam=True)
+    s.close()
+    c = solve_cpu(N, d, threads=1)
+    assert r["status"][0] == 0 and c["status"][0] == 0
+    assert abs(r["f"][0] - c["f"][0]) <= 1e-4
+    o = Oracle(N)
+    f, viol, stat, comp = _kkt_certificate(o, o.default_problem(), d[0], r["x"][0], r["lam_g"][0])
+    assert viol <= 1e-3 + 2e-6 and stat <= 1e-2 and comp <= 2e-3
+    # every leg touches down and carries load only on the ground
+    cs = lc.contact_set(r["x"][0], N)
+    assert cs.any(axis=0).all()
+    U = r["x"][0][12 * N:].reshape(N - 1, 24)
+    assert np.all(U[:, 2:12:3][cs] < 0.02)
+    print("config0: GPU iters %d, CPU iters %d, max|x_gpu - x_cpu| %.2e, identical contact set %s" %
+          (r["iters"][0], c["iters"][0], np.max(np.abs(r["x"][0] - c["x"][0])),
+           np.array_equal(cs, lc.contact_set(c["x"][0], N))))
+
+
+def test_edge_cases_empty_single_and_odd_batches(solver21):
+    import ctypes
+    # empty sweep: a no-op, not an error
+    io = lc.api.SolveIO(None, None, None, None, None, None, None, None)
+    assert solver21.lib.landing_solve_batch(solver21.ctx, 0, lc.HOST, ctypes.byref(solver21.problem),
+                                            ctypes.byref(solver21.options), ctypes.byref(io)) == 0
+    # missing drop conditions: loud failure
+    assert solver21.lib.landing_solve_batch(solver21.ctx, 4, lc.HOST, ctypes.byref(solver21.problem),
+                                            ctypes.byref(solver21.options), ctypes.byref(io)) != 0
+    # one scenario, and more scenarios than resident CTAs (2 x #SM) with a ragged tail: same answers as scenario by scenario
+    solver21.options.max_iter = 25
+    drops = lc.grid_sweep(1024)[::3][:301]
+    allr = solver21.solve(drops)
+    one = solver21.solve(drops[300:301])
+    assert np.array_equal(allr["x"][300], one["x"][0]) and allr["iters"][300] == one["iters"][0]
+    c = solve_cpu(21, drops[295:301], default_options(max_iter=25))
+    assert np.max(np.abs(allr["x"][295:301] - c["x"])) < 1e-6
+
+
+@pytest.mark.parametrize("N", [4, 64])
+def test_smallest_and_large_knot_counts(N):
+    drops = lc.grid_sweep(16)[:4]
+    s = lc.LandingSolver(N=N)
+    s.options.max_iter = 3
+    r = s.solve(drops)
+    c = solve_cpu(N, drops, default_options(max_iter=3))
+    s.close()
+    assert np.array_equal(r["iters"], c["iters"])
+    assert np.max(np.abs(r["x"] - c["x"])) < 1e-9
+
+
 def test_device_buffers_and_statuses(solver21):
     import torch
     B = 64
