@@ -91,7 +91,9 @@ def test_converged_points_are_kkt_points_of_the_reference_functions(solver21):
     cs_same = [np.array_equal(lc.contact_set(r["x"][b], 21), lc.contact_set(c["x"][b], 21)) for b in np.where(both)[0]]
     print("trajectory agreement <1e-6: %.0f%% of %d; identical contact sets: %.0f%%" %
           (100 * frac, both.sum(), 100 * np.mean(cs_same)))
-    assert frac >= 0.2
+    # with the jamming watchdog (71 iterations on average instead of 153) rounding differences are amplified far
+    # less: 88 % of the trajectories agree to 1e-6 and all contact sets are identical in the round-1 run
+    assert frac >= 0.5 and np.mean(cs_same) >= 0.8
 
 
 def test_multipliers_of_the_parameters_follow_nlp_grad(solver21):
