@@ -257,6 +257,8 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
     cudaDeviceGetAttribute(&ws.n_sm, cudaDevAttrMultiProcessorCount, dev);
     CUS(cudaMalloc(&ws.counter, sizeof(int)));
     CUS(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_TOTAL * sizeof(double))));
+    if (const char* e = getenv("LANDING_CARVEOUT"))  // experiments: shared-memory carve-out in percent
+      CUS(cudaFuncSetAttribute(k_solve, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
   }
   const long long slot = slot_doubles(N);
   const long long nslots = (long long)ws.n_sm * CTAS_PER_SM;

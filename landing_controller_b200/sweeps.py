@@ -66,3 +66,28 @@ def random_sweep(B, seed=0, large_tilt=False):
     hz = -sp[:, None] * hip[None, :, 0] + (sr * cp)[:, None] * hip[None, :, 1]
     d[:, 2] = 0.35 + np.abs(hz.min(axis=1)) + np.abs(0.03 * d[:, 11])
     return d
+
+
+def apply_sweep_parameters(pb):
+    """Set the numeric parameters the reference's SWEEP callers use (generate_training_data_automated.m:62-102), which
+    differ from the generator's defaults (generate_landingCtrller_IPOPT.m:173-196): larger force / leg-length limits
+    (the random drops reach v_z = -6 m/s, infeasible with f_max = 200), wider terminal box, other weights.
+    `pb` is any object with the landing_problem fields (ctypes structure of the library or of the oracle)."""
+    def put(name, vals):
+        a = getattr(pb, name)
+        for i, v in enumerate(vals):
+            a[i] = v
+    put("q_term_min", [-10, -10, 0.15, -0.1, -0.1, -10])
+    put("q_term_max", [10, 10, 5, 0.1, 0.1, 10])
+    put("qd_term_min", [-10, -10, -10, -0.5, -0.5, -0.5])
+    put("qd_term_max", [10, 10, 10, 0.5, 0.5, 0.5])
+    put("q_min", [-10, -10, 0.075, -10, -10, -10])
+    put("q_max", [10, 10, 1.0, 10, 10, 10])
+    put("q_term_ref", [0, 0, 0.25, 0, 0, 0])
+    put("QN", [0, 0, 100, 10, 10, 0, 10, 10, 10, 10, 10, 10])
+    side = np.array([1, -1, 1, 1, 1, 1, -1, -1, 1, -1, 1, 1], dtype=float)
+    put("c_ref", side * np.tile([0.2, 0.2, -0.3], 4))
+    pb.mu = 0.75
+    pb.l_leg_max = 0.4
+    pb.f_max = 500.0
+    return pb

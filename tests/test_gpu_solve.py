@@ -181,12 +181,28 @@ def test_device_buffers_and_statuses(solver21):
     torch.cuda.synchronize()  # the library launches on its own stream: device-wide wait
     st_h = st.cpu().numpy()
     assert set(np.unique(st_h)).issubset({0, 1, 2, 3, 4})
-    # the random sweep (v_z down to -6 m/s, body rates, lateral velocity) is much harder than the grid sweep:
-    # the CPU restatement converges on ~30 % of it within 400 iterations; the GPU must do what the CPU does
+    # with the GENERATOR's default parameters (f_max = 200) most of the random drops (v_z down to -6 m/s) are
+    # infeasible: the CPU restatement converges on ~30 % of them; the GPU must do what the CPU does
     c = solve_cpu(21, drops.cpu().numpy(), default_options(max_iter=400))
     assert (st_h == c["status"]).mean() >= 0.9
     assert abs(int((st_h == 0).sum()) - int((c["status"] == 0).sum())) <= 3
     assert torch.isfinite(x[st == 0]).all()
+
+
+def test_random_sweep_with_the_sweep_callers_parameters():
+    """The reference's random sweep (generate_training_data_automated.m:44-102): its own parameter set, N = 30."""
+    from oracle_ip import default_problem
+    N, B = 30, 64
+    drops = lc.random_sweep(B, seed=1)
+    s = lc.LandingSolver(N=N)
+    lc.apply_sweep_parameters(s.problem)
+    r = s.solve(drops)
+    s.close()
+    c = solve_cpu(N, drops, pb=lc.apply_sweep_parameters(default_problem()))
+    assert (r["status"] == 0).mean() >= 0.9 and (c["status"] == 0).mean() >= 0.9
+    both = (r["status"] == 0) & (c["status"] == 0)
+    assert np.max(np.abs(r["f"][both] - c["f"][both])) <= 1e-3
+    assert np.isfinite(r["x"]).all()
 
 
 def test_nan_scenario_does_not_poison_the_batch(solver21):
