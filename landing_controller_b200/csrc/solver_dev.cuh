@@ -299,7 +299,7 @@ __device__ double eval_all(const KParams& P, const Ws& w, const double* x, doubl
 }
 
 struct StepInfo {
-  double a_pr, a_du, dphi_bar, phi_bar, theta;  // barrier parts of dphi / phi, and theta at the current point
+  double a_pr, a_du, dphi_bar, phi_bar, theta;  // barrier part of dphi; -sum of logs and theta at the current point (if asked)
 };
 
 // per-row step recovery for one inequality row: ds, new multiplier, dz, step limits, merit pieces
@@ -316,7 +316,7 @@ __device__ __forceinline__ void row_step(const Ws& w, int idx, double lb, double
     if (ds < 0) si.a_pr = fmin(si.a_pr, -tau * d / ds);
     if (dzl < 0) si.a_du = fmin(si.a_du, -tau * z / dzl);
     si.dphi_bar -= mu * ds / d;
-    si.phi_bar -= mu * log(d);
+    si.phi_bar -= log(d);
   }
   if (isfinite(ub)) {
     const double d = ub - s, z = w.ZU[idx];
@@ -325,7 +325,7 @@ __device__ __forceinline__ void row_step(const Ws& w, int idx, double lb, double
     if (ds > 0) si.a_pr = fmin(si.a_pr, tau * d / ds);
     if (dzu < 0) si.a_du = fmin(si.a_du, -tau * z / dzu);
     si.dphi_bar += mu * ds / d;
-    si.phi_bar -= mu * log(d);
+    si.phi_bar -= log(d);
   }
   w.DS[idx] = ds;
   w.YN[idx] = yn;
@@ -374,30 +374,33 @@ __device__ __forceinline__ void prefetch_rows(const Ws& w, int N, int K, int k, 
   }
 }
 
-// per-row step recovery from shared-memory copies of the row data
+// per-row step recovery from shared-memory copies of the row data.  MERIT: also the pieces of the merit function at the
+// CURRENT point (sum of logs, theta); they are normally carried over from the accepted trial point of the previous
+// iteration (same numbers), so the two logarithms per row are only evaluated after a (re)start.
+template <bool MERIT>
 __device__ __forceinline__ void row_step_sm(const Ws& w, int idx, const double* rb, int rho, double lb, double ub,
                                             double jdx, double mu, double tau, StepInfo& si) {
   const double s = rb[RB_S + rho], rd = rb[RB_G + rho] - s;
   const double ds = jdx + rd;
   double yn = rb[RB_SIG + rho] * ds, dzl = 0.0, dzu = 0.0;
-  si.theta += fabs(rd);
+  if (MERIT) si.theta += fabs(rd);
   if (isfinite(lb)) {
-    const double d = s - lb, z = rb[RB_ZL + rho];
-    yn -= mu / d;
-    dzl = mu / d - z - z / d * ds;
+    const double d = s - lb, z = rb[RB_ZL + rho], id = 1.0 / d, mid = mu * id;
+    yn -= mid;
+    dzl = mid - z - z * id * ds;
     if (ds < 0) si.a_pr = fmin(si.a_pr, -tau * d / ds);
     if (dzl < 0) si.a_du = fmin(si.a_du, -tau * z / dzl);
-    si.dphi_bar -= mu * ds / d;
-    si.phi_bar -= mu * log(d);
+    si.dphi_bar -= mid * ds;
+    if (MERIT) si.phi_bar -= log(d);
   }
   if (isfinite(ub)) {
-    const double d = ub - s, z = rb[RB_ZU + rho];
-    yn += mu / d;
-    dzu = mu / d - z + z / d * ds;
+    const double d = ub - s, z = rb[RB_ZU + rho], id = 1.0 / d, mid = mu * id;
+    yn += mid;
+    dzu = mid - z + z * id * ds;
     if (ds > 0) si.a_pr = fmin(si.a_pr, tau * d / ds);
     if (dzu < 0) si.a_du = fmin(si.a_du, -tau * z / dzu);
-    si.dphi_bar += mu * ds / d;
-    si.phi_bar -= mu * log(d);
+    si.dphi_bar += mid * ds;
+    if (MERIT) si.phi_bar -= log(d);
   }
   w.DS[idx] = ds;
   w.YN[idx] = yn;
@@ -408,6 +411,7 @@ __device__ __forceinline__ void row_step_sm(const Ws& w, int idx, const double* 
 // ds = J_row . dx + (g - s), new multipliers, dz, fraction-to-the-boundary limits, merit pieces.
 // Two knots per round (threads 0-127 / 128-255, one row per thread); the knots' J lists, row data and steps arrive in
 // shared memory through a 4-buffer cp.async ring, so no thread waits on a chain of dependent L2 round trips.
+template <bool MERIT>
 __device__ __noinline__ void row_steps(const KParams& P, const Ws& w, double* smem, const double* tab, const double* drop,
                                        double* red, double mu, double tau, StepInfo& si) {
   const int N = P.N, K = P.K, tid = threadIdx.x, half = tid >> 7, t = tid & 127;
@@ -445,7 +449,7 @@ __device__ __noinline__ void row_steps(const KParams& P, const Ws& w, double* sm
           const int term = t_rterms[p];
           jdx += rb[RB_J + (term & 1023)] * rb[RB_DX + (term >> 10)];  // dc+ is zero at the last knot
         }
-        row_step_sm(w, idx, rb, rho, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
+        row_step_sm<MERIT>(w, idx, rb, rho, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
       }
     }
     __syncthreads();
@@ -457,7 +461,8 @@ __device__ __noinline__ void row_steps(const KParams& P, const Ws& w, double* sm
   si.a_pr = v[0]; si.a_du = v[1]; si.dphi_bar = v[2]; si.phi_bar = v[3]; si.theta = v[4];
 }
 
-// merit function pieces at the trial point (x + a dx, s + a ds) with g(trial) in GT
+// merit function pieces at the trial point (x + a dx, s + a ds) with g(trial) in GT: phi_bar = -sum of logs (times mu
+// gives the barrier part), theta
 __device__ __noinline__ void merit_trial(const KParams& P, const Ws& w, const double* tab, const double* drop,
                                             double* red, double alpha, double mu, double& phi_bar, double& theta) {
   const int K = P.K, MR = P.MR;
@@ -473,8 +478,8 @@ __device__ __noinline__ void merit_trial(const KParams& P, const Ws& w, const do
     const double lb = tab[t], ub = tab[NROWTAB + t];
     const double s = w.S[idx] + alpha * w.DS[idx];
     th += fabs(w.GT[idx] - s);
-    if (isfinite(lb)) ph -= mu * log(s - lb);
-    if (isfinite(ub)) ph -= mu * log(ub - s);
+    if (isfinite(lb)) ph -= log(s - lb);
+    if (isfinite(ub)) ph -= log(ub - s);
   }
   double v[2] = {ph, th};
   const int op[2] = {R_SUM, R_SUM};
@@ -734,6 +739,9 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long
   init_slacks(P, w, tab, mu);
 
   int nfilt = 0, restarts = 0, status = LANDING_ST_MAX_ITER, it = 0, tiny = 0;
+  // merit pieces of the current point, carried over from the accepted trial point (-sum of logs, theta)
+  double slog_cur = 0.0, theta_cur = 0.0;
+  bool have_cur = false;
   double theta0 = -1.0, dw_last = 0.0, viol = 0.0;
   Prof pf{P.prof, 0};
   for (it = 0; it <= opt.max_iter; it++) {
@@ -796,10 +804,16 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long
     costates(P, w);
     pf.lap(PH_FWD);
     StepInfo si;
-    row_steps(P, w, smem, tab, drop, red, mu, tau, si);
+    if (have_cur) {
+      row_steps<false>(P, w, smem, tab, drop, red, mu, tau, si);
+      si.phi_bar = slog_cur;
+      si.theta = theta_cur;
+    } else {
+      row_steps<true>(P, w, smem, tab, drop, red, mu, tau, si);
+    }
     pf.lap(PH_ROWS);
     // filter line search
-    const double theta = si.theta, phi = f + si.phi_bar;
+    const double theta = si.theta, phi = f + mu * si.phi_bar;
     if (theta0 < 0) theta0 = theta;
     const double theta_max = 1e4 * fmax(1.0, theta0), theta_min = 1e-4 * fmax(1.0, theta0);
     double dphi = si.dphi_bar;
@@ -812,16 +826,15 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long
       }
       dphi += bsum(red, d);
     }
-    double alpha = si.a_pr, ft = f;
+    double alpha = si.a_pr, ft = f, phb = 0.0, tht = 0.0;
     bool accepted = false, ftype = false;
     int ls = 0;
     while (alpha > 1e-12 * si.a_pr && ls < 40) {
       for (int i = tid; i < nx; i += NT) w.xt[i] = w.x[i] + alpha * w.dx[i];
       __syncthreads();
       ft = eval_all<false>(P, w, w.xt, w.GT, red);
-      double phb, tht;
       merit_trial(P, w, tab, drop, red, alpha, mu, phb, tht);
-      const double pht = ft + phb;
+      const double pht = ft + mu * phb;
       int filt_ok = 1;
       for (int i = tid; i < nfilt; i += NT)
         if (tht >= w.FT[i] && pht >= w.FP[i]) filt_ok = 0;
@@ -851,6 +864,7 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long
         init_slacks(P, w, tab, mu);
         nfilt = 0;
         theta0 = -1.0;
+        have_cur = false;
         continue;
       }
       status = LANDING_ST_LINESEARCH_FAIL;
@@ -871,6 +885,7 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long
     // accept the trial point
     for (int i = tid; i < nx; i += NT) w.x[i] = w.xt[i];
     f = ft;
+    slog_cur = phb; theta_cur = tht; have_cur = true;
     for (int idx = tid; idx < MR; idx += NT) {
       const int kind = row_kind(idx, K);
       if (kind == ROW_FREE) continue;
