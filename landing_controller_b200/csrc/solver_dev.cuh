@@ -694,7 +694,8 @@ __device__ void build_tables(const KParams& P, double* tab) {
 }
 
 // ---------------------------------------------------------------- one scenario
-__device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long b) {
+__device__ void solve_one(const KParams& P, const Ws& w_slot, double* smem, long long b) {
+  Ws w = w_slot;  // local copy: x / xt and G / GT are swapped instead of copied when a trial point is accepted
   const int N = P.N, K = P.K, nx = P.nx, MR = P.MR, tid = threadIdx.x;
   const landing_options& opt = P.opt;
   const double kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
@@ -882,14 +883,13 @@ __device__ void solve_one(const KParams& P, const Ws& w, double* smem, long long
       if (tid == 0) { w.FT[nfilt] = (1.0 - gamma_theta) * theta; w.FP[nfilt] = phi - gamma_phi * theta; }
       nfilt++;
     }
-    // accept the trial point
-    for (int i = tid; i < nx; i += NT) w.x[i] = w.xt[i];
+    // accept the trial point (x <-> xt, G <-> GT by pointer)
+    { double* t = w.x; w.x = w.xt; w.xt = t; t = w.G; w.G = w.GT; w.GT = t; }
     f = ft;
     slog_cur = phb; theta_cur = tht; have_cur = true;
     for (int idx = tid; idx < MR; idx += NT) {
       const int kind = row_kind(idx, K);
       if (kind == ROW_FREE) continue;
-      w.G[idx] = w.GT[idx];
       const double y = w.Y[idx];
       w.Y[idx] = y + alpha * (w.YN[idx] - y);
       if (kind == ROW_EQ) continue;
