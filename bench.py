@@ -55,7 +55,7 @@ def iter_flops(N):
 
 def scratch_bytes(N, slots):
     K, nx, MR = N - 1, 36 * N - 24, 36 + 104 * (N - 1)
-    n = 3 * nx + 12 * MR + K * (388 + 192) + K * (1152 + 36) + (K + 1) * 312 + 144 + 128
+    n = 3 * nx + 12 * MR + K * (388 + 192 + 480) + K * (1152 + 36) + (K + 1) * 312 + 144 + 128
     return 8 * slots * ((n + 31) // 32 * 32)
 
 
