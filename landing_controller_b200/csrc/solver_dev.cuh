@@ -17,6 +17,7 @@ namespace srb {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+#define TID ((int)threadIdx.x)
 constexpr int NT = 256;          // threads per CTA (= per scenario)
 constexpr int NWARP = NT / 32;
 #ifndef SRB_CTAS
@@ -49,7 +50,7 @@ constexpr int SM_RED = SM_V + V_END;           // block-reduction scratch NWARP 
 constexpr int SM_TAB = SM_RED + NWARP * 8;     // lb[140] ub[140] lbo[140] ubo[140]
 constexpr int TL_WORDS = 296;                  // static tile tables (unsigned short), see sweeps.cuh
 constexpr int SM_TL = SM_TAB + 4 * NROWTAB;
-constexpr int TBL_INTS = 2560;                 // index tables of the sweeps (SolverTables::sm_src)
+constexpr int TBL_INTS = 2392;                 // index tables of the sweeps (SolverTables::sm_src)
 constexpr int SM_TBL = SM_TL + TL_WORDS;
 constexpr int SM_TOTAL = SM_TBL + TBL_INTS / 2;
 static_assert(CTAS_PER_SM * (SM_TOTAL * 8 + 1024) <= 232448, "shared memory budget (227 KB per SM)");
@@ -81,11 +82,11 @@ struct Prof {
   __device__ __forceinline__ void lap(int) {}
   __device__ __forceinline__ void count(int) {}
 #else
-  __device__ __forceinline__ void start() { if (c && threadIdx.x == 0) t = clock64(); }
+  __device__ __forceinline__ void start() { if (c && TID == 0) t = clock64(); }
   __device__ __forceinline__ void lap(int ph) {
-    if (c && threadIdx.x == 0) { const long long n = clock64(); atomicAdd(c + ph, (unsigned long long)(n - t)); t = n; }
+    if (c && TID == 0) { const long long n = clock64(); atomicAdd(c + ph, (unsigned long long)(n - t)); t = n; }
   }
-  __device__ __forceinline__ void count(int ph) { if (c && threadIdx.x == 0) atomicAdd(c + ph, 1ull); }
+  __device__ __forceinline__ void count(int ph) { if (c && TID == 0) atomicAdd(c + ph, 1ull); }
 #endif
 };
 
@@ -130,7 +131,7 @@ __device__ __forceinline__ double rcomb(int op, double a, double b) {
 template <int NQ>
 __device__ __forceinline__ void block_reduce(double* red, double (&v)[NQ], const int (&op)[NQ]) {
   static_assert(NQ <= 8, "reduction scratch holds 8 values per warp");
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = TID & 31, warp = TID >> 5;
 #pragma unroll
   for (int q = 0; q < NQ; q++) {
 #pragma unroll
@@ -230,48 +231,35 @@ __device__ __forceinline__ void load_knot(const KParams& P, const double* x, int
   for (int i = 0; i < 3; i++) { kn.Ib[i] = P.pb.Ib[i]; kn.Ibinv[i] = P.pb.Ib_inv[i]; }
 }
 
+// The LAST knot is evaluated with the interior template too (c+ := 0): its no-slip rows and their entries are
+// never used -- those rows are ROW_FREE (sigma = y = 0 for the whole solve, skipped by every row pass) -- and a
+// second instantiation would run serially in the same warp (divergence) and double the code the warp streams.
 __device__ __noinline__ void eval_knot_j(const KParams& P, const Ws& w, const double* x, double* gout, int k) {
   Knot kn;
   load_knot(P, x, k, kn);
   NoLam nl;
-  if (k == P.K - 1) {
-    JSink<true> s{gout + 36 + RK * k, w.JL + (long long)k * NJ_PAD, P.tab.jl_last};
-    knot_eval<true, true, true, false>(kn, s, nl);
-  } else {
-    JSink<false> s{gout + 36 + RK * k, w.JL + (long long)k * NJ_PAD, nullptr};
-    knot_eval<false, true, true, false>(kn, s, nl);
-  }
+  JSink<false> s{gout + 36 + RK * k, w.JL + (long long)k * NJ_PAD, nullptr};
+  knot_eval<false, true, true, false>(kn, s, nl);
 }
 __device__ __noinline__ void eval_knot_h(const KParams& P, const Ws& w, const double* x, int k) {
   Knot kn;
   load_knot(P, x, k, kn);
-  if (k == P.K - 1) {
-    HSink<true> s{w.HL + (long long)k * NH_PAD, P.tab.hl_last};
-    LamY<true> lam{w.Y + 36 + RK * k};
-    knot_eval<true, false, false, true>(kn, s, lam);
-  } else {
-    HSink<false> s{w.HL + (long long)k * NH_PAD, nullptr};
-    LamY<false> lam{w.Y + 36 + RK * k};
-    knot_eval<false, false, false, true>(kn, s, lam);
-  }
+  HSink<false> s{w.HL + (long long)k * NH_PAD, nullptr};
+  LamY<false> lam{w.Y + 36 + RK * k};
+  knot_eval<false, false, false, true>(kn, s, lam);
 }
 __device__ __noinline__ void eval_knot_g(const KParams& P, const double* x, double* gout, int k) {
   Knot kn;
   load_knot(P, x, k, kn);
   NoLam nl;
-  if (k == P.K - 1) {
-    GSink<true> s{gout + 36 + RK * k};
-    knot_eval<true, true, false, false>(kn, s, nl);
-  } else {
-    GSink<false> s{gout + 36 + RK * k};
-    knot_eval<false, true, false, false>(kn, s, nl);
-  }
+  GSink<false> s{gout + 36 + RK * k};
+  knot_eval<false, true, false, false>(kn, s, nl);
 }
 
 // g(x) (and, when LISTS, the J/H entry lists with multipliers Y) for all knots; returns f(x)
 template <bool LISTS>
 __device__ double eval_all(const KParams& P, const Ws& w, const double* x, double* gout, double* red) {
-  const int N = P.N, K = P.K, tid = threadIdx.x;
+  const int N = P.N, K = P.K, tid = TID;
   if (LISTS) {
     const int part = tid >> 6, t64 = tid & 63;  // warps 0-1: Jacobian lists, warps 4-5: Hessian lists
     if (part == 0) {
@@ -349,8 +337,8 @@ static_assert(RB_SIZE % 2 == 0 && 2 * RB_SIZE <= NW * LDM && RB_SIZE <= LB_REGIO
               "row buffers alias the sweep regions");
 
 __device__ __forceinline__ void prefetch_rows(const Ws& w, int N, int K, int k, double* rb) {
-  // called by 128 threads (t = threadIdx.x & 127) for knot k
-  const int t = threadIdx.x & 127, r0 = 36 + RK * k;
+  // called by 128 threads (t = TID & 127) for knot k
+  const int t = TID & 127, r0 = 36 + RK * k;
   const double* Jk = w.JL + (long long)k * NJ_PAD;
   for (int i = t; i < NJ_PAD / 2; i += 128) cp_async16(rb + RB_J + 2 * i, Jk + 2 * i);
   if (t < RK / 2) {
@@ -414,7 +402,7 @@ __device__ __forceinline__ void row_step_sm(const Ws& w, int idx, const double* 
 template <bool MERIT>
 __device__ __noinline__ void row_steps(const KParams& P, const Ws& w, double* smem, const double* tab, const double* drop,
                                        double* red, double mu, double tau, StepInfo& si) {
-  const int N = P.N, K = P.K, tid = threadIdx.x, half = tid >> 7, t = tid & 127;
+  const int N = P.N, K = P.K, tid = TID, half = tid >> 7, t = tid & 127;
   const int* t_rptr = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_rptr;
   const int* t_rterms = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_rterms;
   si.a_pr = 1.0; si.a_du = 1.0; si.dphi_bar = 0.0; si.phi_bar = 0.0; si.theta = 0.0;
@@ -467,7 +455,7 @@ __device__ __noinline__ void merit_trial(const KParams& P, const Ws& w, const do
                                             double* red, double alpha, double mu, double& phi_bar, double& theta) {
   const int K = P.K, MR = P.MR;
   double ph = 0.0, th = 0.0;
-  for (int idx = threadIdx.x; idx < MR; idx += NT) {
+  for (int idx = TID; idx < MR; idx += NT) {
     const int kind = row_kind(idx, K);
     if (kind == ROW_FREE) continue;
     if (kind == ROW_EQ) {
@@ -498,7 +486,7 @@ __device__ __noinline__ void row_errors(const KParams& P, const Ws& w, const dou
                                            double* red, double mu, Errs& e) {
   const int K = P.K, MR = P.MR;
   double dual = 0, prim = 0, c0 = 0, cmu = 0, ys = 0, zs = 0, viol = 0, nb = 0;
-  for (int idx = threadIdx.x; idx < MR; idx += NT) {
+  for (int idx = TID; idx < MR; idx += NT) {
     const int kind = row_kind(idx, K);
     if (kind == ROW_FREE) continue;
     const double g = w.G[idx], y = w.Y[idx];
@@ -547,7 +535,7 @@ __device__ __noinline__ void row_errors(const KParams& P, const Ws& w, const dou
 __device__ __noinline__ double compl_at(const KParams& P, const Ws& w, const double* tab, double* red, double mu) {
   const int K = P.K, MR = P.MR;
   double cmu = 0;
-  for (int idx = threadIdx.x; idx < MR; idx += NT) {
+  for (int idx = TID; idx < MR; idx += NT) {
     if (row_kind(idx, K) != ROW_INEQ) continue;
     const int t = row_tab(idx);
     const double lb = tab[t], ub = tab[NROWTAB + t], s = w.S[idx];
@@ -560,7 +548,7 @@ __device__ __noinline__ double compl_at(const KParams& P, const Ws& w, const dou
 // yhat = sigma (g - s) - mu/(s-lb) + mu/(ub-s)
 __device__ __noinline__ void row_yhat(const KParams& P, const Ws& w, const double* tab, double mu) {
   const int K = P.K, MR = P.MR;
-  for (int idx = threadIdx.x; idx < MR; idx += NT) {
+  for (int idx = TID; idx < MR; idx += NT) {
     if (row_kind(idx, K) != ROW_INEQ) { w.YH[idx] = 0.0; continue; }
     const int t = row_tab(idx);
     const double lb = tab[t], ub = tab[NROWTAB + t], s = w.S[idx];
@@ -573,7 +561,7 @@ __device__ __noinline__ void row_yhat(const KParams& P, const Ws& w, const doubl
 
 // max |grad f + J' y| (gradient of the Lagrangian w.r.t. x): one (knot, variable) item per thread
 __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const double* smem, double* red) {
-  const int N = P.N, K = P.K, tid = threadIdx.x;
+  const int N = P.N, K = P.K, tid = TID;
   const int* t_cptr = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_cptr;
   const int* t_cterms = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_cterms;
   double dmax = 0.0;
@@ -625,7 +613,7 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
 __device__ __noinline__ void init_slacks(const KParams& P, const Ws& w, const double* tab, double mu) {
   const int K = P.K, MR = P.MR;
   const double bp = P.opt.bound_push, bf = P.opt.bound_frac;
-  for (int idx = threadIdx.x; idx < MR; idx += NT) {
+  for (int idx = TID; idx < MR; idx += NT) {
     w.Y[idx] = 0.0; w.ZL[idx] = 0.0; w.ZU[idx] = 0.0; w.S[idx] = 0.0;
     if (row_kind(idx, K) != ROW_INEQ) continue;
     const int t = row_tab(idx);
@@ -655,7 +643,7 @@ __device__ __noinline__ void init_slacks(const KParams& P, const Ws& w, const do
 __device__ void build_tables(const KParams& P, double* tab) {
   const landing_problem& pb = P.pb;
   const double INF = HUGE_VAL;
-  for (int t = threadIdx.x; t < NROWTAB; t += blockDim.x) {
+  for (int t = TID; t < NROWTAB; t += blockDim.x) {
     double lb = 0.0, ub = 0.0;
     if (t < 12) { lb = ub = 0.0; }
     else if (t < 18) { lb = pb.q_term_min[t - 12]; ub = INF; }
@@ -696,7 +684,7 @@ __device__ void build_tables(const KParams& P, double* tab) {
 // ---------------------------------------------------------------- one scenario
 __device__ void solve_one(const KParams& P, const Ws& w_slot, double* smem, long long b) {
   Ws w = w_slot;  // local copy: x / xt and G / GT are swapped instead of copied when a trial point is accepted
-  const int N = P.N, K = P.K, nx = P.nx, MR = P.MR, tid = threadIdx.x;
+  const int N = P.N, K = P.K, nx = P.nx, MR = P.MR, tid = TID;
   const landing_options& opt = P.opt;
   const double kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
   const double gamma_theta = 1e-5, gamma_phi = 1e-5, eta_phi = 1e-8, s_theta = 1.1, s_phi = 2.3, delta_sw = 1.0;
@@ -944,12 +932,12 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_solve(KParams P) {
   build_tile_tables(reinterpret_cast<unsigned short*>(smem + SM_TL));
   {
     int* tbl = reinterpret_cast<int*>(smem + SM_TBL);
-    for (int i = threadIdx.x; i < P.tab.sm_count; i += NT) tbl[i] = __ldg(P.tab.sm_src + i);
+    for (int i = TID; i < P.tab.sm_count; i += NT) tbl[i] = __ldg(P.tab.sm_src + i);
   }
   __syncthreads();
   const Ws w = carve(P.scratch + (long long)blockIdx.x * P.slot, P.N);
   for (;;) {
-    if (threadIdx.x == 0) s_next = atomicAdd(P.counter, 1);
+    if (TID == 0) s_next = atomicAdd(P.counter, 1);
     __syncthreads();
     const long long b = s_next;
     __syncthreads();

@@ -33,10 +33,12 @@ __host__ __device__ constexpr int ch_off(int b) {
   return o;
 }
 constexpr int TL_COUNT = ch_off(NBLK);
+static_assert(NBLK == 6, "c_ch_off lists the offsets of six block steps");
+__constant__ int c_ch_off[NBLK + 1] = {ch_off(0), ch_off(1), ch_off(2), ch_off(3), ch_off(4), ch_off(5), ch_off(6)};
 static_assert(TL_COUNT <= TL_WORDS * 4, "work table does not fit its shared-memory region");
 
 __device__ void build_tile_tables(unsigned short* tl) {
-  const int tid = threadIdx.x;
+  const int tid = TID;
   if (tid == 0) {
     int n = 0;
     for (int ti = 0; ti < 12; ti++)
@@ -61,7 +63,7 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // stage lists of knot k -> list buffer (asynchronously, 16-byte chunks)
 __device__ __forceinline__ void prefetch_lists(const Ws& w, int k, double* lb) {
-  const int tid = threadIdx.x, rb = 36 + RK * k;
+  const int tid = TID, rb = 36 + RK * k;
   const double* Jk = w.JL + (long long)k * NJ_PAD;
   const double* Hk = w.HL + (long long)k * NH_PAD;
   if (tid < NJ_PAD / 2) cp_async16(lb + LB_J + 2 * tid, Jk + 2 * tid);
@@ -75,18 +77,38 @@ __device__ __forceinline__ void prefetch_lists(const Ws& w, int k, double* lb) {
 // G-column tile (0..11: X,c,f) -> tile index in elimination order
 __device__ __forceinline__ int rot_tile(int t) { return t < 8 ? t + 8 : t - 8; }
 
+// 1/sqrt(e) for a positive, normal e: MUFU.RSQ64H seed (22 bits) + one third-order correction; 52 cycles on the
+// dependent chain instead of the library's 66 (tools/ubench_fp64.cu), max relative error 2.7e-16.
+__device__ __forceinline__ double rsqrt_pos(double a) {
+#ifdef SRB_LIB_RSQRT
+  return rsqrt(a);
+#else
+  double y0;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(a));
+  const double t = a * y0, r = fma(-t, 0.5 * y0, 0.5);
+  const double q = fma(r, 1.5, 1.0), yr = y0 * r;
+  return fma(yr, q, y0);
+#endif
+}
+
 // Blocked partial Cholesky of the lower-stored 48x48 matrix M (+ gradient row qh), 24 pivots.
 // Per block step: (1) the NB x NB diagonal block is factored in registers (right-looking: every pivot hangs on a
 // chain of ~6 FP64 operations) and, fused with it column by column, each panel row (rows below the block; row 48 =
 // gradient) is solved against L_D^T; (2) all threads update the trailing lower triangle.
 // false -> a pivot was not positive (wrong inertia).
-__device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const unsigned short* tl, Prof& pf) {
-  const int tid = threadIdx.x;
+__device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const unsigned short* tl, int* s_bad, Prof& pf) {
+  const int tid = TID;
+#ifdef SRB_CHOL_UNROLL
 #pragma unroll
-  for (int b = 0; b < NBLK; b++) {  // unrolled: the work-table offsets are compile-time constants
+#else
+#pragma unroll 1  // rolled: the unrolled stage loop body (40 KB of code) does not stay in the instruction cache
+#endif
+  for (int b = 0; b < NBLK; b++) {
     const int p0 = NB * b, i0 = p0 + NB;
     double L[NB][NB];
-    {  // every panel thread repeats the small factorisation: cheaper than a broadcast through shared memory
+    if (tid < 64) {
+      // every thread of the two panel warps repeats the small factorisation (cheaper than a broadcast through shared
+      // memory); the other six warps skip it, so the FP64 pipes of their sub-partitions stay free for the co-resident CTA
       double x[NB];
 #pragma unroll
       for (int i = 0; i < NB; i++)
@@ -101,7 +123,7 @@ __device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const un
       for (int j = 0; j < NB; j++) {
         const double e = L[j][j];
         pd = pd && (e > 1e-14);
-        const double r = rsqrt(e);
+        const double r = rsqrt_pos(e);
         L[j][j] = r;  // the diagonal keeps 1/l_jj (what the solves need)
         const double xj = x[j] * r;
         x[j] = xj;
@@ -118,9 +140,10 @@ __device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const un
 #pragma unroll
         for (int j = 0; j < NB; j++) arow[j] = x[j];
       }
-      if (!pd) return false;  // every thread holds the same factor
+      if (!pd && tid == 0) *s_bad = 1;
     }
     __syncthreads();
+    if (*s_bad) return false;  // block-uniform
     pf.lap(PH_C_DIAG);
     if (tid == 63) {  // the block's own factor (nobody reads the diagonal block during the trailing update)
 #pragma unroll
@@ -128,8 +151,13 @@ __device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const un
 #pragma unroll
         for (int j = 0; j <= i; j++) M[(p0 + i) * LDM + p0 + j] = L[i][j];
     }
+#ifdef SRB_CHOL_UNROLL
     const int cnt = ch_count(b);
     const unsigned short* list = tl + ch_off(b);
+#else
+    const int cnt = c_ch_off[b + 1] - c_ch_off[b];
+    const unsigned short* list = tl + c_ch_off[b];
+#endif
     // M[r][c] -= panel_r . panel_c for c in the item's column group, c <= r
     for (int i = tid; i < cnt; i += NT) {
       const int e = list[i], r = e & 255, c0 = i0 + 4 * (e >> 8);
@@ -162,7 +190,7 @@ template <int PENDING> __device__ __forceinline__ void cp_async_wait_group() {
 }
 
 __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double* smem) {
-  const int K = P.K, tid = threadIdx.x;
+  const int K = P.K, tid = TID;
   const int* tbl = reinterpret_cast<const int*>(smem + SM_TBL);
   const SolverTables& tb = P.tab;
   const int* t_g = tbl + tb.o_g;
@@ -229,7 +257,7 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
 
 // condensed data of stage k -> shared memory (asynchronously, 16-byte chunks)
 __device__ __forceinline__ void prefetch_ct(const Ws& w, int k, double* cb) {
-  const int tid = threadIdx.x;
+  const int tid = TID;
   if (tid < CT_STRIDE / 2) cp_async16(cb + 2 * tid, w.CT + (long long)k * CT_STRIDE + 2 * tid);
   cp_async_commit();
 }
@@ -237,7 +265,7 @@ __device__ __forceinline__ void prefetch_ct(const Ws& w, int k, double* cb) {
 // ---------------------------------------------------------------- backward sweep
 // Condenses every stage from the entry lists, factors it and propagates P, p.  false -> not PD.
 __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, double* smem, double dwreg) {
-  const int N = P.N, K = P.K, tid = threadIdx.x;
+  const int N = P.N, K = P.K, tid = TID;
   double* M = smem + SM_M;
   double* Pn = smem + SM_P;
   double* Gs = smem + SM_G;
@@ -246,7 +274,8 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
   const unsigned short* tl = reinterpret_cast<const unsigned short*>(smem + SM_TL);
   const int* tbl = reinterpret_cast<const int*>(smem + SM_TBL);
   const SolverTables& tb = P.tab;
-  __shared__ int s_ok;
+  __shared__ int s_ok, s_bad;
+  if (TID == 0) s_bad = 0;  // (visible after the barriers below)
   const int* t_g = tbl + tb.o_g;
   const int* t_uabh = tbl + tb.o_uabh;
   // this thread's GEMM tile
@@ -375,7 +404,7 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
     __syncthreads();
     pf.lap(PH_B_P4);
     // P5. eliminate the controls
-    if (!partial_cholesky(M, V + V_QH, tl, pf)) {
+    if (!partial_cholesky(M, V + V_QH, tl, &s_bad, pf)) {
       cp_async_wait_all();  // no prefetch may still be in flight when the sweep is retried
       __syncthreads();
       return false;
@@ -437,7 +466,7 @@ constexpr int FB_FY = 0, FB_J = 1152, FB_YV = FB_J + NJ_PAD, FB_R = FB_YV + NS, 
 static_assert(FB_SIZE <= NW * LDM && FB_SIZE <= 2 * 12 * LDG + LB_REGION, "forward buffers alias the backward regions");
 
 __device__ __forceinline__ void prefetch_factors(const Ws& w, int k, double* fb) {
-  const int tid = threadIdx.x;
+  const int tid = TID;
   const double* FY = w.FY + (long long)k * 1152;
   const double* Jk = w.JL + (long long)k * NJ_PAD;
   for (int i = tid; i < 576; i += NT) cp_async16(fb + FB_FY + 2 * i, FY + 2 * i);
@@ -449,7 +478,7 @@ __device__ __forceinline__ void prefetch_factors(const Ws& w, int k, double* fb)
 
 // dx for all stages; equality multipliers of the initial-state rows into YN (dynamics costates: costates())
 __device__ __noinline__ void forward_sweep(const KParams& P, const Ws& w, double* smem, const double* drop) {
-  const int N = P.N, K = P.K, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = P.N, K = P.K, tid = TID, lane = tid & 31, warp = tid >> 5;
   double* fbuf[2] = {smem + SM_M, smem + SM_G};
   double* Pn = smem + SM_P;  // holds P_0 on entry; afterwards the dense G of the current stage
   double* V = smem + SM_V;
@@ -553,7 +582,7 @@ __device__ __noinline__ void forward_sweep(const KParams& P, const Ws& w, double
 // costates = multipliers of the dynamics rows of knot k: -(P_{k+1} [dX_{k+1}; dc_{k+1}] + p_{k+1}), all knots in parallel
 __device__ __noinline__ void costates(const KParams& P, const Ws& w) {
   const int N = P.N, K = P.K;
-  for (int item = threadIdx.x; item < K * 12; item += NT) {
+  for (int item = TID; item < K * 12; item += NT) {
     const int k = item / 12, i = item - k * 12;
     const double* PX = w.PX + (long long)(k + 1) * 288 + i * 24;
     double v = w.PV[(k + 1) * 24 + i];
