@@ -175,6 +175,37 @@ HostTables build_tables_host() {
     }                                                                        \
   } while (0)
 
+// ---------------------------------------------------------------- work-queue order (longest expected first)
+// The scenarios of a sweep need 40 ... 300 interior-point iterations each; with ~300 scenarios in flight the sweep ends
+// when the last long one does, so the queue hands out the scenarios with the largest drop energy g z0 + |v0|^2 / 2
+// first (they tend to need more iterations: correlation 0.2 ... 0.45 on the grid and random sweeps; a late long scenario
+// otherwise leaves the GPU nearly idle for its whole solve).  Rank by counting (O(B^2) comparisons, shared-memory tiles).
+namespace {
+__global__ void __launch_bounds__(256) k_order(const double* __restrict__ drops, long long B, int* __restrict__ order) {
+  __shared__ double tile[256];
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  auto key = [&](long long b) {
+    const double* d = drops + 12 * b;
+    const double k = 9.81 * d[2] + 0.5 * (d[9] * d[9] + d[10] * d[10] + d[11] * d[11]);
+    return k == k ? k : HUGE_VAL;  // NaN input: first in the queue (total order, so the ranks are a permutation)
+  };
+  const double mine = i < B ? key(i) : 0.0;
+  long long rank = 0;
+  for (long long j0 = 0; j0 < B; j0 += 256) {
+    const long long j = j0 + threadIdx.x;
+    __syncthreads();
+    tile[threadIdx.x] = j < B ? key(j) : -HUGE_VAL;
+    __syncthreads();
+    const int n = (int)(B - j0 < 256 ? B - j0 : 256);
+    for (int t = 0; t < n; t++) {
+      const double o = tile[t];
+      rank += (o > mine || (o == mine && j0 + t < i)) ? 1 : 0;
+    }
+  }
+  if (i < B) order[rank] = (int)i;
+}
+}  // namespace
+
 // ---------------------------------------------------------------- FP64 FMA peak (measured, for the roofline)
 namespace {
 __global__ void __launch_bounds__(256) k_fp64_peak(double* out, int iters) {
@@ -226,6 +257,7 @@ void solver_free(SolverWorkspace& ws) {
   if (ws.scratch) cudaFree(ws.scratch);
   if (ws.io) cudaFree(ws.io);
   if (ws.counter) cudaFree(ws.counter);
+  if (ws.order) cudaFree(ws.order);
   if (ws.tab.dev) cudaFree(ws.tab.dev);
   ws = SolverWorkspace{};
 }
@@ -315,6 +347,19 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
   }
   P.prof = d_prof;
   CUS(cudaMemsetAsync(ws.counter, 0, sizeof(int), st));
+  static const bool fifo = getenv("LANDING_FIFO") != nullptr;  // experiments: hand the scenarios out in input order
+  if (!fifo && B > 1) {
+    if ((size_t)B > ws.order_cap) {
+      if (ws.order) cudaFree(ws.order);
+      ws.order = nullptr;
+      ws.order_cap = 0;
+      CUS(cudaMalloc(&ws.order, sizeof(int) * B));
+      ws.order_cap = (size_t)B;
+    }
+    k_order<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(P.drops, B, ws.order);
+    *launches += 1;
+    P.order = ws.order;
+  }
   if (P.lam_g) CUS(cudaMemsetAsync(P.lam_g, 0, sizeof(double) * m * B, st));
   long long gcap = nslots;
   if (const char* e = getenv("LANDING_GRID")) gcap = std::max(1LL, std::min<long long>(nslots, atoll(e)));  // experiments

@@ -69,6 +69,7 @@ struct KParams {
   long long slot;  // doubles per CTA slot
   SolverTables tab;
   unsigned long long* prof;  // optional per-phase cycle counters (LANDING_PROF=1), else nullptr
+  const int* order;          // queue position -> scenario id (nullptr: input order)
 };
 
 // phase ids of the optional cycle profile
@@ -127,41 +128,58 @@ enum { R_SUM = 0, R_MAX = 1, R_MIN = 2 };
 __device__ __forceinline__ double rcomb(int op, double a, double b) {
   return op == R_SUM ? a + b : (op == R_MAX ? fmax(a, b) : fmin(a, b));
 }
-// Reduces NQ quantities over the CTA; every thread returns with the identical results in v[].
-template <int NQ>
-__device__ __forceinline__ void block_reduce(double* red, double (&v)[NQ], const int (&op)[NQ]) {
-  static_assert(NQ <= 8, "reduction scratch holds 8 values per warp");
+// Reduces one quantity over the CTA (shuffles, then the eight warp results serially); every thread returns with
+// the identical result.
+template <int OP>
+__device__ __forceinline__ double block_reduce1(double* red, double v) {
   const int lane = TID & 31, warp = TID >> 5;
 #pragma unroll
-  for (int q = 0; q < NQ; q++) {
+  for (int o = 16; o; o >>= 1) v = rcomb(OP, v, __shfl_xor_sync(FULL, v, o));
+  if (lane == 0) red[warp * 8] = v;
+  __syncthreads();
+  double a = red[0];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) v[q] = rcomb(op[q], v[q], __shfl_xor_sync(FULL, v[q], o));
-  }
-  if (lane == 0) {
+  for (int w2 = 1; w2 < NWARP; w2++) a = rcomb(OP, a, red[w2 * 8]);
+  __syncthreads();
+  return a;
+}
+// Reduces sizeof...(OPS) <= 8 quantities over the CTA: the values are transposed through the (idle) stage-matrix region
+// of shared memory and WARP q reduces quantity q, so the code is one short loop instead of NQ unrolled shuffle
+// trees (1.2k instructions for eight quantities; the kernel is instruction-fetch bound).
+// Every thread returns with the identical results in v[].  `red` = smem + SM_RED.
+template <int... OPS>
+__device__ __forceinline__ void block_reduce(double* red, double (&v)[sizeof...(OPS)]) {
+  constexpr int NQ = sizeof...(OPS);
+  static_assert(NQ <= NWARP && NQ * NT <= NW * LDM, "one warp per quantity; the transpose buffer aliases the stage matrix");
+  double* buf = red - SM_RED + SM_M;
+  const int tid = TID, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
-    for (int q = 0; q < NQ; q++) red[warp * 8 + q] = v[q];
+  for (int q = 0; q < NQ; q++) buf[q * NT + tid] = v[q];
+  __syncthreads();
+  if (warp < NQ) {
+    constexpr int ops[NQ] = {OPS...};
+    int op = ops[0];
+#pragma unroll
+    for (int q = 1; q < NQ; q++) op = (warp == q) ? ops[q] : op;
+    const double* b = buf + warp * NT + lane;
+    double a = b[0];
+#pragma unroll
+    for (int j = 1; j < NT / 32; j++) a = rcomb(op, a, b[32 * j]);
+#pragma unroll 1
+    for (int o = 16; o; o >>= 1) a = rcomb(op, a, __shfl_xor_sync(FULL, a, o));
+    if (lane == 0) red[warp] = a;
   }
   __syncthreads();
 #pragma unroll
-  for (int q = 0; q < NQ; q++) {
-    double a = red[q];
-#pragma unroll
-    for (int w2 = 1; w2 < NWARP; w2++) a = rcomb(op[q], a, red[w2 * 8 + q]);
-    v[q] = a;
-  }
+  for (int q = 0; q < NQ; q++) v[q] = red[q];
   __syncthreads();
 }
-__device__ __forceinline__ double bsum(double* red, double x) {
-  double v[1] = {x};
-  const int op[1] = {R_SUM};
-  block_reduce<1>(red, v, op);
-  return v[0];
+// one copy of each in the kernel (code size: the kernel is instruction-fetch bound)
+__device__ __noinline__ double bsum(double* red, double x) {
+  return block_reduce1<R_SUM>(red, x);
 }
-__device__ __forceinline__ double bmax(double* red, double x) {
-  double v[1] = {x};
-  const int op[1] = {R_MAX};
-  block_reduce<1>(red, v, op);
-  return v[0];
+__device__ __noinline__ double bmax(double* red, double x) {
+  return block_reduce1<R_MAX>(red, x);
 }
 
 // last-knot template row -> interior row numbering
@@ -365,8 +383,7 @@ __device__ __forceinline__ void prefetch_rows(const Ws& w, int N, int K, int k, 
 // per-row step recovery from shared-memory copies of the row data.  MERIT: also the pieces of the merit function at the
 // CURRENT point (sum of logs, theta); they are normally carried over from the accepted trial point of the previous
 // iteration (same numbers), so the two logarithms per row are only evaluated after a (re)start.
-template <bool MERIT>
-__device__ __forceinline__ void row_step_sm(const Ws& w, int idx, const double* rb, int rho, double lb, double ub,
+__device__ __forceinline__ void row_step_sm(const bool MERIT, const Ws& w, int idx, const double* rb, int rho, double lb, double ub,
                                             double jdx, double mu, double tau, StepInfo& si) {
   const double s = rb[RB_S + rho], rd = rb[RB_G + rho] - s;
   const double ds = jdx + rd;
@@ -399,8 +416,7 @@ __device__ __forceinline__ void row_step_sm(const Ws& w, int idx, const double* 
 // ds = J_row . dx + (g - s), new multipliers, dz, fraction-to-the-boundary limits, merit pieces.
 // Two knots per round (threads 0-127 / 128-255, one row per thread); the knots' J lists, row data and steps arrive in
 // shared memory through a 4-buffer cp.async ring, so no thread waits on a chain of dependent L2 round trips.
-template <bool MERIT>
-__device__ __noinline__ void row_steps(const KParams& P, const Ws& w, double* smem, const double* tab, const double* drop,
+__device__ __noinline__ void row_steps(const bool MERIT, const KParams& P, const Ws& w, double* smem, const double* tab, const double* drop,
                                        double* red, double mu, double tau, StepInfo& si) {
   const int N = P.N, K = P.K, tid = TID, half = tid >> 7, t = tid & 127;
   const int* t_rptr = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_rptr;
@@ -437,15 +453,14 @@ __device__ __noinline__ void row_steps(const KParams& P, const Ws& w, double* sm
           const int term = t_rterms[p];
           jdx += rb[RB_J + (term & 1023)] * rb[RB_DX + (term >> 10)];  // dc+ is zero at the last knot
         }
-        row_step_sm<MERIT>(w, idx, rb, rho, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
+        row_step_sm(MERIT, w, idx, rb, rho, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
       }
     }
     __syncthreads();
   }
   cp_async_wait_group<0>();
   double v[5] = {si.a_pr, si.a_du, si.dphi_bar, si.phi_bar, si.theta};
-  const int op[5] = {R_MIN, R_MIN, R_SUM, R_SUM, R_SUM};
-  block_reduce<5>(red, v, op);
+  block_reduce<R_MIN, R_MIN, R_SUM, R_SUM, R_SUM>(red, v);
   si.a_pr = v[0]; si.a_du = v[1]; si.dphi_bar = v[2]; si.phi_bar = v[3]; si.theta = v[4];
 }
 
@@ -470,8 +485,7 @@ __device__ __noinline__ void merit_trial(const KParams& P, const Ws& w, const do
     if (isfinite(ub)) ph -= log(ub - s);
   }
   double v[2] = {ph, th};
-  const int op[2] = {R_SUM, R_SUM};
-  block_reduce<2>(red, v, op);
+  block_reduce<R_SUM, R_SUM>(red, v);
   phi_bar = v[0];
   theta = v[1];
 }
@@ -526,8 +540,7 @@ __device__ __noinline__ void row_errors(const KParams& P, const Ws& w, const dou
     w.SIG[idx] = sg;
   }
   double v[8] = {dual, prim, c0, cmu, ys, zs, viol, nb};
-  const int op[8] = {R_MAX, R_MAX, R_MAX, R_MAX, R_SUM, R_SUM, R_MAX, R_SUM};
-  block_reduce<8>(red, v, op);
+  block_reduce<R_MAX, R_MAX, R_MAX, R_MAX, R_SUM, R_SUM, R_MAX, R_SUM>(red, v);
   e.dual = v[0]; e.prim = v[1]; e.c0 = v[2]; e.cmu = v[3]; e.ysum = v[4]; e.zsum = v[5]; e.viol = v[6];
   e.nzb = (int)(v[7] + 0.5);
 }
@@ -794,11 +807,11 @@ __device__ void solve_one(const KParams& P, const Ws& w_slot, double* smem, long
     pf.lap(PH_FWD);
     StepInfo si;
     if (have_cur) {
-      row_steps<false>(P, w, smem, tab, drop, red, mu, tau, si);
+      row_steps(false, P, w, smem, tab, drop, red, mu, tau, si);
       si.phi_bar = slog_cur;
       si.theta = theta_cur;
     } else {
-      row_steps<true>(P, w, smem, tab, drop, red, mu, tau, si);
+      row_steps(true, P, w, smem, tab, drop, red, mu, tau, si);
     }
     pf.lap(PH_ROWS);
     // filter line search
@@ -937,7 +950,10 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_solve(KParams P) {
   __syncthreads();
   const Ws w = carve(P.scratch + (long long)blockIdx.x * P.slot, P.N);
   for (;;) {
-    if (TID == 0) s_next = atomicAdd(P.counter, 1);
+    if (TID == 0) {
+      const long long q = atomicAdd(P.counter, 1);
+      s_next = (P.order && q < P.B) ? P.order[q] : q;  // queue position -> scenario id
+    }
     __syncthreads();
     const long long b = s_next;
     __syncthreads();
