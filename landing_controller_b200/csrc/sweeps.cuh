@@ -409,24 +409,35 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
       __syncthreads();
       return false;
     }
-    // P6. P_k, p_k, yv and what the forward sweep needs
-    for (int idx = tid; idx < NS * NS; idx += NT) {
-      const int i = idx / NS, j = idx - i * NS, a = i < j ? j : i, b2 = i < j ? i : j;
-      const double v = M[(24 + a) * LDM + 24 + b2];
-      Pn[i * LDP + j] = v;
-      if (i < 12) w.PX[(long long)k * 288 + idx] = v;
-    }
-    if (tid < NS) {
-      V[V_PN + tid] = V[V_QH + 24 + tid];
-      w.PV[k * 24 + tid] = V[V_QH + 24 + tid];
-      w.yvf[k * 24 + tid] = V[V_QH + tid];
-    } else if (tid >= 32 && tid < 44) {
-      w.rf[k * 12 + tid - 32] = V[V_R + tid - 32];
-    }
-    double* FY = w.FY + (long long)k * 1152;
-    for (int idx = tid; idx < 1152; idx += NT) {
-      const int i = idx / NS, j = idx - i * NS;
-      FY[idx] = M[i * LDM + j];  // rows 0-23: L (strict lower, 1/l_ii on the diagonal); rows 24-47: Yt
+    // P6. P_k, p_k, yv and what the forward sweep needs.  Thread (row = tid / 8, three columns from 3 (tid % 8)):
+    // no divisions, every loop fully unrolled, consecutive threads on consecutive addresses.
+    {
+      const int i = tid >> 3, c = 3 * (tid & 7);
+      double* FY = w.FY + (long long)k * 1152;
+      if (i < NS) {  // P_k from the lower triangle of the Schur complement (rows 24..47 of M)
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          const int j = c + d, a = i < j ? j : i, b2 = i < j ? i : j;
+          const double v = M[(24 + a) * LDM + 24 + b2];
+          Pn[i * LDP + j] = v;
+          if (i < 12) w.PX[(long long)k * 288 + i * NS + j] = v;
+        }
+      }
+      // rows 0-23: L (strict lower, 1/l_ii on the diagonal); rows 24-47: Yt
+#pragma unroll
+      for (int d = 0; d < 3; d++) FY[i * NS + c + d] = M[i * LDM + c + d];
+      if (i < 16) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) FY[(32 + i) * NS + c + d] = M[(32 + i) * LDM + c + d];
+      }
+      if (tid >= 224 && tid < 224 + NS) {
+        const int t = tid - 224;
+        V[V_PN + t] = V[V_QH + 24 + t];
+        w.PV[k * 24 + t] = V[V_QH + 24 + t];
+        w.yvf[k * 24 + t] = V[V_QH + t];
+      } else if (tid >= 192 && tid < 204) {
+        w.rf[k * 12 + tid - 192] = V[V_R + tid - 192];
+      }
     }
     pf.lap(PH_B_P6);
   }
