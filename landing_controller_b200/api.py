@@ -204,6 +204,16 @@ class LandingSolver:
         return p, x0
 
     # ---- the solve: one NLP per drop condition ----------------------------------------------
+    def set_flavour(self, name):
+        """Option set of the reference's two serialized solvers: "cold" = landingCtrller_IPOPT
+        (generate_landingCtrller_IPOPT.m:241-242: bound_push = bound_frac = 0.5), "ws" = landingCtrller_IPOPT_ws
+        (generate_landingCtrller_IPOPT_warmstart.m:246-247: 5e-3, called with a previous solution as x0 (:227-230));
+        everything else is identical in the two generators."""
+        v = {"cold": 0.5, "ws": 5e-3}[name]
+        self.options.bound_push = v
+        self.options.bound_frac = v
+        return self
+
     def solve(self, drops, x0=None, want_lam=False, want_lam_p=False):
         """drops: host numpy [B,12] (q_init[6], qd_init[6]). Returns dict of host arrays.
 

@@ -59,3 +59,26 @@ def solve_cpu(N, drops, opt=None, pb=None, threads=0):
                 f=np.array([r.f for r in res]), viol=np.array([r.viol for r in res]),
                 n_factor=np.array([r.n_factor for r in res]), mu=np.array([r.mu for r in res]),
                 dual_inf=np.array([r.dual_inf for r in res]), compl_inf=np.array([r.compl_inf for r in res]))
+
+
+def solve_cpu_x0(N, drops, x0, opt=None, pb=None):
+    """Like solve_cpu, but from the caller's initial guess x0 [B,nx] (the `_ws` flavour of the reference is called with a
+    previous solution: generate_landingCtrller_IPOPT_warmstart.m:227-230). One scenario at a time through ip_solve."""
+    from oracle_lib import Oracle
+    lib = _lib()
+    o = Oracle(N)
+    opt = opt or default_options()
+    pb = pb or default_problem()
+    drops = np.ascontiguousarray(drops, dtype=np.float64)
+    x0 = np.ascontiguousarray(x0, dtype=np.float64)
+    B, nx = drops.shape[0], 36 * N - 24
+    x = np.zeros((B, nx))
+    res = (IpResult * B)()
+    for b in range(B):
+        p, _ = o.build_p_x0(pb, drops[b, :6], drops[b, 6:])
+        p = np.ascontiguousarray(p)
+        rc = lib.ip_solve(o.plan, _dp(p), _dp(x0[b]), ctypes.byref(opt), _dp(x[b]), None,
+                          ctypes.byref(res[b]))
+        assert rc == 0
+    return dict(x=x, status=np.array([r.status for r in res]), iters=np.array([r.iters for r in res]),
+                f=np.array([r.f for r in res]), viol=np.array([r.viol for r in res]))

@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 
 import landing_controller_b200 as lc
-from oracle_ip import default_options, solve_cpu
+from oracle_ip import default_options, solve_cpu, solve_cpu_x0
 from oracle_lib import Oracle
 
 pytestmark = pytest.mark.gpu
@@ -213,3 +213,34 @@ def test_nan_scenario_does_not_poison_the_batch(solver21):
     assert r["status"][3] in (1, 2, 3, 4)
     ok = np.delete(np.arange(8), 3)
     assert np.all(np.isfinite(r["x"][ok]))
+
+
+def test_warm_start_flavour_matches_cpu_restatement():
+    """landingCtrller_IPOPT_ws (generate_landingCtrller_IPOPT_warmstart.m:227-230,246-247): bound_push = bound_frac =
+    5e-3 and x0 = the solution of the previous drop of the sweep.  Same iterates as the CPU restatement after a fixed
+    number of iterations; converged: same cost as a cold solve, in fewer iterations."""
+    N = 21
+    drops = lc.grid_sweep(1024)[[100, 613, 900]]
+    near = drops.copy()
+    near[:, 9] += 0.05
+    s = lc.LandingSolver(N=N)
+    cold = s.solve(drops)
+    assert (cold["status"] == 0).all()
+    x0 = cold["x"].copy()
+    x0[:, :12] = near
+    s.set_flavour("ws")
+    ws = default_options(bound_push=5e-3, bound_frac=5e-3)
+    for iters in (1, 4):
+        s.options.max_iter = iters
+        ws.max_iter = iters
+        g = s.solve(near, x0=x0)
+        c = solve_cpu_x0(N, near, x0, opt=ws)
+        assert np.max(np.abs(g["x"] - c["x"])) <= 1e-9 * max(1.0, np.max(np.abs(c["x"])))
+    s.options.max_iter = 3000
+    warm = s.solve(near, x0=x0)
+    s.set_flavour("cold")
+    ref = s.solve(near)
+    s.close()
+    assert (warm["status"] == 0).all() and (ref["status"] == 0).all()
+    assert np.max(np.abs(warm["f"] - ref["f"])) <= 1e-4
+    assert warm["iters"].sum() < ref["iters"].sum()

@@ -2,7 +2,7 @@
 import numpy as np
 
 import landing_controller_b200 as lc
-from oracle_ip import default_options, default_problem, solve_cpu
+from oracle_ip import default_options, default_problem, solve_cpu, solve_cpu_x0
 from oracle_lib import Oracle
 
 
@@ -47,3 +47,23 @@ def test_small_sweep_converges_and_is_deterministic():
     b = solve_cpu(21, d, default_options(max_iter=1500), threads=2)
     assert (a["status"] == 0).mean() >= 0.9
     assert np.array_equal(a["x"], b["x"]) and np.array_equal(a["iters"], b["iters"])
+
+
+def test_warm_start_flavour_restarts_from_a_previous_solution():
+    """landingCtrller_IPOPT_ws: same NLP, bound_push = bound_frac = 5e-3, x0 = a previous solution
+    (generate_landingCtrller_IPOPT_warmstart.m:227-230,246-247). From the cold solution of a neighbouring drop the
+    solve converges again, in fewer iterations than from the reference guess, to the same cost."""
+    N = 21
+    drops = lc.grid_sweep(1024)[[100, 613]]
+    cold = solve_cpu(N, drops)
+    assert (cold["status"] == 0).all()
+    near = drops.copy()
+    near[:, 9] += 0.05  # the next drop of a sweep: 5 cm/s more forward velocity
+    ws = default_options(bound_push=5e-3, bound_frac=5e-3)
+    x0 = cold["x"].copy()
+    x0[:, :12] = near  # (the initial-state rows pin X_0 to the new drop)
+    warm = solve_cpu_x0(N, near, x0, opt=ws)
+    ref = solve_cpu(N, near)
+    assert (warm["status"] == 0).all() and (ref["status"] == 0).all()
+    assert np.max(np.abs(warm["f"] - ref["f"])) <= 1e-4
+    assert warm["iters"].sum() < ref["iters"].sum()
