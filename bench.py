@@ -34,7 +34,9 @@ UNIT = "NLP/s"
 def workload(n_gpus, rank, batch):
     import landing_controller_b200 as lc
     allb = lc.grid_sweep(batch * n_gpus)
-    return allb[rank * batch:(rank + 1) * batch].copy()
+    # interleaved shards: the iteration count grows along the axes of the grid, contiguous blocks would give the last
+    # rank the hard end of the sweep
+    return allb[lc.shard_indices(batch * n_gpus, n_gpus, rank, "interleaved")].copy()
 
 
 def iter_bytes(N):
@@ -302,7 +304,8 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": "SRB landing sweep, %d grid drop conditions per GPU (height x pitch x roll x v_x, v_z=-3), N=%d knots"
                        % (B, N), "knots": N, "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": "scenario-sharded x%d, one all-gather of results" % world,
+                       "parallelism": "scenario-sharded x%d (interleaved shards of the %d-scenario grid), one all-gather of results"
+                                      % (world, B * world),
                        "l2": "per-scenario solver scratch of the 296 resident CTAs (%.2f GB) exceeds the 126 MB L2 and "
                              "every step rewrites all of it; no flush needed" % (1e-9 * scratch_bytes(N, 296)),
                        "options": "tol 1e-4, constr_viol_tol 1e-3, max_iter 3000 (generate_landingCtrller_IPOPT.m:232-236)"},

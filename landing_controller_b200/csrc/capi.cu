@@ -174,6 +174,7 @@ void landing_options_default(landing_options* o) {
   o->bound_relax_factor = 1e-6;
   o->max_soc = 4;
   o->jam_iters = 5;
+  o->max_restarts = 8;
   o->jam_alpha = 0.02;
 }
 

@@ -857,10 +857,10 @@ __device__ void solve_one(const KParams& P, const Ws& w_slot, double* smem, long
     // watchdog against jamming at the fraction-to-the-boundary rule: a run of tiny accepted steps is treated like a
     // failed line search (ip_ref.c)
     if (accepted) tiny = (alpha < opt.jam_alpha) ? tiny + 1 : 0;
-    if (accepted && opt.jam_iters > 0 && tiny >= opt.jam_iters && restarts < 20) accepted = false;
+    if (accepted && opt.jam_iters > 0 && tiny >= opt.jam_iters && restarts < opt.max_restarts) accepted = false;
     if (!accepted) {
       tiny = 0;
-      if (restarts < 20) {  // re-centre: slacks back inside their bounds, multipliers reset, mu = mu_init
+      if (restarts < opt.max_restarts) {  // re-centre: slacks back inside their bounds, multipliers reset, mu = mu_init
         restarts++;
         mu = opt.mu_init;
         init_slacks(P, w, tab, mu);

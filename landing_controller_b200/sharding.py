@@ -1,4 +1,5 @@
-"""Scenario sharding for multi-GPU sweeps: contiguous blocks of the sweep per rank,
+"""Scenario sharding for multi-GPU sweeps: contiguous blocks of the sweep per rank or -- to equalise
+difficulty, the iteration count grows along the axes of a grid sweep -- interleaved (rank r takes scenarios r, r+G, ...);
 no data-path collective, ONE all-gather of the per-scenario result records at the end."""
 import numpy as np
 
@@ -8,6 +9,22 @@ def shard_bounds(n_scenarios, world, rank):
     base, rem = divmod(n_scenarios, world)
     lo = rank * base + min(rank, rem)
     return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_indices(n_scenarios, world, rank, mode="interleaved"):
+    """Global scenario ids of rank `rank`: "interleaved" (rank, rank+world, ...) or "block" (shard_bounds)."""
+    if mode == "block":
+        lo, hi = shard_bounds(n_scenarios, world, rank)
+        return np.arange(lo, hi)
+    if mode != "interleaved":
+        raise ValueError("mode must be 'interleaved' or 'block'")
+    return np.arange(rank, n_scenarios, world)
+
+
+def unshard_order(n_scenarios, world, mode="interleaved"):
+    """Permutation that puts the rank-major concatenation of all shards back into global scenario order:
+    full[unshard_order] = concatenated."""
+    return np.concatenate([shard_indices(n_scenarios, world, r, mode) for r in range(world)])
 
 
 def pack_records(x, f, status, iters):
@@ -25,11 +42,12 @@ def unpack_records(rec):
     return dict(x=rec[:, :-3], f=rec[:, -3], status=rec[:, -2].astype(np.int32), iters=rec[:, -1].astype(np.int32))
 
 
-def gather_records(rec_local, n_scenarios, world, rank):
-    """All-gather ragged shards with torch.distributed (any backend): pads to the largest shard."""
+def gather_records(rec_local, n_scenarios, world, rank, mode="block"):
+    """All-gather ragged shards with torch.distributed (any backend): pads to the largest shard; the result is in
+    global scenario order for either sharding mode."""
     import torch
     import torch.distributed as dist
-    sizes = [shard_bounds(n_scenarios, world, r) for r in range(world)]
+    sizes = [(0, len(shard_indices(n_scenarios, world, r, mode))) for r in range(world)]
     mx = max(hi - lo for lo, hi in sizes)
     dev = rec_local.device if isinstance(rec_local, torch.Tensor) else None
     t = rec_local if isinstance(rec_local, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rec_local))
@@ -38,4 +56,9 @@ def gather_records(rec_local, n_scenarios, world, rank):
     out = torch.zeros(world * mx, t.shape[1], dtype=t.dtype, device=dev)
     dist.all_gather_into_tensor(out, pad)
     parts = [out[r * mx:r * mx + (hi - lo)] for r, (lo, hi) in enumerate(sizes)]
-    return torch.cat(parts, dim=0)
+    cat = torch.cat(parts, dim=0)
+    if mode == "block":
+        return cat
+    full = torch.empty_like(cat)
+    full[torch.from_numpy(unshard_order(n_scenarios, world, mode)).to(cat.device)] = cat
+    return full

@@ -41,6 +41,7 @@ void ip_options_default(ip_options *o) {
   o->verbose = 0;
   o->jam_alpha = 0.02;
   o->jam_iters = 5;
+  o->max_restarts = 8;
 }
 
 typedef struct {
@@ -544,7 +545,7 @@ static int ip_solve_ws(ipws *w, const double *p, const double *x0, const ip_opti
     const double s_d = fmax(s_max, (ysum + zsum) / (double)(m + nzb)) / s_max;
     const double s_c = fmax(s_max, zsum / (double)(nzb > 0 ? nzb : 1)) / s_max;
     const double E0 = fmax(fmax(err[0] / s_d, err[1]), err[2] / s_c);
-    res->dual_inf = err[0]; res->compl_inf = err[2]; res->mu = mu;
+    res->dual_inf = err[0]; res->compl_inf = err[2]; res->mu = mu; res->restarts = restarts;
     /* constraint violation w.r.t. the original bounds */
     double viol = 0;
     for (int i = 0; i < m; i++) viol = fmax(viol, fmax(w->lbo[i] - w->g[i], w->g[i] - w->ubo[i]));
@@ -657,18 +658,18 @@ static int ip_solve_ws(ipws *w, const double *p, const double *x0, const ip_opti
     /* watchdog against jamming at the fraction-to-the-boundary rule: a run of tiny accepted steps is treated like
      * a failed line search (IPOPT would leave such a phase through its restoration phase) */
     if (accepted) tiny = (alpha < opt->jam_alpha) ? tiny + 1 : 0;
-    if (accepted && opt->jam_iters > 0 && tiny >= opt->jam_iters && restarts < 20) { accepted = 0; }
+    if (accepted && opt->jam_iters > 0 && tiny >= opt->jam_iters && restarts < opt->max_restarts) { accepted = 0; }
     if (!accepted) {
       tiny = 0;
       /* no restoration phase: re-centre instead -- slacks pushed back inside their bounds at the
        * current x, multipliers reset, barrier parameter back to mu_init, filter cleared */
-      if (restarts < 20) {
+      if (restarts < opt->max_restarts) {
         restarts++;
         mu = opt->mu_init;
         init_slacks(w, opt, mu);
         w->nfilt = 0;
         theta0 = -1;
-        if (opt->verbose) printf("   -- line search failed: restart %d\n", restarts);
+        if (opt->verbose) printf("   -- line search failed: restart %d (theta %.6e, it %d)\n", restarts, theta, it);
         continue;
       }
       status = 2;

@@ -28,6 +28,7 @@ typedef struct ip_options {
   int verbose;
   double jam_alpha; /* watchdog: accepted primal step below this ... */
   int jam_iters;    /* ... for this many consecutive iterations -> re-centre (0 = off) */
+  int max_restarts; /* re-centrings allowed per scenario */
 } ip_options;
 
 typedef struct ip_result {
@@ -35,6 +36,7 @@ typedef struct ip_result {
   int iters;
   int n_factor; /* Riccati factorisations (incl. inertia-correction retries) */
   double f, viol, dual_inf, compl_inf, mu;
+  int restarts; /* re-centrings (failed line searches / jamming watchdog) */
 } ip_result;
 
 void ip_options_default(ip_options *o);

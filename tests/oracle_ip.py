@@ -12,13 +12,13 @@ class IpOptions(ctypes.Structure):
                 ("dual_inf_tol", ctypes.c_double), ("compl_inf_tol", ctypes.c_double),
                 ("mu_init", ctypes.c_double), ("bound_push", ctypes.c_double), ("bound_frac", ctypes.c_double),
                 ("bound_relax_factor", ctypes.c_double), ("max_soc", ctypes.c_int), ("verbose", ctypes.c_int),
-                ("jam_alpha", ctypes.c_double), ("jam_iters", ctypes.c_int)]
+                ("jam_alpha", ctypes.c_double), ("jam_iters", ctypes.c_int), ("max_restarts", ctypes.c_int)]
 
 
 class IpResult(ctypes.Structure):
     _fields_ = [("status", ctypes.c_int), ("iters", ctypes.c_int), ("n_factor", ctypes.c_int),
                 ("f", ctypes.c_double), ("viol", ctypes.c_double), ("dual_inf", ctypes.c_double),
-                ("compl_inf", ctypes.c_double), ("mu", ctypes.c_double)]
+                ("compl_inf", ctypes.c_double), ("mu", ctypes.c_double), ("restarts", ctypes.c_int)]
 
 
 def _lib():
@@ -58,7 +58,8 @@ def solve_cpu(N, drops, opt=None, pb=None, threads=0):
     return dict(x=x, status=np.array([r.status for r in res]), iters=np.array([r.iters for r in res]),
                 f=np.array([r.f for r in res]), viol=np.array([r.viol for r in res]),
                 n_factor=np.array([r.n_factor for r in res]), mu=np.array([r.mu for r in res]),
-                dual_inf=np.array([r.dual_inf for r in res]), compl_inf=np.array([r.compl_inf for r in res]))
+                dual_inf=np.array([r.dual_inf for r in res]), compl_inf=np.array([r.compl_inf for r in res]),
+                restarts=np.array([r.restarts for r in res]))
 
 
 def solve_cpu_x0(N, drops, x0, opt=None, pb=None):

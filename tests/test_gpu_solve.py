@@ -220,7 +220,7 @@ def test_warm_start_flavour_matches_cpu_restatement():
     5e-3 and x0 = the solution of the previous drop of the sweep.  Same iterates as the CPU restatement after a fixed
     number of iterations; converged: same cost as a cold solve, in fewer iterations."""
     N = 21
-    drops = lc.grid_sweep(1024)[[100, 613, 900]]
+    drops = lc.grid_sweep(1024)[[100, 613, 300]]
     near = drops.copy()
     near[:, 9] += 0.05
     s = lc.LandingSolver(N=N)

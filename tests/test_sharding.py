@@ -30,29 +30,46 @@ def test_grid_sweep_shapes():
     assert np.array_equal(r, lc.random_sweep(100, seed=0)) and r[:, 2].min() > 0.35
 
 
-def _worker(rank, world, port, n, nx, q):
+def test_interleaved_shards_partition_the_sweep():
+    for n in (1, 7, 1024, 1000):
+        for w in (1, 2, 4, 8):
+            ids = [lc.shard_indices(n, w, r) for r in range(w)]
+            assert np.array_equal(np.sort(np.concatenate(ids)), np.arange(n))
+            assert max(map(len, ids)) - min(map(len, ids)) <= 1
+            assert np.array_equal(lc.shard_indices(n, w, 0, "block"), np.arange(*lc.shard_bounds(n, w, 0)))
+            order = lc.unshard_order(n, w)
+            full = np.empty(n)
+            full[order] = np.concatenate([i.astype(float) for i in ids])
+            assert np.array_equal(full, np.arange(n))
+
+
+def _worker(rank, world, port, n, nx, q, mode="block"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     drops = lc.grid_sweep(1024)[:n]
-    lo, hi = lc.shard_bounds(n, world, rank)
-    mine = drops[lo:hi]
+    ids = lc.shard_indices(n, world, rank, mode)
+    mine = drops[ids]
     # stand-in for the GPU solve: a deterministic function of the drop condition
     x = np.repeat(mine[:, :1] + mine[:, 2:3] * 10 + mine[:, 4:5] * 100 + mine[:, 9:10] * 1000, nx, axis=1)
-    rec = lc.pack_records(x, mine[:, 2], np.arange(lo, hi) % 3, np.arange(lo, hi))
-    full = lc.gather_records(rec, n, world, rank).numpy()
+    rec = lc.pack_records(x, mine[:, 2], ids % 3, ids)
+    full = lc.gather_records(rec, n, world, rank, mode).numpy()
     if rank == 0:
         q.put(full)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_all_gather_of_records_world2_gloo():
+import pytest
+
+
+@pytest.mark.parametrize("mode", ["block", "interleaved"])
+def test_all_gather_of_records_world2_gloo(mode):
     n, nx, world = 37, 5, 2  # ragged on purpose
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, nx, q)) for r in range(world)]
+    port = 29500 + (os.getpid() % 2000) + (7 if mode == "block" else 0)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, nx, q, mode)) for r in range(world)]
     for p in procs:
         p.start()
     full = q.get(timeout=120)
