@@ -328,6 +328,15 @@ def main():
                                  "iteration of one scenario; the kernel is FP64-latency bound (DESIGN.md 2.3), the hbm "
                                  "line uses the algorithmic bytes of SURVEY 8d-ii, the fp64 line the algorithmic flops"},
         }
+        # the evaluation kernels (HBM-bound rows a-3..a-5 of SURVEY 8): 16k scenarios, SoA, a few milliseconds
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            from bench_eval import measure
+            line["roofline"]["eval_kernels"] = [
+                {k: r[k] for k in ("function", "N", "B", "layout", "ms", "achieved", "peak", "unit", "frac")}
+                for r in measure(N, 16384, 10, "soa", solver=solver, device=local_rank)]
+        except Exception as e:  # reported, never hidden
+            line["roofline"]["eval_kernels"] = {"error": repr(e)}
         # CPU baseline on the host cores (bounded sample of the same workload)
         cores = os.cpu_count() or 1
         ns = args.cpu_sample or B  # default: the whole sweep of rank 0 (about 10 s on 16 host threads)

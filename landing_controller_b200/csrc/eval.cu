@@ -70,13 +70,65 @@ struct GradSink {  // acc[var] += lam[row] * dg_row/dvar  (J^T lam, knot-local)
   __device__ __forceinline__ void h(int, int, int, double) {}
 };
 
-template <bool WG, bool WJ, bool WH>
-__global__ void __launch_bounds__(TPB) k_eval(EvalArgs a) {
+// ---- the knot's entries are dealt to NPART threads (blockIdx.z): every thread runs the same knot template behind a
+// compile-time filter, so the compiler drops whatever feeds only other parts' entries.  One thread per knot needs
+// 255 registers + 1-2 kB of spills and leaves 8 warps per SM; a quarter of the entries per thread fits the register
+// file and puts four times as many store streams in flight (the kernels are HBM-write bound).
+template <bool LAST> __device__ constexpr int leg_of_row(int row) {  // -1: not a per-leg row
+  using RW = Rows<LAST>;
+  if (row >= 12 && row < 16) return row - 12;
+  if (row >= 16 && row < RW::fric) return (row - 16) / (LAST ? 6 : 12);
+  if (row >= RW::fric && row < RW::state) return (row - RW::fric) & 3;
+  return -1;
+}
+__device__ constexpr int leg_of_var(int var) {  // X 0-11 | c 12-23 | f 24-35 | X+ 36-47 | c+ 48-59
+  if (var >= 12 && var < 36) return ((var - 12) % 12) / 3;
+  if (var >= 48) return (var - 48) / 3;
+  return -1;
+}
+template <bool LAST> __device__ constexpr int g_owner(int row) {
+  const int l = leg_of_row<LAST>(row);
+  return l >= 0 ? l : (row & 3);
+}
+template <bool LAST> __device__ constexpr int j_owner(int row, int var) {
+  const int lv = leg_of_var(var);
+  return lv >= 0 ? lv : g_owner<LAST>(row);
+}
+__device__ constexpr int h_owner(int e, int va, int vb) {
+  const int la = leg_of_var(va), lb = leg_of_var(vb);
+  return la >= 0 ? la : (lb >= 0 ? lb : (e & 3));
+}
+template <int PART, int NP, bool LAST> struct PartSink {  // NP = 1: everything; 2: legs {0,2} | {1,3}; 4: one leg each
+  ScatterSink& s;
+  __device__ __forceinline__ void g(int row, double v) { if (g_owner<LAST>(row) % NP == PART) s.g(row, v); }
+  __device__ __forceinline__ void j(int e, int row, int var, double v) { if (j_owner<LAST>(row, var) % NP == PART) s.j(e, row, var, v); }
+  __device__ __forceinline__ void h(int e, int va, int vb, double v) { if (h_owner(e, va, vb) % NP == PART) s.h(e, va, vb, v); }
+};
+template <int PART, int NP, bool WG, bool WJ, bool WH>
+__device__ __forceinline__ void eval_part(const Knot& kn, ScatterSink& s, const LamRow& lam, bool last) {
+  if (last) {
+    PartSink<PART, NP, true> ps{s};
+    knot_eval<true, WG, WJ, WH>(kn, ps, lam);
+  } else {
+    PartSink<PART, NP, false> ps{s};
+    knot_eval<false, WG, WJ, WH>(kn, ps, lam);
+  }
+}
+
+// Measured on B200 (tools/bench_eval.py, 16k scenarios, SoA): the Jacobian kernels gain from the split (59 % -> 75 % of
+// the measured HBM copy bandwidth with four parts at 168 registers); nlp_g and nlp_hess_l lose (their loads of x and of
+// the multipliers are repeated per part) and keep one thread per knot (88 % / 79 %).
+#ifndef EVAL_NP_J
+#define EVAL_NP_J 4
+#endif
+template <bool WG, bool WJ, bool WH, int NP>
+__global__ void __launch_bounds__(TPB, NP > 1 ? 3 : 1) k_eval(EvalArgs a) {
   const long long b = (long long)blockIdx.x * TPB + threadIdx.x;
   const int k = blockIdx.y + a.k0, N = a.pl.N;
   if (b >= a.B) return;
   bool bad = false;
   if (k == N - 1) {
+    if (blockIdx.z != 0) return;
     // ---- boundary slice: rows 0-35 (generate_landingCtrller_IPOPT.m:90-97), objective (:83-85)
     const int xo = 12 * (N - 1);
     if (WG) {
@@ -116,10 +168,19 @@ __global__ void __launch_bounds__(TPB) k_eval(EvalArgs a) {
     load_knot(a, k, b, kn, last);
     ScatterSink s{a, b, 36 + 104 * k, a.pl.jmap + k * NJ_INT, a.pl.hmap + k * NH_INT, false};
     LamRow lam{a.lam_g, b, 36 + 104 * k};
-    if (last)
-      knot_eval<true, WG, WJ, WH>(kn, s, lam);
-    else
-      knot_eval<false, WG, WJ, WH>(kn, s, lam);
+    if (NP == 1) {
+      eval_part<0, 1, WG, WJ, WH>(kn, s, lam, last);
+    } else if (NP == 2) {
+      if (blockIdx.z == 0) eval_part<0, 2, WG, WJ, WH>(kn, s, lam, last);  // (block-uniform)
+      else eval_part<1, 2, WG, WJ, WH>(kn, s, lam, last);
+    } else {
+      switch (blockIdx.z) {
+        case 0: eval_part<0, NP, WG, WJ, WH>(kn, s, lam, last); break;
+        case 1: eval_part<1 % NP, NP, WG, WJ, WH>(kn, s, lam, last); break;
+        case 2: eval_part<2 % NP, NP, WG, WJ, WH>(kn, s, lam, last); break;
+        default: eval_part<3 % NP, NP, WG, WJ, WH>(kn, s, lam, last); break;
+      }
+    }
     bad = s.bad;
   }
   if (bad && a.status) a.status[b] = -1;
@@ -332,19 +393,22 @@ int launch_eval(const EvalArgs& a, cudaStream_t st) {
     // one fused launch per requested output combination (nlp_jac_g returns g and jac together)
     EvalArgs c = a;
     dim3 gr = grid;
+    constexpr int NPJ = EVAL_NP_J;
+    if (wj && !wh) gr.z = NPJ;
     switch ((wg ? 1 : 0) | (wj ? 2 : 0) | (wh ? 4 : 0)) {
       case 0:  // f / grad_f only: just the boundary slice
         c.k0 = a.pl.N - 1;
         gr.y = 1;
-        k_eval<false, false, false><<<gr, TPB, 0, st>>>(c);
+        gr.z = 1;
+        k_eval<false, false, false, 1><<<gr, TPB, 0, st>>>(c);
         break;
-      case 1: k_eval<true, false, false><<<gr, TPB, 0, st>>>(c); break;
-      case 2: k_eval<false, true, false><<<gr, TPB, 0, st>>>(c); break;
-      case 3: k_eval<true, true, false><<<gr, TPB, 0, st>>>(c); break;
-      case 4: k_eval<false, false, true><<<gr, TPB, 0, st>>>(c); break;
-      case 5: k_eval<true, false, true><<<gr, TPB, 0, st>>>(c); break;
-      case 6: k_eval<false, true, true><<<gr, TPB, 0, st>>>(c); break;
-      default: k_eval<true, true, true><<<gr, TPB, 0, st>>>(c); break;
+      case 1: k_eval<true, false, false, 1><<<gr, TPB, 0, st>>>(c); break;
+      case 2: k_eval<false, true, false, NPJ><<<gr, TPB, 0, st>>>(c); break;
+      case 3: k_eval<true, true, false, NPJ><<<gr, TPB, 0, st>>>(c); break;
+      case 4: k_eval<false, false, true, 1><<<gr, TPB, 0, st>>>(c); break;
+      case 5: k_eval<true, false, true, 1><<<gr, TPB, 0, st>>>(c); break;
+      case 6: k_eval<false, true, true, 1><<<gr, TPB, 0, st>>>(c); break;
+      default: k_eval<true, true, true, 1><<<gr, TPB, 0, st>>>(c); break;
     }
     launches++;
   }

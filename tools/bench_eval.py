@@ -1,0 +1,77 @@
+"""Roofline check of the batched evaluation kernels: nlp_g, nlp_jac_g, nlp_hess_l on B scenarios,
+device buffers; algorithmic bytes = 8 * (inputs read + outputs written) per scenario, against the measured HBM copy
+bandwidth (MEASURED_PEAKS.json).
+   usage: python tools/bench_eval.py [N] [B] [reps] [soa|aos]        (prints one JSON line per function)"""
+import ctypes
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measure(N=30, B=16384, reps=20, layout="soa", solver=None, device=0):
+    import numpy as np
+    import torch
+    import landing_controller_b200 as lc
+    s = solver or lc.LandingSolver(N=N, device=device, lib_path=os.environ.get("LANDING_LIB", lc.api.LIB_PATH))
+    LAYOUT = lc.SOA if layout == "soa" else lc.AOS
+    d = s.dims
+    dev = torch.device("cuda", device)
+    drops = torch.tensor(np.ascontiguousarray(np.vstack([lc.grid_sweep(1024)] * ((B + 1023) // 1024))[:B]), device=dev)
+    shape = (lambda n: (n, B)) if LAYOUT == lc.SOA else (lambda n: (B, n))
+    z = lambda n: torch.zeros(*shape(n), dtype=torch.float64, device=dev)
+    p, x = z(d["np"]), z(d["nx"])
+    s._check(s.lib.landing_build_batch(s.ctx, B, lc.DEVICE, LAYOUT, ctypes.byref(s.problem), lc.api._ptr(drops),
+                                       lc.api._ptr(p), lc.api._ptr(x)), "landing_build_batch")
+    torch.cuda.synchronize()
+    x += 0.01 * torch.randn_like(x)
+    lam_g = torch.randn(*shape(d["m"]), dtype=torch.float64, device=dev)
+    lam_f = torch.ones(B, dtype=torch.float64, device=dev)
+    g, J, H = z(d["m"]), z(d["nnzJ"]), z(d["nnzH"])
+    peak, peak_src = hbm_peak()
+    stream = torch.cuda.ExternalStream(s.stream_ptr, device=dev)
+    cases = {
+        "nlp_g": (dict(x=x, p=p, g=g), d["nx"] + d["np"] + d["m"]),
+        "nlp_jac_g": (dict(x=x, p=p, g=g, jac=J), d["nx"] + d["np"] + d["m"] + d["nnzJ"]),
+        "nlp_hess_l": (dict(x=x, p=p, lam_f=lam_f, lam_g=lam_g, hess=H), d["nx"] + d["np"] + 1 + d["m"] + d["nnzH"]),
+    }
+    out = []
+    torch.cuda.synchronize()
+    for name, (kw, words) in cases.items():
+        for _ in range(3):
+            s.eval(B, lc.DEVICE, LAYOUT, **kw)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = s.launches
+        with torch.cuda.stream(stream):
+            e0.record()
+        for _ in range(reps):
+            s.eval(B, lc.DEVICE, LAYOUT, **kw)
+        with torch.cuda.stream(stream):
+            e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        gbs = 8.0 * words * B / (ms * 1e-3) / 1e9
+        out.append({"function": name, "N": N, "B": B, "layout": layout, "ms": ms,
+                    "launches_per_call": (s.launches - l0) / reps, "algorithmic_bytes_per_scenario": 8 * words,
+                    "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak, "peak_source": peak_src,
+                    "evals_per_s": B / (ms * 1e-3)})
+    return out
+
+
+if __name__ == "__main__":
+    N = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+    B = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
+    reps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+    layout = sys.argv[4] if len(sys.argv) > 4 else "soa"
+    for r in measure(N, B, reps, layout):
+        print(json.dumps(r))
