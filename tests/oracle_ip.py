@@ -78,8 +78,6 @@ def solve_cpu_x0(N, drops, x0, opt=None, pb=None):
     for b in range(B):
         p, _ = o.build_p_x0(pb, drops[b, :6], drops[b, 6:])
         p = np.ascontiguousarray(p)
-        rc = lib.ip_solve(o.plan, _dp(p), _dp(x0[b]), ctypes.byref(opt), _dp(x[b]), None,
-                          ctypes.byref(res[b]))
-        assert rc == 0
+        lib.ip_solve(o.plan, _dp(p), _dp(x0[b]), ctypes.byref(opt), _dp(x[b]), None, ctypes.byref(res[b]))  # returns the status
     return dict(x=x, status=np.array([r.status for r in res]), iters=np.array([r.iters for r in res]),
                 f=np.array([r.f for r in res]), viol=np.array([r.viol for r in res]))
