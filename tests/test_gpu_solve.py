@@ -244,3 +244,28 @@ def test_warm_start_flavour_matches_cpu_restatement():
     assert (warm["status"] == 0).all() and (ref["status"] == 0).all()
     assert np.max(np.abs(warm["f"] - ref["f"])) <= 1e-4
     assert warm["iters"].sum() < ref["iters"].sum()
+
+
+def test_full_config1_sweep_is_order_and_shard_invariant():
+    """BASELINE configs[1] at full size (1024 grid drops, N = 30).  Scenarios are independent, so the result of a
+    scenario must not depend on the work-queue order, on which CTA slot solved it, or on how the sweep was sharded:
+    the two interleaved shards of a 2-GPU run reproduce the single-GPU sweep bit for bit.  Every scenario converges and
+    a sample of the converged points is certified with the oracle's functions."""
+    N = 30
+    drops = lc.grid_sweep(1024)
+    s = lc.LandingSolver(N=N)
+    full = s.solve(drops, want_lam=True)
+    assert (full["status"] == 0).all()
+    assert 40 <= full["iters"].mean() <= 120 and full["iters"].max() <= 400
+    for rank in range(2):
+        ids = lc.shard_indices(1024, 2, rank)
+        part = s.solve(drops[ids])
+        assert np.array_equal(part["x"], full["x"][ids]) and np.array_equal(part["iters"], full["iters"][ids])
+        assert np.array_equal(part["f"], full["f"][ids])
+    s.close()
+    o = Oracle(N)
+    pb = o.default_problem()
+    for b in range(0, 1024, 64):
+        f, viol, stat, comp = _kkt_certificate(o, pb, drops[b], full["x"][b], full["lam_g"][b])
+        assert viol <= 1e-3 + 2e-6 and stat <= 1e-2 and comp <= 2e-3
+        assert abs(f - full["f"][b]) <= 1e-9 * max(1.0, abs(f))
