@@ -74,30 +74,6 @@ struct GradSink {  // acc[var] += lam[row] * dg_row/dvar  (J^T lam, knot-local)
 // compile-time filter, so the compiler drops whatever feeds only other parts' entries.  One thread per knot needs
 // 255 registers + 1-2 kB of spills and leaves 8 warps per SM; a quarter of the entries per thread fits the register
 // file and puts four times as many store streams in flight (the kernels are HBM-write bound).
-template <bool LAST> __device__ constexpr int leg_of_row(int row) {  // -1: not a per-leg row
-  using RW = Rows<LAST>;
-  if (row >= 12 && row < 16) return row - 12;
-  if (row >= 16 && row < RW::fric) return (row - 16) / (LAST ? 6 : 12);
-  if (row >= RW::fric && row < RW::state) return (row - RW::fric) & 3;
-  return -1;
-}
-__device__ constexpr int leg_of_var(int var) {  // X 0-11 | c 12-23 | f 24-35 | X+ 36-47 | c+ 48-59
-  if (var >= 12 && var < 36) return ((var - 12) % 12) / 3;
-  if (var >= 48) return (var - 48) / 3;
-  return -1;
-}
-template <bool LAST> __device__ constexpr int g_owner(int row) {
-  const int l = leg_of_row<LAST>(row);
-  return l >= 0 ? l : (row & 3);
-}
-template <bool LAST> __device__ constexpr int j_owner(int row, int var) {
-  const int lv = leg_of_var(var);
-  return lv >= 0 ? lv : g_owner<LAST>(row);
-}
-__device__ constexpr int h_owner(int e, int va, int vb) {
-  const int la = leg_of_var(va), lb = leg_of_var(vb);
-  return la >= 0 ? la : (lb >= 0 ? lb : (e & 3));
-}
 template <int PART, int NP, bool LAST> struct PartSink {  // NP = 1: everything; 2: legs {0,2} | {1,3}; 4: one leg each
   ScatterSink& s;
   __device__ __forceinline__ void g(int row, double v) { if (g_owner<LAST>(row) % NP == PART) s.g(row, v); }

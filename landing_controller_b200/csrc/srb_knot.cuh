@@ -465,4 +465,31 @@ SRB_HD void knot_eval(const Knot& kn, Sink& out, const Lam& lam) {
   }
 }
 
+// ---- dealing the entries of one knot to several threads (evaluation kernels, solver): owner part of a row / entry.
+// Per-leg rows and entries w.r.t. leg variables go to their leg, the rest round-robin.
+template <bool LAST> SRB_HD constexpr int leg_of_row(int row) {  // -1: not a per-leg row
+  using RW = Rows<LAST>;
+  if (row >= 12 && row < 16) return row - 12;
+  if (row >= 16 && row < RW::fric) return (row - 16) / (LAST ? 6 : 12);
+  if (row >= RW::fric && row < RW::state) return (row - RW::fric) & 3;
+  return -1;
+}
+SRB_HD constexpr int leg_of_var(int var) {  // X 0-11 | c 12-23 | f 24-35 | X+ 36-47 | c+ 48-59
+  if (var >= 12 && var < 36) return ((var - 12) % 12) / 3;
+  if (var >= 48) return (var - 48) / 3;
+  return -1;
+}
+template <bool LAST> SRB_HD constexpr int g_owner(int row) {
+  const int l = leg_of_row<LAST>(row);
+  return l >= 0 ? l : (row & 3);
+}
+template <bool LAST> SRB_HD constexpr int j_owner(int row, int var) {
+  const int lv = leg_of_var(var);
+  return lv >= 0 ? lv : g_owner<LAST>(row);
+}
+SRB_HD constexpr int h_owner(int e, int va, int vb) {
+  const int la = leg_of_var(va), lb = leg_of_var(vb);
+  return la >= 0 ? la : (lb >= 0 ? lb : (e & 3));
+}
+
 }  // namespace srb
