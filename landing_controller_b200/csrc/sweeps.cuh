@@ -33,8 +33,8 @@ __host__ __device__ constexpr int ch_off(int b) {
   return o;
 }
 constexpr int TL_COUNT = ch_off(NBLK);
-static_assert(NBLK == 6, "c_ch_off lists the offsets of six block steps");
-__constant__ int c_ch_off[NBLK + 1] = {ch_off(0), ch_off(1), ch_off(2), ch_off(3), ch_off(4), ch_off(5), ch_off(6)};
+static_assert(NBLK <= 6 && NB % 4 == 0, "c_ch_off lists the offsets of up to six block steps; column groups are 4 wide");
+__constant__ int c_ch_off[7] = {ch_off(0), ch_off(1), ch_off(2), ch_off(3), ch_off(4), ch_off(5), ch_off(6)};
 static_assert(TL_COUNT <= TL_WORDS * 4, "work table does not fit its shared-memory region");
 
 __device__ void build_tile_tables(unsigned short* tl) {
