@@ -331,10 +331,19 @@ def main():
         # the evaluation kernels (HBM-bound rows a-3..a-5 of SURVEY 8): 16k scenarios, SoA, a few milliseconds
         try:
             sys.path.insert(0, os.path.join(ROOT, "tools"))
-            from bench_eval import measure
+            from bench_eval import cpu_reference, measure
+            keys = ("function", "N", "B", "layout", "ms", "achieved", "peak", "unit", "frac", "evals_per_s")
             line["roofline"]["eval_kernels"] = [
-                {k: r[k] for k in ("function", "N", "B", "layout", "ms", "achieved", "peak", "unit", "frac")}
-                for r in measure(N, 16384, 10, "soa", solver=solver, device=local_rank)]
+                {k: r[k] for k in keys} for r in measure(N, 16384, 10, "soa", solver=solver, device=local_rank)]
+            # the size the reference ships generated C for (N = 21), with the reference's own compiled functions
+            # timed on the host cores beside it (oracle/_ref, kind "reference")
+            ref = cpu_reference()
+            s21 = lc.LandingSolver(N=21, device=local_rank)
+            rows = [{k: r[k] for k in keys} for r in measure(21, 16384, 10, "soa", solver=s21, device=local_rank)]
+            s21.close()
+            for r in rows:
+                r["cpu_baseline"] = ref[r["function"]] if ref else None
+            line["roofline"]["eval_kernels_n21"] = rows
         except Exception as e:  # reported, never hidden
             line["roofline"]["eval_kernels"] = {"error": repr(e)}
         # CPU baseline on the host cores (bounded sample of the same workload)

@@ -68,10 +68,51 @@ def measure(N=30, B=16384, reps=20, layout="soa", solver=None, device=0):
     return out
 
 
+def cpu_reference(B=8192, reps=3, threads=None):
+    """The REFERENCE's compiled functions (oracle/_ref/landingCtrller_IPOPT.so, N = 21) on the host cores, OpenMP over
+    scenarios (oracle/ref_timing.c): evaluations per second of nlp_g, nlp_jac_g, nlp_hess_l.  None if the reference
+    library was not built (make -C oracle ref)."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import REF_SO, Oracle, build_oracle
+    import landing_controller_b200 as lc
+    if not os.path.exists(REF_SO):
+        return None
+    lib = ctypes.CDLL(build_oracle())
+    threads = threads or (os.cpu_count() or 1)
+    o = Oracle(21)
+    pb = o.default_problem()
+    d = lc.grid_sweep(1024)[:: 1024 // 64]
+    P0 = np.zeros((len(d), o.np_))
+    X0 = np.zeros((len(d), o.nx))
+    for b in range(len(d)):
+        P0[b], X0[b] = o.build_p_x0(pb, d[b, :6], d[b, 6:])
+    rng = np.random.default_rng(0)
+    P = np.ascontiguousarray(np.tile(P0, (B // len(d) + 1, 1))[:B])
+    X = np.ascontiguousarray(np.tile(X0, (B // len(d) + 1, 1))[:B] + 0.01 * rng.standard_normal((B, o.nx)))
+    lam_f, lam_g = np.ones(B), rng.standard_normal((B, o.m))
+    dp = ctypes.POINTER(ctypes.c_double)
+    out = {}
+    # (the first parallel regions of a process pay for the OpenMP thread team: one untimed round first)
+    for name, ins in 2 * (("nlp_g", [X, P]), ("nlp_jac_g", [X, P]), ("nlp_hess_l", [X, P, lam_f, lam_g])):
+        arr = (dp * 4)(*[a.ctypes.data_as(dp) for a in ins] + [None] * (4 - len(ins)))
+        sec, chk = ctypes.c_double(), ctypes.c_double()
+        rc = lib.ref_time_function(REF_SO.encode(), name.encode(), B, arr, reps, threads, ctypes.byref(sec), ctypes.byref(chk))
+        if rc != 0 or not np.isfinite(chk.value):
+            return None
+        out[name] = {"value": B * reps / sec.value, "unit": "evaluations/s", "cores": threads, "kind": "reference",
+                     "sample": "%d scenarios x %d passes of the reference's gcc -O3 %s (N=21), OpenMP over scenarios"
+                               % (B, reps, name)}
+    return out
+
+
 if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 30
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
     reps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
     layout = sys.argv[4] if len(sys.argv) > 4 else "soa"
+    ref = cpu_reference() if N == 21 else None
     for r in measure(N, B, reps, layout):
+        if ref:
+            r["cpu_baseline"] = ref[r["function"]]
         print(json.dumps(r))
