@@ -91,6 +91,12 @@ typedef struct landing_problem {
   double c_ref[12];
   double QN[12];
   double mu, l_leg_max, f_max, mass, Ib[3], Ib_inv[3];
+  /* Variant data used by the SOLVER only (the generated-function ABI above is the landingCtrller_IPOPT problem):
+   * running GRF cost sum_k sum_legs (Qf . f^2) dt_k and kinematic box half-widths (x, y, z) -- the "CCC" landing
+   * problem whose IPOPT solutions the reference stores (generate_quadruped_SRBM_CCC.m:80-91,169-176 with
+   * analysis/eval_SRBM_CCC.m:49-52: QX = Qc = 0, Qf = (1e-4, 1e-4, 1e-3), box 0.05/0.05/0.27).
+   * Defaults {0,0,0} and {0.15, 0.15, 0.30} = generate_landingCtrller_IPOPT.m:83-85,150-155. */
+  double Qf[3], kin_box[3];
 } landing_problem;
 
 void landing_problem_default(landing_problem *pb);

@@ -41,7 +41,8 @@ class Problem(ctypes.Structure):
         "qd_term_max", "q_term_ref", "qd_term_ref")] + [
         ("c_ref", ctypes.c_double * 12), ("QN", ctypes.c_double * 12),
         ("mu", ctypes.c_double), ("l_leg_max", ctypes.c_double), ("f_max", ctypes.c_double),
-        ("mass", ctypes.c_double), ("Ib", ctypes.c_double * 3), ("Ib_inv", ctypes.c_double * 3)]
+        ("mass", ctypes.c_double), ("Ib", ctypes.c_double * 3), ("Ib_inv", ctypes.c_double * 3),
+        ("Qf", ctypes.c_double * 3), ("kin_box", ctypes.c_double * 3)]
 
 
 class Options(ctypes.Structure):

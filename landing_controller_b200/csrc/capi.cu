@@ -154,6 +154,8 @@ void landing_problem_default(landing_problem* pb) {
   pb->mu = 1.0;
   pb->l_leg_max = 0.35;
   pb->f_max = 200.0;
+  for (int i = 0; i < 3; i++) pb->Qf[i] = 0.0;
+  pb->kin_box[0] = 0.15; pb->kin_box[1] = 0.15; pb->kin_box[2] = 0.30;
   // composite rigid-body inertia at q_home (get_mass_matrix.m:19-54, generate_landingCtrller_IPOPT.m:99-104)
   pb->mass = 8.251999999999999;
   pb->Ib[0] = 0.05757729852959269; pb->Ib[1] = 0.23400899479539086; pb->Ib[2] = 0.2796738482657981;

@@ -290,6 +290,24 @@ __device__ __noinline__ void eval_knot_g(const KParams& P, const double* x, doub
   }
 }
 
+// running GRF cost of the "CCC" variant (landing_problem.Qf; all zero for the landingCtrller_IPOPT problem)
+__device__ __forceinline__ bool has_run_cost(const KParams& P) {
+  return P.pb.Qf[0] != 0.0 || P.pb.Qf[1] != 0.0 || P.pb.Qf[2] != 0.0;
+}
+
+// this thread's share of sum_k sum_j Qf[j%3] f_kj^2 dt (dx == nullptr) or of its directional derivative along dx
+__device__ __noinline__ double run_cost_part(const KParams& P, const double* x, const double* dx) {
+  const int N = P.N;
+  const double h = P.pb.T / (double)(N - 1);
+  double acc = 0.0;
+  for (int item = TID; item < P.K * 12; item += NT) {
+    const int k = item / 12, j = item - 12 * k, iv = 12 * N + 24 * k + 12 + j;
+    const double q = P.pb.Qf[j % 3] * h * x[iv];
+    acc += dx ? 2.0 * q * dx[iv] : q * x[iv];
+  }
+  return acc;
+}
+
 // g(x) (and, when LISTS, the J/H entry lists with multipliers Y) for all knots; returns f(x)
 template <bool LISTS>
 __device__ double eval_all(const KParams& P, const Ws& w, const double* x, double* gout, double* red) {
@@ -334,6 +352,7 @@ __device__ double eval_all(const KParams& P, const Ws& w, const double* x, doubl
     const double ref = i < 6 ? P.pb.q_term_ref[i] : P.pb.qd_term_ref[i - 6];
     fl = P.pb.QN[i] * (q - ref) * (q - ref);
   }
+  if (has_run_cost(P)) fl += run_cost_part(P, x, nullptr);  // (block-uniform)
   return bsum(red, fl);  // (syncs: gout / lists are visible to the whole CTA afterwards)
 }
 
@@ -623,6 +642,7 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
         a += Jk[term & 1023] * yk[term >> 10];
       }
     }
+    if (v >= 24 && has_run_cost(P)) a += 2.0 * P.pb.Qf[(v - 24) % 3] * w.x[12 * N + 24 * k + 12 + (v - 24)] * (P.pb.T / (double)(N - 1));
     if (v < NS) {
       if (k > 0) {  // what knot k-1 contributes to (X_k, c_k) through its X+ / c+ columns
         const double* Jp = Jk - NJ_PAD;
@@ -706,8 +726,8 @@ __device__ void build_tables(const KParams& P, double* tab) {
         else if (j == 1) { lb = -INF; ub = 0.001; }
         else if (j < 5) { lb = -INF; ub = 0.01; }
         else if (j < 8) { lb = -0.01; ub = INF; }
-        else if (j < 10) { lb = -0.15; ub = 0.15; }
-        else if (j == 10) { lb = -0.30; ub = 0.0; }
+        else if (j < 10) { lb = -pb.kin_box[j - 8]; ub = pb.kin_box[j - 8]; }
+        else if (j == 10) { lb = -pb.kin_box[2]; ub = 0.0; }
         else { lb = -INF; ub = pb.l_leg_max * pb.l_leg_max; }
       }
       else if (rho < 80) { lb = -INF; ub = 0.0; }
@@ -859,6 +879,7 @@ __device__ void solve_one(const KParams& P, const Ws& w_slot, double* smem, long
         const double ref = tid < 6 ? P.pb.q_term_ref[tid] : P.pb.qd_term_ref[tid - 6];
         d = 2.0 * P.pb.QN[tid] * (q - ref) * w.dx[12 * (N - 1) + tid];
       }
+      if (has_run_cost(P)) d += run_cost_part(P, w.x, w.dx);
       dphi += bsum(red, d);
     }
     double alpha = si.a_pr, ft = f, phb = 0.0, tht = 0.0;

@@ -42,10 +42,13 @@ void ip_options_default(ip_options *o) {
   o->jam_alpha = 0.02;
   o->jam_iters = 5;
   o->max_restarts = 8;
+  o->run_Qf[0] = o->run_Qf[1] = o->run_Qf[2] = 0.0;
+  o->kin_box[0] = 0.15; o->kin_box[1] = 0.15; o->kin_box[2] = 0.30;
 }
 
 typedef struct {
   const srb_plan *pl;
+  const ip_options *opt; /* (variant data: run_Qf, kin_box) */
   int N, nx, m;
   srb_jpat jpi[SRB_NJ_INT], jpl[SRB_NJ_LAST];
   srb_hpat hpi[SRB_NH_INT], hpl[SRB_NH_LAST];
@@ -108,11 +111,26 @@ static void ws_free(ipws *w) {
 }
 
 /* ---------------------------------------------------------------- evaluation */
+/* running GRF cost sum_k sum_j Qf[j%3] f_kj^2 dt_k (generate_quadruped_SRBM_CCC.m:80-88 with Uref forces 0) */
+static double run_cost(const ipws *w, const double *p, const double *x) {
+  const int N = w->N;
+  const double *Qf = w->opt->run_Qf;
+  if (Qf[0] == 0.0 && Qf[1] == 0.0 && Qf[2] == 0.0) return 0.0;
+  double c = 0.0;
+  for (int k = 0; k < N - 1; k++) {
+    const double h = p[w->pl->o_dt + k];
+    for (int j = 0; j < 12; j++) {
+      const double fj = x[12 * N + 24 * k + 12 + j];
+      c += Qf[j % 3] * fj * fj * h;
+    }
+  }
+  return c;
+}
 static double eval_g(ipws *w, const double *p, const double *x, double *g) {
   double f;
   srb_f(w->pl, x, p, &f);
   srb_g(w->pl, x, p, g);
-  return f;
+  return f + run_cost(w, p, x);
 }
 
 /* barrier objective and constraint violation (1-norm) at (x, s) with g = g(x) */
@@ -231,6 +249,16 @@ static void assemble(ipws *w, const double *p, double mu, double *err, double *c
     }
     if (last)
       for (int i = 36; i < 48; i++) M[i * NW + i] = 1.0; /* dummy c+ of the last stage */
+    {                                                      /* running GRF cost: gradient and Hessian diagonal */
+      const double *Qf = w->opt->run_Qf, h = p[pl->o_dt + k];
+      if (Qf[0] != 0.0 || Qf[1] != 0.0 || Qf[2] != 0.0)
+        for (int j = 0; j < 12; j++) {
+          const double gj = 2.0 * Qf[j % 3] * w->x[12 * N + 24 * k + 12 + j] * h;
+          q[24 + j] += gj;
+          M[(24 + j) * NW + 24 + j] += 2.0 * Qf[j % 3] * h;
+          w->gradL[gvar(N, k, 24 + j)] += gj;
+        }
+    }
   }
   for (int i = 0; i < w->nx; i++) dual = fmax(dual, fabs(w->gradL[i]));
   err[0] = dual; err[1] = prim; err[2] = c0;
@@ -523,6 +551,14 @@ static int ip_solve_ws(ipws *w, const double *p, const double *x0, const ip_opti
   memset(res, 0, sizeof *res);
   memcpy(w->x, x0, sizeof(double) * nx);
   srb_bounds(w->pl, p, w->lbo, w->ubo);
+  w->opt = opt;
+  for (int k = 0; k < N - 1; k++) /* kinematic box of the variant */
+    for (int l = 0; l < 4; l++) {
+      const int last = (k == N - 2), kin = 36 + 104 * k + 16 + (last ? 6 : 12) * l + (last ? 2 : 8);
+      w->lbo[kin] = -opt->kin_box[0]; w->ubo[kin] = opt->kin_box[0];
+      w->lbo[kin + 1] = -opt->kin_box[1]; w->ubo[kin + 1] = opt->kin_box[1];
+      w->lbo[kin + 2] = -opt->kin_box[2]; w->ubo[kin + 2] = 0.0;
+    }
   /* relaxed bounds (bound_relax_factor) on inequality rows */
   for (int i = 0; i < m; i++) {
     w->lb[i] = w->lbo[i];
@@ -625,6 +661,12 @@ static int ip_solve_ws(ipws *w, const double *p, const double *x0, const ip_opti
     double dphi = 0;
     for (int i = 0; i < 12; i++)
       dphi += 2.0 * p[w->pl->o_QN + i] * (w->x[12 * (N - 1) + i] - p[12 * (N - 1) + i]) * w->dx[12 * (N - 1) + i];
+    if (opt->run_Qf[0] != 0.0 || opt->run_Qf[1] != 0.0 || opt->run_Qf[2] != 0.0)
+      for (int k = 0; k < N - 1; k++)
+        for (int j = 0; j < 12; j++) {
+          const int iv = 12 * N + 24 * k + 12 + j;
+          dphi += 2.0 * opt->run_Qf[j % 3] * w->x[iv] * p[w->pl->o_dt + k] * w->dx[iv];
+        }
     for (int i = 0; i < m; i++) {
       if (is_eq_row(N, i)) continue;
       if (isfinite(w->lb[i])) dphi -= mu * w->ds[i] / (w->s[i] - w->lb[i]);

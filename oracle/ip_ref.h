@@ -8,9 +8,14 @@
  * site (:264-277,:314-327); the algorithm restated here is the published primal-dual
  * filter line-search interior-point method (Waechter & Biegler, Math. Prog. 106, 2006) with the
  * monotone barrier update, specialised to this problem's stage structure (Riccati recursion on
- * the condensed KKT system).  "IPOPT substitute": PARITY UNPINNED against real IPOPT output for the
- * N=21 problem (no stored solutions, no binary); this file is the oracle for the CUDA solver,
- * which implements the same algorithm step by step.
+ * the condensed KKT system).  "IPOPT substitute": for the N=21 landingCtrller_IPOPT problem the reference keeps no
+ * IPOPT output (no stored solutions, no binary), so converged trajectories of THAT problem are parity unpinned.
+ * The restatement itself is pinned -- softly, at the 1e-3 level IPOPT's tol = 1e-4 allows -- against the only real
+ * IPOPT outputs in the repository: on the N=41 "CCC" variant (run_Qf, kin_box below) it lands on the stored solution
+ * for 25 of the 43 committed runs (same cost to 0.2 %, identical touchdown knots, terminal state within 1e-3, vertical
+ * GRFs within ~0.5 N) and in a different local solution of the non-convex problem for the rest
+ * (tests/test_reference_solutions.py).  This file is the oracle for the CUDA solver, which implements the same
+ * algorithm step by step.
  */
 #ifndef IP_REF_H
 #define IP_REF_H
@@ -29,6 +34,12 @@ typedef struct ip_options {
   double jam_alpha; /* watchdog: accepted primal step below this ... */
   int jam_iters;    /* ... for this many consecutive iterations -> re-centre (0 = off) */
   int max_restarts; /* re-centrings allowed per scenario */
+  /* Problem-variant data that the reference's parameter vector p (landingCtrller_IPOPT layout) does not carry:
+   * running GRF cost sum_k sum_legs (Qf . f^2) dt_k and the kinematic box half-widths of the "CCC" variant
+   * (generate_quadruped_SRBM_CCC.m:80-91,169-176; analysis/eval_SRBM_CCC.m:49-52).  Defaults {0,0,0} and
+   * {0.15, 0.15, 0.30} give the IPOPT variant (generate_landingCtrller_IPOPT.m:83-85,150-155). */
+  double run_Qf[3];
+  double kin_box[3];
 } ip_options;
 
 typedef struct ip_result {

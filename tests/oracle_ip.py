@@ -12,7 +12,8 @@ class IpOptions(ctypes.Structure):
                 ("dual_inf_tol", ctypes.c_double), ("compl_inf_tol", ctypes.c_double),
                 ("mu_init", ctypes.c_double), ("bound_push", ctypes.c_double), ("bound_frac", ctypes.c_double),
                 ("bound_relax_factor", ctypes.c_double), ("max_soc", ctypes.c_int), ("verbose", ctypes.c_int),
-                ("jam_alpha", ctypes.c_double), ("jam_iters", ctypes.c_int), ("max_restarts", ctypes.c_int)]
+                ("jam_alpha", ctypes.c_double), ("jam_iters", ctypes.c_int), ("max_restarts", ctypes.c_int),
+                ("run_Qf", ctypes.c_double * 3), ("kin_box", ctypes.c_double * 3)]
 
 
 class IpResult(ctypes.Structure):
@@ -30,7 +31,11 @@ def default_options(**kw):
     o = IpOptions()
     _lib().ip_options_default(ctypes.byref(o))
     for k, v in kw.items():
-        setattr(o, k, v)
+        if k in ("run_Qf", "kin_box"):
+            for i in range(3):
+                getattr(o, k)[i] = v[i]
+        else:
+            setattr(o, k, v)
     return o
 
 
