@@ -34,8 +34,21 @@ struct landing_ctx {
   // grow-only device staging for host-buffer calls
   void* stage = nullptr;
   size_t stage_bytes = 0;
+  // grow-only scratch for the transposed (SoA) copies of AoS batches
+  void* tr = nullptr;
+  size_t tr_bytes = 0;
   SolverWorkspace ws;
 };
+
+static int ensure_tr(landing_ctx* c, size_t bytes) {
+  if (bytes <= c->tr_bytes) return LANDING_OK;
+  if (c->tr) cudaFree(c->tr);
+  c->tr = nullptr;
+  c->tr_bytes = 0;
+  CU(cudaMalloc(&c->tr, bytes));
+  c->tr_bytes = bytes;
+  return LANDING_OK;
+}
 
 static int ensure_stage(landing_ctx* c, size_t bytes) {
   if (bytes <= c->stage_bytes) return LANDING_OK;
@@ -106,6 +119,7 @@ void landing_destroy(landing_ctx* c) {
   cudaSetDevice(c->device);
   solver_free(c->ws);
   if (c->stage) cudaFree(c->stage);
+  if (c->tr) cudaFree(c->tr);
   if (c->d_maps) cudaFree(c->d_maps);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
@@ -219,6 +233,28 @@ int landing_eval_batch(landing_ctx* c, long long B, int memspace, int layout, co
     for (int i = 0; i < 4; i++) din[i] = in_p[i];
     for (int i = 0; i < 7; i++) dout[i] = out_p[i];
   }
+  // AoS batches (one CasADi vector per scenario) would make every warp access 32 different rows: for batches the
+  // kernels run on transposed (SoA) copies instead and the results are transposed back through shared-memory tiles
+  // (3 x the traffic of a SoA call, but coalesced: DESIGN.md 2.2).  Small batches (the CasADi ABI: B = 1) go direct.
+  double* aos_out[7] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  const bool via_soa = (layout == LANDING_AOS && B >= 64);
+  if (via_soa) {
+    size_t tot = 0;
+    for (int i = 0; i < 4; i++) if (din[i]) tot += sizeof(double) * in_n[i] * B;
+    for (int i = 0; i < 7; i++) if (dout[i]) tot += sizeof(double) * out_n[i] * B;
+    int rc = ensure_tr(c, tot + 256);
+    if (rc) return rc;
+    double* cur = (double*)c->tr;
+    for (int i = 0; i < 4; i++)
+      if (din[i]) {
+        c->launches += launch_transpose(din[i], cur, B, in_n[i], c->stream);  // [B][n] -> [n][B]
+        din[i] = cur;
+        cur += in_n[i] * B;
+      }
+    for (int i = 0; i < 7; i++)
+      if (dout[i]) { aos_out[i] = dout[i]; dout[i] = cur; cur += out_n[i] * B; }
+    layout = LANDING_SOA;
+  }
   EvalArgs a{};
   a.pl = pl;
   a.B = B;
@@ -236,6 +272,14 @@ int landing_eval_batch(landing_ctx* c, long long B, int memspace, int layout, co
   a.status = dstatus;
   c->launches += launch_eval(a, c->stream);
   CU(cudaGetLastError());
+  if (via_soa) {
+    for (int i = 0; i < 7; i++)
+      if (aos_out[i]) {
+        c->launches += launch_transpose(dout[i], aos_out[i], out_n[i], B, c->stream);  // [n][B] -> [B][n]
+        dout[i] = aos_out[i];
+      }
+    CU(cudaGetLastError());
+  }
   if (memspace == LANDING_HOST) {
     for (int i = 0; i < 7; i++)
       if (out_p[i])

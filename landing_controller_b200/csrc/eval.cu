@@ -356,7 +356,29 @@ __global__ void __launch_bounds__(TPB) k_build(DevicePlan pl, long long B, Probl
   }
 }
 
+// dst[c][r] = src[r][c]: 32 x 32 tiles through shared memory (33-column padding), 256 threads; both the reads and
+// the writes of a warp are 256 contiguous bytes
+__global__ void __launch_bounds__(256) k_transpose(const double* __restrict__ src, double* __restrict__ dst,
+                                                   long long rows, long long cols) {
+  __shared__ double tile[32][33];
+  const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = ty; j < 32; j += 8)
+    if (r0 + j < rows && c0 + tx < cols) tile[j][tx] = src[(r0 + j) * cols + c0 + tx];
+  __syncthreads();
+#pragma unroll
+  for (int j = ty; j < 32; j += 8)
+    if (c0 + j < cols && r0 + tx < rows) dst[(c0 + j) * rows + r0 + tx] = tile[tx][j];
+}
+
 }  // namespace
+
+int launch_transpose(const double* src, double* dst, long long rows, long long cols, cudaStream_t st) {
+  const dim3 grid((unsigned)((cols + 31) / 32), (unsigned)((rows + 31) / 32));
+  k_transpose<<<grid, 256, 0, st>>>(src, dst, rows, cols);
+  return 1;
+}
 
 int launch_eval(const EvalArgs& a, cudaStream_t st) {
   int launches = 0;

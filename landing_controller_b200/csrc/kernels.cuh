@@ -43,6 +43,9 @@ struct EvalArgs {
   int k0 = 0;  // first knot slice handled by blockIdx.y == 0
 };
 
+// dst[c][r] = src[r][c] for a row-major rows x cols matrix of doubles (32 x 32 shared-memory tiles); returns 1
+int launch_transpose(const double* src, double* dst, long long rows, long long cols, cudaStream_t st);
+
 // returns number of kernel launches issued
 int launch_eval(const EvalArgs& a, cudaStream_t st);
 int launch_bounds(const DevicePlan& pl, long long B, CView p, View lbg, View ubg, cudaStream_t st);
