@@ -5,3 +5,4 @@ from .api import (AOS, DEVICE, DROPIN_PATH, HOST, LIB_PATH, SOA, STATUS, Landing
 from .sweeps import apply_sweep_parameters, grid_sweep, random_sweep, single_drop  # noqa: F401
 from .sharding import (gather_records, pack_records, shard_bounds, shard_indices, unpack_records,  # noqa: F401
                        unshard_order)
+from . import sweep_io  # noqa: F401,E402
