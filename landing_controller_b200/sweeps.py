@@ -91,3 +91,41 @@ def apply_sweep_parameters(pb):
     pb.l_leg_max = 0.4
     pb.f_max = 500.0
     return pb
+
+
+CCC_N = 41
+CCC_QF = (1e-4, 1e-4, 1e-3)
+CCC_KIN_BOX = (0.05, 0.05, 0.27)
+CCC_QN = (0, 0, 100, 100, 100, 0, 10, 10, 10, 10, 10, 10)
+CCC_Q_TERM_REF = (0, 0, 0.2, 0, 0, 0)
+
+
+def apply_ccc_parameters(pb):
+    """Set the numeric parameters of the "CCC" landing problem, the one behind the reference's stored IPOPT solutions
+    (generate_quadruped_SRBM_CCC.m solved through analysis/eval_SRBM_CCC.m:21-67): N = 41 knots over T = 0.6 s, running
+    GRF cost Qf (QX = Qc = 0), kinematic box 0.05 / 0.05 / 0.27, f_max = 250, q_term_ref z = 0.2,
+    c_ref = (+-0.2, +-0.1, -0.35), velocity bounds +-40.  `pb`: landing_problem (carries Qf / kin_box itself) or the
+    oracle's srb_problem (the variant data then goes into ip_options.run_Qf / kin_box)."""
+    def put(name, vals):
+        a = getattr(pb, name)
+        for i, v in enumerate(vals):
+            a[i] = v
+    pb.T = 0.6
+    put("q_min", [-10, -10, 0.15, -10, -10, -10])
+    put("q_max", [10, 10, 1.0, 10, 10, 10])
+    put("qd_min", [-10, -10, -10, -40, -40, -40])
+    put("qd_max", [10, 10, 10, 40, 40, 40])
+    put("q_term_min", [-10, -10, 0.15, -0.1, -0.1, -10])
+    put("q_term_max", [10, 10, 5, 0.1, 0.1, 10])
+    put("qd_term_min", [-10, -10, -10, -40, -40, -40])
+    put("qd_term_max", [10, 10, 10, 40, 40, 40])
+    put("q_term_ref", CCC_Q_TERM_REF)
+    put("qd_term_ref", [0] * 6)
+    put("QN", CCC_QN)
+    side = np.array([1, -1, 1, 1, 1, 1, -1, -1, 1, -1, 1, 1], dtype=float)
+    put("c_ref", side * np.tile([0.2, 0.1, -0.35], 4))
+    pb.mu, pb.l_leg_max, pb.f_max = 1.0, 0.35, 250.0
+    if hasattr(pb, "Qf"):
+        put("Qf", CCC_QF)
+        put("kin_box", CCC_KIN_BOX)
+    return pb
