@@ -1,6 +1,9 @@
 """The "CCC" landing problem whose IPOPT solutions the reference stores (optimizations/landing/data/*.mat):
-generate_quadruped_SRBM_CCC.m with the parameter values of analysis/eval_SRBM_CCC.m:21-67.  Same rows as the hot-path
-NLP; differences: from landing_controller_b200.sweeps import (CCC_KIN_BOX as KIN_BOX, CCC_N as N, CCC_QF as QF, CCC_QN as QN,  # noqa: F401
+generate_quadruped_SRBM_CCC.m with the parameter values of analysis/eval_SRBM_CCC.m:21-67 (the values live in
+landing_controller_b200/sweeps.py:apply_ccc_parameters).  Helpers for the known-answer tests."""
+import numpy as np
+
+from landing_controller_b200.sweeps import (CCC_KIN_BOX as KIN_BOX, CCC_N as N, CCC_QF as QF, CCC_QN as QN,  # noqa: F401
                                             CCC_Q_TERM_REF as Q_TERM_REF, apply_ccc_parameters as fill_problem)
 
 
