@@ -97,6 +97,12 @@ __device__ __forceinline__ void eval_part(const Knot& kn, ScatterSink& s, const 
 #ifndef EVAL_NP_J
 #define EVAL_NP_J 4
 #endif
+#ifndef EVAL_NP_H
+#define EVAL_NP_H 1
+#endif
+#ifndef EVAL_NP_G
+#define EVAL_NP_G 1
+#endif
 template <bool WG, bool WJ, bool WH, int NP>
 __global__ void __launch_bounds__(TPB, NP > 1 ? 3 : 1) k_eval(EvalArgs a) {
   const long long b = (long long)blockIdx.x * TPB + threadIdx.x;
@@ -391,8 +397,10 @@ int launch_eval(const EvalArgs& a, cudaStream_t st) {
     // one fused launch per requested output combination (nlp_jac_g returns g and jac together)
     EvalArgs c = a;
     dim3 gr = grid;
-    constexpr int NPJ = EVAL_NP_J;
+    constexpr int NPJ = EVAL_NP_J, NPH = EVAL_NP_H, NPG = EVAL_NP_G;
     if (wj && !wh) gr.z = NPJ;
+    if (wh && !wj && !wg) gr.z = NPH;
+    if (wg && !wj && !wh) gr.z = NPG;
     switch ((wg ? 1 : 0) | (wj ? 2 : 0) | (wh ? 4 : 0)) {
       case 0:  // f / grad_f only: just the boundary slice
         c.k0 = a.pl.N - 1;
@@ -400,10 +408,10 @@ int launch_eval(const EvalArgs& a, cudaStream_t st) {
         gr.z = 1;
         k_eval<false, false, false, 1><<<gr, TPB, 0, st>>>(c);
         break;
-      case 1: k_eval<true, false, false, 1><<<gr, TPB, 0, st>>>(c); break;
+      case 1: k_eval<true, false, false, NPG><<<gr, TPB, 0, st>>>(c); break;
       case 2: k_eval<false, true, false, NPJ><<<gr, TPB, 0, st>>>(c); break;
       case 3: k_eval<true, true, false, NPJ><<<gr, TPB, 0, st>>>(c); break;
-      case 4: k_eval<false, false, true, 1><<<gr, TPB, 0, st>>>(c); break;
+      case 4: k_eval<false, false, true, NPH><<<gr, TPB, 0, st>>>(c); break;
       case 5: k_eval<true, false, true, 1><<<gr, TPB, 0, st>>>(c); break;
       case 6: k_eval<false, true, true, 1><<<gr, TPB, 0, st>>>(c); break;
       default: k_eval<true, true, true, 1><<<gr, TPB, 0, st>>>(c); break;
