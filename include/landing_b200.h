@@ -151,6 +151,24 @@ typedef struct landing_solve_io {
 int landing_solve_batch(landing_ctx *ctx, long long B, int memspace, const landing_problem *pb,
                         const landing_options *opt, const landing_solve_io *io);
 
+/* Time-varying LQR pass along solved trajectories (replaces, for a batch, quadruped_SRBM_NLP.m:428-497 with
+ * srbm-utilities/generateVariationalDynamics.m:9-62 and generateRiccatiIntegrator.m:24,49-53): P(t_k), k = 0..n_steps-1,
+ * t_k = k dt, from P(t_{n_steps-1}) = F by explicit Euler steps of Pdot = A'P + PA - P B R^-1 B'P + Q, and the gains
+ * K_k = R^-1 B(t_k)' P(t_k).  State (p, rpy, omega, v, feet[12]), control = GRFs[12].  Matrices row-major. */
+typedef struct landing_tvlqr {
+  double T;        /* horizon of the trajectories (knot spacing T/(N-1)) */
+  double dt;       /* Riccati step, 0.022 in the reference */
+  int n_steps;     /* time points */
+  double Q[576], F[576], R[12]; /* running weight, terminal weight, diagonal of the control weight (90) */
+  double Ib[9];    /* full 3x3 body inertia, get_mass_matrix(model, zeros(18,1), 0) */
+  double mass;
+} landing_tvlqr;
+void landing_tvlqr_default(landing_tvlqr *par);
+/* x_star [B x n_x] (AoS, as landing_solve_batch returns it); P_out [B x n_steps x 576], K_out [B x n_steps x 288]
+ * (12 x 24 row-major); either output may be NULL. */
+int landing_tvlqr_batch(landing_ctx *ctx, long long B, int memspace, const landing_tvlqr *par,
+                        const double *x_star, double *P_out, double *K_out);
+
 /* Measured FP64 FMA throughput of the context's device in TFLOP/s (a DFMA micro-kernel timed with CUDA
  * events): the roofline denominator of the interior-point kernel, which is FP64-pipe bound by design. */
 int landing_fp64_peak(landing_ctx *ctx, double *tflops);

@@ -54,6 +54,12 @@ class Options(ctypes.Structure):
                 ("max_restarts", ctypes.c_int), ("reserved", ctypes.c_int * 5)]
 
 
+class Tvlqr(ctypes.Structure):
+    _fields_ = [("T", ctypes.c_double), ("dt", ctypes.c_double), ("n_steps", ctypes.c_int),
+                ("Q", ctypes.c_double * 576), ("F", ctypes.c_double * 576), ("R", ctypes.c_double * 12),
+                ("Ib", ctypes.c_double * 9), ("mass", ctypes.c_double)]
+
+
 class SolveIO(ctypes.Structure):
     _fields_ = [("drops", _dp), ("x0", _dp), ("x_star", _dp), ("f_star", _dp), ("lam_g", _dp),
                 ("viol", _dp), ("status", _ip), ("iters", _ip)]
@@ -240,6 +246,25 @@ class LandingSolver:
             g = self.eval_host(out["x"], p, lam_f=np.ones(B), lam_g=out["lam_g"], want=("grad_x", "grad_p"))
             out["lam_x"], out["lam_p"] = -g["grad_x"], -g["grad_p"]
         return out
+
+    def tvlqr_default(self):
+        par = Tvlqr()
+        self.lib.landing_tvlqr_default(ctypes.byref(par))
+        par.T = self.problem.T
+        par.n_steps = int(round(par.T / par.dt)) + 1
+        return par
+
+    def tvlqr(self, x_star, par=None, want_K=True):
+        """Time-varying LQR pass along solved trajectories x_star [B, nx] (quadruped_SRBM_NLP.m:428-497):
+        P [B, n_steps, 24, 24] and, if asked, the gains K [B, n_steps, 12, 24]."""
+        par = par or self.tvlqr_default()
+        x = np.ascontiguousarray(x_star, dtype=np.float64)
+        B = x.shape[0]
+        P = np.zeros((B, par.n_steps, 24, 24))
+        K = np.zeros((B, par.n_steps, 12, 24)) if want_K else None
+        self._check(self.lib.landing_tvlqr_batch(self.ctx, B, HOST, ctypes.byref(par), _ptr(x), _ptr(P), _ptr(K)),
+                    "landing_tvlqr_batch")
+        return (P, K) if want_K else P
 
     def solve_device(self, drops, x_star, f_star, status, iters, viol=None, lam_g=None, x0=None):
         """All arguments are CUDA torch tensors already resident in HBM (no copies)."""

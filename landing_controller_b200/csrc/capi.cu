@@ -291,6 +291,51 @@ int landing_eval_batch(landing_ctx* c, long long B, int memspace, int layout, co
   return LANDING_OK;
 }
 
+void landing_tvlqr_default(landing_tvlqr* q) {
+  // quadruped_SRBM_NLP.m:436-475: F = diag(1 1 1, 5 5 5, 4 4 4, 3 3 3, 0...), Q = diag(.25 x3, 1 x3, .5 x3, 1 x3, 0...),
+  // R = 90 I, dt = 0.022; inertia at the zero configuration (generateVariationalDynamics.m:4-7; oracle/crba_constants.py)
+  static const double f[12] = {1, 1, 1, 5, 5, 5, 4, 4, 4, 3, 3, 3};
+  static const double w[12] = {0.25, 0.25, 0.25, 1, 1, 1, 0.5, 0.5, 0.5, 1, 1, 1};
+  for (int i = 0; i < 576; i++) q->Q[i] = q->F[i] = 0.0;
+  for (int i = 0; i < 12; i++) { q->F[i * 24 + i] = f[i]; q->Q[i * 24 + i] = w[i]; q->R[i] = 90.0; }
+  q->T = 0.6;
+  q->dt = 0.022;
+  q->n_steps = 28;  // T / dt + 1
+  static const double Ib[9] = {8.2057376e-02, 0.0, -5.020000000000024e-05, 0.0, 2.46291e-01, 0.0,
+                               -5.020000000000024e-05, 0.0, 2.67475776e-01};
+  for (int i = 0; i < 9; i++) q->Ib[i] = Ib[i];
+  q->mass = 8.251999999999999;
+}
+
+int landing_tvlqr_batch(landing_ctx* c, long long B, int memspace, const landing_tvlqr* par, const double* x_star,
+                        double* P_out, double* K_out) {
+  if (!c || !par || !x_star || B < 0 || par->n_steps < 1) return fail(LANDING_ERR_ARG, "landing_tvlqr_batch: bad arguments");
+  if (B == 0) return LANDING_OK;
+  CU(cudaSetDevice(c->device));
+  const long long nx = c->dpl.nx, ns = par->n_steps;
+  TvlqrArgs a{};
+  a.N = c->N; a.nx = nx; a.par = *par;
+  a.x_star = x_star; a.P_out = P_out; a.K_out = K_out;
+  if (memspace == LANDING_HOST) {
+    const size_t bx = sizeof(double) * nx * B, bp = P_out ? sizeof(double) * 576 * ns * B : 0, bk = K_out ? sizeof(double) * 288 * ns * B : 0;
+    int rc = ensure_stage(c, bx + bp + bk + 256);
+    if (rc) return rc;
+    char* s = (char*)c->stage;
+    CU(cudaMemcpyAsync(s, x_star, bx, cudaMemcpyHostToDevice, c->stream));
+    a.x_star = (const double*)s;
+    a.P_out = P_out ? (double*)(s + bx) : nullptr;
+    a.K_out = K_out ? (double*)(s + bx + bp) : nullptr;
+  }
+  c->launches += launch_tvlqr(a, B, c->stream);
+  CU(cudaGetLastError());
+  if (memspace == LANDING_HOST) {
+    if (P_out) CU(cudaMemcpyAsync(P_out, a.P_out, sizeof(double) * 576 * ns * B, cudaMemcpyDeviceToHost, c->stream));
+    if (K_out) CU(cudaMemcpyAsync(K_out, a.K_out, sizeof(double) * 288 * ns * B, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
+  return LANDING_OK;
+}
+
 int landing_bounds_batch(landing_ctx* c, long long B, int memspace, int layout, const double* p,
                          double* lbg, double* ubg) {
   if (!c || !p || !lbg || !ubg || B <= 0) return fail(LANDING_ERR_ARG, "landing_bounds_batch: bad arguments");

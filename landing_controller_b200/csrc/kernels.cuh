@@ -46,6 +46,15 @@ struct EvalArgs {
 // dst[c][r] = src[r][c] for a row-major rows x cols matrix of doubles (32 x 32 shared-memory tiles); returns 1
 int launch_transpose(const double* src, double* dst, long long rows, long long cols, cudaStream_t st);
 
+struct TvlqrArgs {
+  int N;
+  long long nx;
+  const double* x_star;  // [B][nx] solved trajectories (AoS)
+  double *P_out, *K_out; // [B][n_steps][24*24], [B][n_steps][12*24] (either may be null)
+  landing_tvlqr par;
+};
+int launch_tvlqr(const TvlqrArgs& a, long long B, cudaStream_t st);
+
 // returns number of kernel launches issued
 int launch_eval(const EvalArgs& a, cudaStream_t st);
 int launch_bounds(const DevicePlan& pl, long long B, CView p, View lbg, View ubg, cudaStream_t st);

@@ -1,0 +1,165 @@
+// tvlqr.cu -- time-varying LQR pass along solved landing trajectories, batched (sm_100a, FP64).
+//
+// Replaces, for a whole sweep, what optimizations/landing/quadruped_SRBM_NLP.m:428-497 does per trajectory through
+// CasADi functions: variational single-rigid-body dynamics A(t) [24x24], B(t) [24x12]
+// (utilities_general/srbm-utilities/generateVariationalDynamics.m:9-62) and explicit-Euler backward integration of
+// the Riccati differential equation  Pdot = A'P + PA - P B R^-1 B'P + Q  (generateRiccatiIntegrator.m:24,49-53),
+// returning P(t_k) and the feedback gains K_k = R^-1 B_k' P_k.
+//
+// One CTA (192 threads = 576 / 3 entries of P per thread) per trajectory; P, A, B, A'P and PB live in shared memory;
+// per step 27.6k multiply-adds and one 4.6 kB store of P (+ 2.3 kB of K): the kernel is bound by the sequential
+// chain of n_steps small products (four barriers per step), the sweep as a whole by the HBM writes of P and K.
+#include "kernels.cuh"
+
+namespace srb {
+namespace {
+
+constexpr int TNT = 192, NSV = 24, NCV = 12, LDA = 25, LDB = 13;
+
+__device__ __forceinline__ double skew_entry(const double* v, int i, int j) {  // skew(v)[i][j]
+  if (i == j) return 0.0;
+  const int k = 3 - i - j;
+  const double s = ((j - i + 3) % 3 == 1) ? -1.0 : 1.0;
+  return s * v[k];
+}
+
+__global__ void __launch_bounds__(TNT) k_tvlqr(TvlqrArgs a) {
+  __shared__ double P[NSV * LDA], A[NSV * LDA], W[NSV * LDA], Bm[NSV * LDB], S[NSV * LDB];
+  __shared__ double xd[24], ud[12], Rt[9], Ibi[9], tau[3], fsum[3], Ibom[3];
+  const long long b = blockIdx.x;
+  const int tid = threadIdx.x, N = a.N;
+  const double* x = a.x_star + b * a.nx;
+  const landing_tvlqr& q = a.par;
+  if (tid < 9) {  // inverse of the 3x3 inertia (adjugate)
+    const double* I = q.Ib;
+    const double det = I[0] * (I[4] * I[8] - I[5] * I[7]) - I[1] * (I[3] * I[8] - I[5] * I[6]) + I[2] * (I[3] * I[7] - I[4] * I[6]);
+    const int i = tid / 3, j = tid % 3, i1 = (j + 1) % 3, i2 = (j + 2) % 3, j1 = (i + 1) % 3, j2 = (i + 2) % 3;
+    Ibi[tid] = (I[i1 * 3 + j1] * I[i2 * 3 + j2] - I[i1 * 3 + j2] * I[i2 * 3 + j1]) / det;
+  }
+  for (int e = tid; e < NSV * NSV; e += TNT) P[(e / NSV) * LDA + e % NSV] = q.F[e];
+  __syncthreads();
+  const double hk = q.T / (double)(N - 1);
+  for (int k = q.n_steps - 1; k >= 0; k--) {
+    // reference point at t = k dt (quadruped_SRBM_NLP.m:478-487)
+    const double t_int = k * q.dt;
+    int ko = 0;
+    while (t_int > (ko + 1) * hk && ko < N - 2) ko++;
+    const double al = ((ko + 1) * hk - t_int) / hk;
+    if (tid < 12) xd[tid] = al * x[12 * ko + tid] + (1.0 - al) * x[12 * (ko + 1) + tid];
+    else if (tid < 24) xd[tid] = x[12 * N + 24 * ko + (tid - 12)];
+    else if (tid < 36) ud[tid - 24] = x[12 * N + 24 * ko + 12 + (tid - 24)];
+    for (int e = tid; e < NSV * LDA; e += TNT) A[e] = 0.0;
+    for (int e = tid; e < NSV * LDB; e += TNT) Bm[e] = 0.0;
+    __syncthreads();
+    if (tid == 0) {  // R' = rpyToRotMat(rpy) (body -> world), torque, force sum, Ib * omega
+      double sr, cr, sp, cp, sy, cy;
+      sincos(xd[3], &sr, &cr);
+      sincos(xd[4], &sp, &cp);
+      sincos(xd[5], &sy, &cy);
+      Rt[0] = cy * cp; Rt[1] = cy * sp * sr - sy * cr; Rt[2] = cy * sp * cr + sy * sr;
+      Rt[3] = sy * cp; Rt[4] = sy * sp * sr + cy * cr; Rt[5] = sy * sp * cr - cy * sr;
+      Rt[6] = -sp; Rt[7] = cp * sr; Rt[8] = cp * cr;
+      double tw[3] = {0, 0, 0}, fs[3] = {0, 0, 0};
+      for (int l = 0; l < 4; l++) {
+        const double r0 = xd[12 + 3 * l] - xd[0], r1 = xd[13 + 3 * l] - xd[1], r2 = xd[14 + 3 * l] - xd[2];
+        const double f0 = ud[3 * l], f1 = ud[3 * l + 1], f2 = ud[3 * l + 2];
+        tw[0] += r1 * f2 - r2 * f1; tw[1] += r2 * f0 - r0 * f2; tw[2] += r0 * f1 - r1 * f0;
+        fs[0] += f0; fs[1] += f1; fs[2] += f2;
+      }
+      for (int i = 0; i < 3; i++) {
+        tau[i] = Rt[3 * i] * tw[0] + Rt[3 * i + 1] * tw[1] + Rt[3 * i + 2] * tw[2];
+        fsum[i] = fs[i];
+        Ibom[i] = q.Ib[3 * i] * xd[6] + q.Ib[3 * i + 1] * xd[7] + q.Ib[3 * i + 2] * xd[8];
+      }
+    }
+    __syncthreads();
+    // A, B (generateVariationalDynamics.m:32-55): 11 blocks of 3x3 on the omega rows + the constant blocks
+    if (tid < 99) {
+      const int blk = tid / 9, i = (tid % 9) / 3, j = tid % 3;
+      double m[3];  // column j of the 3x3 matrix that Ib_inv multiplies
+      if (blk == 0) {                       // skew(tau)
+        for (int r = 0; r < 3; r++) m[r] = skew_entry(tau, r, j);
+      } else if (blk == 2) {                // skew(Ib om) - skew(om) Ib
+        const double* om = xd + 6;
+        for (int r = 0; r < 3; r++) {
+          double v = skew_entry(Ibom, r, j);
+          for (int c = 0; c < 3; c++) v -= skew_entry(om, r, c) * q.Ib[3 * c + j];
+          m[r] = v;
+        }
+      } else {                              // R' skew(v) (sign below)
+        double v[3];
+        if (blk == 1) { v[0] = fsum[0]; v[1] = fsum[1]; v[2] = fsum[2]; }
+        else if (blk < 7) { const int l = blk - 3; v[0] = -ud[3 * l]; v[1] = -ud[3 * l + 1]; v[2] = -ud[3 * l + 2]; }
+        else { const int l = blk - 7; v[0] = xd[12 + 3 * l] - xd[0]; v[1] = xd[13 + 3 * l] - xd[1]; v[2] = xd[14 + 3 * l] - xd[2]; }
+        for (int r = 0; r < 3; r++) {
+          double acc = 0.0;
+          for (int c = 0; c < 3; c++) acc += Rt[3 * r + c] * skew_entry(v, c, j);
+          m[r] = acc;
+        }
+      }
+      const double val = Ibi[3 * i] * m[0] + Ibi[3 * i + 1] * m[1] + Ibi[3 * i + 2] * m[2];
+      if (blk == 0) A[(6 + i) * LDA + 3 + j] = val;
+      else if (blk == 1) A[(6 + i) * LDA + j] = val;
+      else if (blk == 2) A[(6 + i) * LDA + 6 + j] = val;
+      else if (blk < 7) A[(6 + i) * LDA + 12 + 3 * (blk - 3) + j] = val;
+      else Bm[(6 + i) * LDB + 3 * (blk - 7) + j] = val;
+    } else if (tid < 108) {
+      const int i = (tid - 99) / 3, j = (tid - 99) % 3;
+      A[(3 + i) * LDA + 3 + j] = -skew_entry(xd + 6, i, j);
+      if (i == j) {
+        A[i * LDA + 9 + i] = 1.0;
+        A[(3 + i) * LDA + 6 + i] = 1.0;
+        for (int l = 0; l < 4; l++) Bm[(9 + i) * LDB + 3 * l + i] = 1.0 / q.mass;
+      }
+    } else if (tid < 120) {
+      const int i = tid - 108;
+      A[(12 + i) * LDA + 12 + i] = -0.00001;
+    }
+    __syncthreads();
+    // W = A'P, S = P B
+    for (int e = tid; e < NSV * NSV; e += TNT) {
+      const int i = e / NSV, j = e % NSV;
+      double acc = 0.0;
+#pragma unroll 8
+      for (int l = 0; l < NSV; l++) acc += A[l * LDA + i] * P[l * LDA + j];
+      W[i * LDA + j] = acc;
+    }
+    for (int e = tid; e < NSV * NCV; e += TNT) {
+      const int i = e / NCV, c = e % NCV;
+      double acc = 0.0;
+#pragma unroll 8
+      for (int l = 0; l < NSV; l++) acc += P[i * LDA + l] * Bm[l * LDB + c];
+      S[i * LDB + c] = acc;
+    }
+    __syncthreads();
+    // outputs of this time point, then the Euler step towards t - dt
+    double* Pout = a.P_out ? a.P_out + (b * q.n_steps + k) * (NSV * NSV) : nullptr;
+    double* Kout = a.K_out ? a.K_out + (b * q.n_steps + k) * (NCV * NSV) : nullptr;
+    double pn[3];
+    int cnt = 0;
+    for (int e = tid; e < NSV * NSV; e += TNT, cnt++) {
+      const int i = e / NSV, j = e % NSV;
+      const double pij = P[i * LDA + j];
+      if (Pout) Pout[e] = pij;
+      double acc = W[i * LDA + j] + W[j * LDA + i] + q.Q[e];
+#pragma unroll
+      for (int c = 0; c < NCV; c++) acc -= S[i * LDB + c] * S[j * LDB + c] / q.R[c];
+      pn[cnt] = pij + q.dt * acc;
+    }
+    if (Kout)
+      for (int e = tid; e < NCV * NSV; e += TNT) Kout[e] = S[(e % NSV) * LDB + e / NSV] / q.R[e / NSV];
+    __syncthreads();
+    cnt = 0;
+    for (int e = tid; e < NSV * NSV; e += TNT, cnt++) P[(e / NSV) * LDA + e % NSV] = pn[cnt];
+    __syncthreads();
+  }
+}
+
+}  // namespace
+
+int launch_tvlqr(const TvlqrArgs& a, long long B, cudaStream_t st) {
+  k_tvlqr<<<(unsigned)B, TNT, 0, st>>>(a);
+  return 1;
+}
+
+}  // namespace srb

@@ -69,7 +69,7 @@ def flip_along_y(I_in):
     return out
 
 
-def composite_inertia():
+def composite_inertia(q_leg=(0.0, -1.45, 2.65)):
     # get_robot_params('mc3D')
     body = spatial_inertia(3.3, [0, 0, 0], 1e-6 * np.diag([11253.0, 36203.0, 42673.0]))
     abad = spatial_inertia(0.54, [0, 0.036, 0], 1e-6 * np.array([[381, 58, 0.45], [58, 560, 0.95], [0.45, 0.95, 444]]))
@@ -79,7 +79,6 @@ def composite_inertia():
     hip_loc = np.array([0, 0.062, 0])
     knee_loc = np.array([0, 0, -0.209])
     side = np.array([[1, 1, -1, -1], [-1, 1, -1, 1], [1, 1, 1, 1]], dtype=float)
-    q_leg = [0.0, -1.45, 2.65]
     Ic = body.copy()
     leg_side = -1
     for leg in range(4):
@@ -98,6 +97,13 @@ def composite_inertia():
         Ic += Xup[0].T @ IC[0] @ Xup[0]
         leg_side = -leg_side
     return Ic
+
+
+def zero_configuration():
+    """H = get_mass_matrix(model, zeros(18,1), 0) of srbm-utilities/generateVariationalDynamics.m:4-7:
+    full 3x3 body inertia and mass with straight legs (the TVLQR post-pass uses these, not the q_home values)."""
+    Ic = composite_inertia((0.0, 0.0, 0.0))
+    return dict(mass=Ic[5, 5], Ib3=Ic[0:3, 0:3].copy())
 
 
 def constants():
