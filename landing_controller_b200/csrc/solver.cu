@@ -6,18 +6,18 @@
 // generate_data/generate_training_data_automated.m:130-136).
 //
 // B200 design (device code in solver_dev.cuh)
-//  * ONE persistent kernel; ONE CTA of 128 threads = ONE SCENARIO for the whole solve (all
+//  * ONE persistent kernel; ONE CTA of 256 threads = ONE SCENARIO for the whole solve (all
 //    interior-point iterations, line searches and inertia corrections run on the device, no host
-//    round trip, no lock-step between scenarios); 4 CTAs resident per SM pull scenario ids from an
-//    atomic work queue, so a slow scenario never stalls the others and the latency-bound Cholesky
-//    chain of one scenario overlaps with the throughput phases of its neighbours.
+//    round trip, no lock-step between scenarios); 2 CTAs resident per SM pull scenario ids from an
+//    atomic work queue (longest expected first, k_order), so a slow scenario never stalls the others
+//    and the latency-bound Cholesky chain of one scenario overlaps with the phases of its neighbour.
 //  * Evaluation: one THREAD per knot (srb_knot.cuh), Jacobian and Hessian lists on different warps.
 //  * Linear algebra: slacks and bound multipliers are eliminated; the remaining equality-constrained
 //    QP (linearised Euler dynamics) is solved by a Riccati recursion with state (X_k, c_k) [24] and
 //    control (f_k, c_{k+1}) [24].  Each stage is built in shared memory from the stage's entry
-//    lists by a host-made "condensing schedule" (no atomics, deterministic), factored by a
-//    Cholesky whose pivots are broadcast by warp shuffles, and only the factors needed by the
-//    forward sweep are written to the per-CTA scratch (L2-resident).
+//    lists by a host-made "condensing schedule" (no atomics, deterministic), factored by a blocked
+//    partial Cholesky (diagonal blocks in the registers of the two panel warps), and only the factors
+//    needed by the forward sweep are written to the per-CTA scratch.
 //  * Reductions (errors, step lengths, merit function) are shuffle + shared-memory block
 //    reductions: every thread ends up with the identical value, so all control flow is
 //    block-uniform and deterministic.

@@ -1,5 +1,5 @@
-// sweeps.cuh -- the two sequential passes of the Riccati solve, one stage at a time, all 128
-// threads of the CTA on one stage (included by solver_dev.cuh).
+// sweeps.cuh -- the condensing pre-pass and the two sequential passes of the Riccati solve, one stage at a time,
+// all 256 threads of the CTA on one stage (included by solver_dev.cuh).
 //
 // Stage matrix layout: the 48 stage variables are stored in ELIMINATION order
 //     m = 0..11 f_k | 12..23 c_{k+1} | 24..35 X_k | 36..47 c_k          (m = (s + 24) mod 48)

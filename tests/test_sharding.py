@@ -82,3 +82,20 @@ def test_all_gather_of_records_world2_gloo(mode):
     assert np.array_equal(out["iters"], np.arange(n)) and np.array_equal(out["status"], np.arange(n) % 3)
     assert np.allclose(out["f"], drops[:, 2])
     assert np.allclose(out["x"][:, 0], drops[:, 0] + drops[:, 2] * 10 + drops[:, 4] * 100 + drops[:, 9] * 1000)
+
+
+def test_reference_arm_line_schema():
+    """bench.py --impl reference prints one JSON line with the contract's keys (CPU oracle, tiny sample)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--batch", "8",
+                          "--steps", "1", "--warmup", "0", "--knots", "21"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "NLP/s" and line["higher_is_better"] is True
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"] > 0
+    for k in ("metric", "n_gpus", "steps", "warmup", "ms_per_step", "scaling", "dtype", "data", "config"):
+        assert k in line
