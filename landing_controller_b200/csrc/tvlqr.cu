@@ -7,8 +7,8 @@
 // returning P(t_k) and the feedback gains K_k = R^-1 B_k' P_k.
 //
 // One CTA (192 threads = 576 / 3 entries of P per thread) per trajectory; P, A, B, A'P and PB live in shared memory;
-// per step 27.6k multiply-adds and one 4.6 kB store of P (+ 2.3 kB of K): the kernel is bound by the sequential
-// chain of n_steps small products (four barriers per step), the sweep as a whole by the HBM writes of P and K.
+// per step 11.5k multiply-adds (A and B are used with their fixed sparsity) and one 4.6 kB store of P (+ 2.3 kB of K):
+// the kernel is bound by the sequential chain of n_steps small products (four barriers per step).
 #include "kernels.cuh"
 
 namespace srb {
@@ -25,7 +25,7 @@ __device__ __forceinline__ double skew_entry(const double* v, int i, int j) {  /
 
 __global__ void __launch_bounds__(TNT) k_tvlqr(TvlqrArgs a) {
   __shared__ double P[NSV * LDA], A[NSV * LDA], W[NSV * LDA], Bm[NSV * LDB], S[NSV * LDB];
-  __shared__ double xd[24], ud[12], Rt[9], Ibi[9], tau[3], fsum[3], Ibom[3];
+  __shared__ double xd[24], ud[12], Rt[9], Ibi[9], tau[3], fsum[3], Ibom[3], Rinv[12];
   const long long b = blockIdx.x;
   const int tid = threadIdx.x, N = a.N;
   const double* x = a.x_star + b * a.nx;
@@ -37,6 +37,10 @@ __global__ void __launch_bounds__(TNT) k_tvlqr(TvlqrArgs a) {
     Ibi[tid] = (I[i1 * 3 + j1] * I[i2 * 3 + j2] - I[i1 * 3 + j2] * I[i2 * 3 + j1]) / det;
   }
   for (int e = tid; e < NSV * NSV; e += TNT) P[(e / NSV) * LDA + e % NSV] = q.F[e];
+  // A and B keep their zero pattern: only the structural entries are rewritten at every time point
+  for (int e = tid; e < NSV * LDA; e += TNT) A[e] = 0.0;
+  for (int e = tid; e < NSV * LDB; e += TNT) Bm[e] = 0.0;
+  if (tid >= 32 && tid < 44) Rinv[tid - 32] = 1.0 / q.R[tid - 32];
   __syncthreads();
   const double hk = q.T / (double)(N - 1);
   for (int k = q.n_steps - 1; k >= 0; k--) {
@@ -48,8 +52,6 @@ __global__ void __launch_bounds__(TNT) k_tvlqr(TvlqrArgs a) {
     if (tid < 12) xd[tid] = al * x[12 * ko + tid] + (1.0 - al) * x[12 * (ko + 1) + tid];
     else if (tid < 24) xd[tid] = x[12 * N + 24 * ko + (tid - 12)];
     else if (tid < 36) ud[tid - 24] = x[12 * N + 24 * ko + 12 + (tid - 24)];
-    for (int e = tid; e < NSV * LDA; e += TNT) A[e] = 0.0;
-    for (int e = tid; e < NSV * LDB; e += TNT) Bm[e] = 0.0;
     __syncthreads();
     if (tid == 0) {  // R' = rpyToRotMat(rpy) (body -> world), torque, force sum, Ib * omega
       double sr, cr, sp, cp, sy, cy;
@@ -116,20 +118,22 @@ __global__ void __launch_bounds__(TNT) k_tvlqr(TvlqrArgs a) {
       A[(12 + i) * LDA + 12 + i] = -0.00001;
     }
     __syncthreads();
-    // W = A'P, S = P B
+    // W = A'P and S = P B with the fixed sparsity of A and B (generateVariationalDynamics.m:32-55): only the omega rows
+    // 6..8 of A are dense (columns 0-8, 12-23); the rest is I blocks, -skew(omega) and the -1e-5 diagonal; B has the
+    // omega rows and I/m on the v rows.  6 + 4 multiply-adds per entry instead of 24 + 24.
     for (int e = tid; e < NSV * NSV; e += TNT) {
       const int i = e / NSV, j = e % NSV;
-      double acc = 0.0;
-#pragma unroll 8
-      for (int l = 0; l < NSV; l++) acc += A[l * LDA + i] * P[l * LDA + j];
+      double acc = A[6 * LDA + i] * P[6 * LDA + j] + A[7 * LDA + i] * P[7 * LDA + j] + A[8 * LDA + i] * P[8 * LDA + j];
+      if (i >= 3 && i < 6) acc += A[3 * LDA + i] * P[3 * LDA + j] + A[4 * LDA + i] * P[4 * LDA + j] + A[5 * LDA + i] * P[5 * LDA + j];
+      else if (i >= 6 && i < 9) acc += P[(i - 3) * LDA + j];
+      else if (i >= 9 && i < 12) acc += P[(i - 9) * LDA + j];
+      else if (i >= 12) acc += -0.00001 * P[i * LDA + j];
       W[i * LDA + j] = acc;
     }
     for (int e = tid; e < NSV * NCV; e += TNT) {
       const int i = e / NCV, c = e % NCV;
-      double acc = 0.0;
-#pragma unroll 8
-      for (int l = 0; l < NSV; l++) acc += P[i * LDA + l] * Bm[l * LDB + c];
-      S[i * LDB + c] = acc;
+      S[i * LDB + c] = P[i * LDA + 6] * Bm[6 * LDB + c] + P[i * LDA + 7] * Bm[7 * LDB + c] + P[i * LDA + 8] * Bm[8 * LDB + c] +
+                       P[i * LDA + 9 + c % 3] * Bm[(9 + c % 3) * LDB + c];
     }
     __syncthreads();
     // outputs of this time point, then the Euler step towards t - dt
@@ -143,11 +147,11 @@ __global__ void __launch_bounds__(TNT) k_tvlqr(TvlqrArgs a) {
       if (Pout) Pout[e] = pij;
       double acc = W[i * LDA + j] + W[j * LDA + i] + q.Q[e];
 #pragma unroll
-      for (int c = 0; c < NCV; c++) acc -= S[i * LDB + c] * S[j * LDB + c] / q.R[c];
+      for (int c = 0; c < NCV; c++) acc -= S[i * LDB + c] * Rinv[c] * S[j * LDB + c];
       pn[cnt] = pij + q.dt * acc;
     }
     if (Kout)
-      for (int e = tid; e < NCV * NSV; e += TNT) Kout[e] = S[(e % NSV) * LDB + e / NSV] / q.R[e / NSV];
+      for (int e = tid; e < NCV * NSV; e += TNT) Kout[e] = S[(e % NSV) * LDB + e / NSV] * Rinv[e / NSV];
     __syncthreads();
     cnt = 0;
     for (int e = tid; e < NSV * NSV; e += TNT, cnt++) P[(e / NSV) * LDA + e % NSV] = pn[cnt];
