@@ -342,7 +342,7 @@ def main():
             rows = [{k: r[k] for k in keys} for r in measure(21, 16384, 10, "soa", solver=s21, device=local_rank)]
             s21.close()
             for r in rows:
-                r["cpu_baseline"] = ref[r["function"]] if ref else None
+                r["cpu_baseline"] = ref.get(r["function"]) if ref else None
             line["roofline"]["eval_kernels_n21"] = rows
         except Exception as e:  # reported, never hidden
             line["roofline"]["eval_kernels"] = {"error": repr(e)}

@@ -37,12 +37,15 @@ def measure(N=30, B=16384, reps=20, layout="soa", solver=None, device=0):
     lam_g = torch.randn(*shape(d["m"]), dtype=torch.float64, device=dev)
     lam_f = torch.ones(B, dtype=torch.float64, device=dev)
     g, J, H = z(d["m"]), z(d["nnzJ"]), z(d["nnzH"])
+    fv, gx, gp = torch.zeros(B, dtype=torch.float64, device=dev), z(d["nx"]), z(d["np"])
     peak, peak_src = hbm_peak()
     stream = torch.cuda.ExternalStream(s.stream_ptr, device=dev)
     cases = {
         "nlp_g": (dict(x=x, p=p, g=g), d["nx"] + d["np"] + d["m"]),
         "nlp_jac_g": (dict(x=x, p=p, g=g, jac=J), d["nx"] + d["np"] + d["m"] + d["nnzJ"]),
         "nlp_hess_l": (dict(x=x, p=p, lam_f=lam_f, lam_g=lam_g, hess=H), d["nx"] + d["np"] + 1 + d["m"] + d["nnzH"]),
+        "nlp_grad": (dict(x=x, p=p, lam_f=lam_f, lam_g=lam_g, f=fv, g=g, grad_x=gx, grad_p=gp),
+                     2 * (d["nx"] + d["np"] + 1 + d["m"])),
     }
     out = []
     torch.cuda.synchronize()
@@ -113,6 +116,6 @@ if __name__ == "__main__":
     layout = sys.argv[4] if len(sys.argv) > 4 else "soa"
     ref = cpu_reference() if N == 21 else None
     for r in measure(N, B, reps, layout):
-        if ref:
+        if ref and r["function"] in ref:
             r["cpu_baseline"] = ref[r["function"]]
         print(json.dumps(r))
