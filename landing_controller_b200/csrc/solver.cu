@@ -348,7 +348,7 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
   P.prof = d_prof;
   CUS(cudaMemsetAsync(ws.counter, 0, sizeof(int), st));
   static const bool fifo = getenv("LANDING_FIFO") != nullptr;  // experiments: hand the scenarios out in input order
-  if (!fifo && B > 1) {
+  if (!fifo && B > 1 && B <= 262144) {  // (rank by counting is O(B^2): beyond 256k scenarios keep the input order)
     if ((size_t)B > ws.order_cap) {
       if (ws.order) cudaFree(ws.order);
       ws.order = nullptr;
