@@ -269,3 +269,22 @@ def test_full_config1_sweep_is_order_and_shard_invariant():
         f, viol, stat, comp = _kkt_certificate(o, pb, drops[b], full["x"][b], full["lam_g"][b])
         assert viol <= 1e-3 + 2e-6 and stat <= 1e-2 and comp <= 2e-3
         assert abs(f - full["f"][b]) <= 1e-9 * max(1.0, abs(f))
+
+
+def test_restart_budget_bounds_the_cost_of_hopeless_scenarios():
+    """`max_restarts`: scenarios that keep jamming end with LANDING_ST_LINESEARCH_FAIL once the budget of re-centrings is
+    used up; the budget bounds their iteration count (2k grid, N = 30: scenarios 335 and 343 never converge), leaves
+    converging scenarios alone, and GPU and CPU restatement report the same status for them."""
+    N = 30
+    drops = lc.grid_sweep(2048)[[335, 343, 0, 700]]
+    s = lc.LandingSolver(N=N)
+    out = {}
+    for budget in (2, 8):
+        s.options.max_restarts = budget
+        out[budget] = s.solve(drops)
+    s.close()
+    assert out[8]["status"].tolist()[:2] == [2, 2] and out[2]["status"].tolist()[:2] == [2, 2]
+    assert (out[8]["status"][2:] == 0).all()
+    assert (out[2]["iters"][:2] < out[8]["iters"][:2]).all() and (out[8]["iters"][:2] < 400).all()
+    c = solve_cpu(N, drops, opt=default_options(max_restarts=8))
+    assert c["status"].tolist() == out[8]["status"].tolist()
