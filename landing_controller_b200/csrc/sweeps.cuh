@@ -18,6 +18,13 @@
 #define SRB_NB 4
 #endif
 constexpr int NB = SRB_NB;                    // pivot block size
+// the Riccati factors are written once per stage and read once by the forward sweep: streaming stores (evict-first) keep
+// the L2 for the row arrays and the iterate, which every pass of an iteration touches
+#ifdef SRB_NO_STREAM_STORES
+#define ST_STREAM(p, v) (*(p) = (v))
+#else
+#define ST_STREAM(p, v) __stcs((p), (v))
+#endif
 constexpr int NBLK = NS / NB;                 // block steps
 // (row r | column group g << 8): r in [i0, 48] (48 = gradient row), columns i0 + 4g .. i0 + 4g + 3, i0 + 4g <= r;
 // ordered group by group: a warp reads ONE column group (broadcast) and consecutive rows (conflict-free)
@@ -238,7 +245,7 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
           const int ab = abh & 4095, ta = ab / NW;
           if (ta < 12 && ab == ta * NW + ta) a0 += run2h(ta);
         }
-        ct[it] = a0 + a1;
+        ST_STREAM(&ct[it], a0 + a1);
       } else if (it < tb.n_u + NW) {
         const int m = it - tb.n_u;
         double a0 = 0.0, a1 = 0.0;
@@ -249,10 +256,10 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
           a1 += YHs[u1 >> 10] * Js[u1 & 1023];
         }
         if (run && m < 12) a0 += run2h(m) * w.x[12 * P.N + 24 * k + 12 + m];  // gradient of the running GRF cost
-        ct[CT_Q + m] = a0 + a1;
+        ST_STREAM(&ct[CT_Q + m], a0 + a1);
       } else if (it < tb.n_u + NW + tb.n_g) {
         const int n = it - tb.n_u - NW;
-        ct[CT_G + n] = -Js[t_g[n] & 1023];
+        ST_STREAM(&ct[CT_G + n], -Js[t_g[n] & 1023]);
       } else if (it < tb.n_u + NW + tb.n_g + 12) {
         const int i = it - tb.n_u - NW - tb.n_g;
         ct[CT_R + dyn_state(i)] = -lb[LB_GD + i];
@@ -428,15 +435,15 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
           const int j = c + d, a = i < j ? j : i, b2 = i < j ? i : j;
           const double v = M[(24 + a) * LDM + 24 + b2];
           Pn[i * LDP + j] = v;
-          if (i < 12) w.PX[(long long)k * 288 + i * NS + j] = v;
+          if (i < 12) ST_STREAM(&w.PX[(long long)k * 288 + i * NS + j], v);
         }
       }
       // rows 0-23: L (strict lower, 1/l_ii on the diagonal); rows 24-47: Yt
 #pragma unroll
-      for (int d = 0; d < 3; d++) FY[i * NS + c + d] = M[i * LDM + c + d];
+      for (int d = 0; d < 3; d++) ST_STREAM(&FY[i * NS + c + d], M[i * LDM + c + d]);
       if (i < 16) {
 #pragma unroll
-        for (int d = 0; d < 3; d++) FY[(32 + i) * NS + c + d] = M[(32 + i) * LDM + c + d];
+        for (int d = 0; d < 3; d++) ST_STREAM(&FY[(32 + i) * NS + c + d], M[(32 + i) * LDM + c + d]);
       }
       if (tid >= 224 && tid < 224 + NS) {
         const int t = tid - 224;
