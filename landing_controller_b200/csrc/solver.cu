@@ -88,7 +88,9 @@ HostTables build_tables_host() {
       gp.push_back(e | ((dyn_state_host(pi.jac[e].first) * 36 + pi.jac[e].second) << 10));
   T.n_g = (int)gp.size();
   T.o_g = pushs(gp);
-  // unified condensing targets: lower triangle in elimination order; Hessian entry + sigma-weighted terms
+  // unified condensing targets: lower triangle in elimination order; Hessian entry + sigma-weighted terms.
+  // The term lists are padded with null terms (the padding slot of the J list is 0.0) to pairs (condensing) or fours
+  // (row / column schedules): the device loops run two / four terms per trip, so their dependent loads overlap
   auto rot = [](int s) { return s < 24 ? s + 24 : s - 24; };
   std::map<int, std::vector<int>> tg;
   std::map<int, int> th;
@@ -143,6 +145,7 @@ HostTables build_tables_host() {
   for (int rho = 0; rho < RK; rho++) {
     if (rho >= 12)
       for (int e : rows[rho]) rterms.push_back((sidx_host(pi.jac[e].second) << 10) | e);
+    while (rterms.size() & 3) rterms.push_back(NULL_E);  // (stage variable 0, zero list slot)
     rptr[rho + 1] = (int)rterms.size();
   }
   T.o_rptr = push(rptr);
@@ -154,6 +157,7 @@ HostTables build_tables_host() {
   for (int v = 0; v < 60; v++) {
     for (int e = 0; e < NJ_INT; e++)
       if (pi.jac[e].second == v) cterms.push_back((pi.jac[e].first << 10) | e);
+    while (cterms.size() & 3) cterms.push_back(NULL_E);  // (row 0, zero list slot)
     cptr.push_back((int)cterms.size());
   }
   T.o_cptr = push(cptr);
@@ -385,6 +389,14 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
       if (bn[i][0] && i != 5)
         fprintf(stderr, "[landing prof]   backward %-18s %8.0f cycles per stage\n", bn[i],
                 (double)h[PH_B_WAIT + i] / (double)std::max(1ull, h[PH_B_STAGES]));
+    static const char* fn[] = {"wait+sync", "rhs,G", "L^-T solve", "next state"};
+    const double fst = (double)std::max(1ull, h[PH_NITER]) * (P.K);
+    for (int i = 0; i < 4; i++)
+      fprintf(stderr, "[landing prof]   forward %-18s %8.0f cycles per stage\n", fn[i], (double)h[PH_F_WAIT + i] / fst);
+    for (int i = 0; i < 8; i++)
+      if (h[PH_X0 + i]) fprintf(stderr, "[landing prof]   X%d %10.0f cycles per iteration\n", i, (double)h[PH_X0 + i] / (double)std::max(1ull, h[PH_NITER]));
+    fprintf(stderr, "[landing prof]   one lap of the instrumentation costs %.0f cycles\n",
+            (double)h[PH_CAL] / (4.0 * (double)std::max(1ull, h[PH_NITER])));
   }
   if (memspace == LANDING_HOST) {
     CUS(cudaMemcpyAsync(io.x_star, P.x_star, sizeof(double) * nx * B, cudaMemcpyDeviceToHost, st));

@@ -28,7 +28,7 @@ constexpr int NWARP = NT / 32;
 constexpr int CTAS_PER_SM = SRB_CTAS;
 constexpr int NS = 24;           // stage state / control size
 constexpr int NW = 48;           // stage variables X(12) c(12) f(12) c+(12)
-constexpr int LDM = 49, LDP = 25, LDG = 37;  // leading dimensions (padding against bank conflicts)
+constexpr int LDC = 52, LDMS = 28, LDP = 28, LDG = 37;  // leading dimensions: 4 or 12 (mod 16) doubles keeps the DMMA fragment loads conflict free
 constexpr int MAXFILTER = 64;
 constexpr int RK = 104;          // rows per knot (interior numbering)
 constexpr int NROWTAB = 36 + RK;
@@ -38,23 +38,24 @@ constexpr int NJ_PAD = 388, NH_PAD = 192;  // strides of the per-knot entry list
 constexpr int CT_Q = 280, CT_G = 328, CT_R = 468, CT_STRIDE = 480;
 
 // ---- shared memory carve-up (doubles) per CTA
-constexpr int SM_M = 0;                        // 48 x 49 stage matrix (lower triangle, elimination order)
-constexpr int SM_P = SM_M + NW * LDM;          // 24 x 25   P_{k+1}
-constexpr int SM_G = SM_P + NS * LDP;          // 12 x 37   dynamics Jacobian G
-constexpr int SM_T = SM_G + 12 * LDG;          // 12 x 37   Pxx*G
+constexpr int SM_M = 0;                        // 48 x 52 condensed stage matrix Mc (lower triangle, elimination order)
+constexpr int SM_P = SM_M + NW * LDC;          // 24 x 28   P_{k+1} (full, symmetric)
+constexpr int SM_W = SM_P + NS * LDP;          // 24 x 52   W = [G^ ; E]: next stage state = W (stage variables)
+constexpr int SM_T = SM_W + NS * LDC;          // 24 x 52   T = P W
+constexpr int SM_MS = SM_T + NS * LDC;         // 49 x 28   panel buffer: L | Yt | yv of the stage being factored
+constexpr int SM_G = SM_W;                     // (forward sweep: second factor buffer)
 // stage list buffers (double-buffered, filled by cp.async): J | H | sigma | yhat | dynamics defects
 constexpr int LB_J = 0, LB_H = 388, LB_SIG = 580, LB_YH = 684, LB_GD = 788, LB_SIZE = 800;
-constexpr int SM_LB0 = SM_T + 12 * LDG;
+constexpr int SM_LB0 = SM_MS + 49 * LDMS;
 constexpr int LB_REGION = 2 * CT_STRIDE;       // two condensed-stage buffers (backward) / one list buffer (pre-pass)
 constexpr int SM_V = SM_LB0 + LB_REGION;       // vectors
-constexpr int V_Q = 0, V_QH = 48, V_R = 96, V_T = 108, V_YV = 120, V_PN = 144, V_XI = 168, V_U = 192, V_END = 216;
+constexpr int V_Q = 0, V_Z = 48, V_R = 96, V_T = 108, V_YV = 132, V_PN = 156, V_XI = 180, V_U = 204, V_END = 228;  // V_Z: 24 zeros
 constexpr int SM_RED = SM_V + V_END;           // block-reduction scratch NWARP x 8
 constexpr int SM_TAB = SM_RED + NWARP * 8;     // lb[140] ub[140] lbo[140] ubo[140]
-constexpr int TL_WORDS = 296;                  // static tile tables (unsigned short), see sweeps.cuh
-constexpr int SM_TL = SM_TAB + 4 * NROWTAB;
-constexpr int TBL_INTS = 2392;                 // index tables of the sweeps (SolverTables::sm_src)
-constexpr int SM_TBL = SM_TL + TL_WORDS;
+constexpr int TBL_INTS = 2688;                 // index tables of the sweeps (SolverTables::sm_src)
+constexpr int SM_TBL = SM_TAB + 4 * NROWTAB;
 constexpr int SM_TOTAL = SM_TBL + TBL_INTS / 2;
+static_assert(SM_MS % 2 == 0 && SM_LB0 % 2 == 0 && SM_V % 2 == 0, "16-byte alignment of the regions");
 static_assert(CTAS_PER_SM * (SM_TOTAL * 8 + 1024) <= 232448, "shared memory budget (227 KB per SM)");
 
 struct KParams {
@@ -76,18 +77,21 @@ struct KParams {
 
 // phase ids of the optional cycle profile
 enum { PH_EVAL = 0, PH_ERR, PH_DUAL, PH_MU, PH_BACK, PH_FWD, PH_ROWS, PH_LS, PH_ACCEPT, PH_NBACK, PH_NITER,
-       PH_B_WAIT, PH_B_P1, PH_B_P2, PH_B_P3, PH_B_P4, PH_B_CHOL, PH_B_P6, PH_B_STAGES, PH_C_DIAG, PH_C_TRAIL, PH_COUNT };
+       PH_B_WAIT, PH_B_P1, PH_B_P2, PH_B_P3, PH_B_P4, PH_B_CHOL, PH_B_P6, PH_B_STAGES, PH_C_DIAG, PH_C_TRAIL,
+       PH_F_WAIT, PH_F_RHS, PH_F_SOLVE, PH_F_NEXT, PH_CAL,
+       PH_X0, PH_X1, PH_X2, PH_X3, PH_X4, PH_X5, PH_X6, PH_X7, PH_COUNT };
 struct Prof {
   unsigned long long* c;
   long long t;
+  int who = 0;  // the thread that measures
 #ifndef SRB_PROF  // build with make EXTRA=-DSRB_PROF for the per-phase cycle profile (costs ~4 %)
   __device__ __forceinline__ void start() {}
   __device__ __forceinline__ void lap(int) {}
   __device__ __forceinline__ void count(int) {}
 #else
-  __device__ __forceinline__ void start() { if (c && TID == 0) t = clock64(); }
+  __device__ __forceinline__ void start() { if (c && TID == who) t = clock64(); }
   __device__ __forceinline__ void lap(int ph) {
-    if (c && TID == 0) { const long long n = clock64(); atomicAdd(c + ph, (unsigned long long)(n - t)); t = n; }
+    if (c && TID == who) { const long long n = clock64(); atomicAdd(c + ph, (unsigned long long)(n - t)); t = n; }
   }
   __device__ __forceinline__ void count(int ph) { if (c && TID == 0) atomicAdd(c + ph, 1ull); }
 #endif
@@ -152,7 +156,7 @@ __device__ __forceinline__ double block_reduce1(double* red, double v) {
 template <int... OPS>
 __device__ __forceinline__ void block_reduce(double* red, double (&v)[sizeof...(OPS)]) {
   constexpr int NQ = sizeof...(OPS);
-  static_assert(NQ <= NWARP && NQ * NT <= NW * LDM, "one warp per quantity; the transpose buffer aliases the stage matrix");
+  static_assert(NQ <= NWARP && NQ * NT <= NW * LDC, "one warp per quantity; the transpose buffer aliases the stage matrix");
   double* buf = red - SM_RED + SM_M;
   const int tid = TID, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
@@ -405,7 +409,7 @@ __device__ __forceinline__ int stage_var(int N, int k, int sv) {
 // row buffer of one knot for row_steps (doubles): J list | s | g | sigma | zL | zU | dx of the 48 stage variables
 constexpr int RB_J = 0, RB_S = NJ_PAD, RB_G = RB_S + RK, RB_SIG = RB_G + RK, RB_ZL = RB_SIG + RK, RB_ZU = RB_ZL + RK,
               RB_DX = RB_ZU + RK, RB_SIZE = RB_DX + NW + 4;
-static_assert(RB_SIZE % 2 == 0 && 2 * RB_SIZE <= NW * LDM && RB_SIZE <= LB_REGION && RB_SIZE <= NS * LDP + 2 * 12 * LDG,
+static_assert(RB_SIZE % 2 == 0 && 2 * RB_SIZE <= NW * LDC && RB_SIZE <= LB_REGION && RB_SIZE <= NS * LDP + 2 * NS * LDC,
               "row buffers alias the sweep regions");
 
 __device__ __forceinline__ void prefetch_rows(const Ws& w, int N, int K, int k, double* rb) {
@@ -489,28 +493,39 @@ __device__ __noinline__ void row_steps(const bool MERIT, const KParams& P, const
     const int j = tid - 12, i = (j < 12 ? j % 6 : 6 + (j - 12) % 6);
     row_step(w, tid, tab[tid], tab[NROWTAB + tid], w.dx[12 * (N - 1) + i], mu, tau, si);
   }
+  Prof pf{P.prof, 0, 20};  // (thread 20: an inequality row)
+  pf.start();
   for (int r = 0; r < rounds; r++) {
     const int k = 2 * r + half, kn = k + 2;
     if (kn < K) prefetch_rows(w, N, K, kn, ring(kn));
     cp_async_commit();
+    pf.lap(PH_X0);
     cp_async_wait_group<1>();
     __syncthreads();
+    pf.lap(PH_X1);
     if (k < K && t < RK) {
       const double* rb = ring(k);
       const int rho = t, idx = 36 + RK * k + rho;
       if (rho < 12) {
         si.theta += fabs(rb[RB_G + rho]);
       } else if (!(k == K - 1 && is_noslip(rho))) {
-        double jdx = 0.0;
+        double jdx = 0.0, jd1 = 0.0;
         const int p0 = t_rptr[rho], p1 = t_rptr[rho + 1];
-        for (int p = p0; p < p1; p++) {
-          const int term = t_rterms[p];
-          jdx += rb[RB_J + (term & 1023)] * rb[RB_DX + (term >> 10)];  // dc+ is zero at the last knot
+        for (int p = p0; p < p1; p += 4) {  // (lists padded to fours with null terms; dc+ is zero at the last knot)
+          const int u0 = t_rterms[p], u1 = t_rterms[p + 1], u2 = t_rterms[p + 2], u3 = t_rterms[p + 3];
+          jdx += rb[RB_J + (u0 & 1023)] * rb[RB_DX + (u0 >> 10)];
+          jd1 += rb[RB_J + (u1 & 1023)] * rb[RB_DX + (u1 >> 10)];
+          jdx += rb[RB_J + (u2 & 1023)] * rb[RB_DX + (u2 >> 10)];
+          jd1 += rb[RB_J + (u3 & 1023)] * rb[RB_DX + (u3 >> 10)];
         }
+        jdx += jd1;
+        pf.lap(PH_X2);
         row_step_sm(MERIT, w, idx, rb, rho, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
+        pf.lap(PH_X3);
       }
     }
     __syncthreads();
+    pf.lap(PH_X4);
   }
   cp_async_wait_group<0>();
   double v[5] = {si.a_pr, si.a_du, si.dphi_bar, si.phi_bar, si.theta};
@@ -520,23 +535,43 @@ __device__ __noinline__ void row_steps(const bool MERIT, const KParams& P, const
 
 // merit function pieces at the trial point (x + a dx, s + a ds) with g(trial) in GT: phi_bar = -sum of logs (times mu
 // gives the barrier part), theta
+// Row passes over the 104 K + 36 rows of the iterate: one row per thread and round.  The rows of RU consecutive rounds
+// are LOADED FIRST and then processed (the arrays live in the L2-resident scratch: one exposed round trip per RU rounds
+// instead of one per round; with 8 warps per scenario nothing else hides that latency).
+constexpr int RU = 4;
+
 __device__ __noinline__ void merit_trial(const KParams& P, const Ws& w, const double* tab, const double* drop,
                                             double* red, double alpha, double mu, double& phi_bar, double& theta) {
   const int K = P.K, MR = P.MR;
+  const double* __restrict__ GT = w.GT;
+  const double* __restrict__ S = w.S;
+  const double* __restrict__ DS = w.DS;
   double ph = 0.0, th = 0.0;
-  for (int idx = TID; idx < MR; idx += NT) {
-    const int kind = row_kind(idx, K);
-    if (kind == ROW_FREE) continue;
-    if (kind == ROW_EQ) {
-      th += fabs(w.GT[idx] - (idx < 12 ? drop[idx] : 0.0));
-      continue;
+  for (int base = TID; base < MR; base += RU * NT) {
+    double gt[RU], sv[RU], ds[RU];
+#pragma unroll
+    for (int u = 0; u < RU; u++) {
+      const int idx = base + u * NT;
+      const bool in = idx < MR;
+      gt[u] = in ? GT[idx] : 0.0; sv[u] = in ? S[idx] : 0.0; ds[u] = in ? DS[idx] : 0.0;
     }
-    const int t = row_tab(idx);
-    const double lb = tab[t], ub = tab[NROWTAB + t];
-    const double s = w.S[idx] + alpha * w.DS[idx];
-    th += fabs(w.GT[idx] - s);
-    if (isfinite(lb)) ph -= log(s - lb);
-    if (isfinite(ub)) ph -= log(ub - s);
+#pragma unroll
+    for (int u = 0; u < RU; u++) {
+      const int idx = base + u * NT;
+      if (idx >= MR) break;
+      const int kind = row_kind(idx, K);
+      if (kind == ROW_FREE) continue;
+      if (kind == ROW_EQ) {
+        th += fabs(gt[u] - (idx < 12 ? drop[idx] : 0.0));
+        continue;
+      }
+      const int t = row_tab(idx);
+      const double lb = tab[t], ub = tab[NROWTAB + t];
+      const double s = sv[u] + alpha * ds[u];
+      th += fabs(gt[u] - s);
+      if (isfinite(lb)) ph -= log(s - lb);
+      if (isfinite(ub)) ph -= log(ub - s);
+    }
   }
   double v[2] = {ph, th};
   block_reduce<R_SUM, R_SUM>(red, v);
@@ -553,45 +588,64 @@ struct Errs {
 __device__ __noinline__ void row_errors(const KParams& P, const Ws& w, const double* tab, const double* drop,
                                            double* red, double mu, Errs& e) {
   const int K = P.K, MR = P.MR;
+  const double* __restrict__ G = w.G;
+  const double* __restrict__ Y = w.Y;
+  const double* __restrict__ S = w.S;
+  const double* __restrict__ ZL = w.ZL;
+  const double* __restrict__ ZU = w.ZU;
+  double* __restrict__ SIG = w.SIG;
   double dual = 0, prim = 0, c0 = 0, cmu = 0, ys = 0, zs = 0, viol = 0, nb = 0;
-  for (int idx = TID; idx < MR; idx += NT) {
-    const int kind = row_kind(idx, K);
-    if (kind == ROW_FREE) continue;
-    const double g = w.G[idx], y = w.Y[idx];
-    ys += fabs(y);
-    if (kind == ROW_EQ) {
-      const double c = fabs(g - (idx < 12 ? drop[idx] : 0.0));
-      prim = fmax(prim, c);
-      viol = fmax(viol, c);
-      w.SIG[idx] = 0.0;
-      continue;
+  for (int base = TID; base < MR; base += RU * NT) {
+    double gv[RU], yv[RU], sv[RU], zl[RU], zu[RU];
+#pragma unroll
+    for (int u = 0; u < RU; u++) {
+      const int idx = base + u * NT;
+      const bool in = idx < MR;
+      gv[u] = in ? G[idx] : 0.0; yv[u] = in ? Y[idx] : 0.0; sv[u] = in ? S[idx] : 0.0;
+      zl[u] = in ? ZL[idx] : 0.0; zu[u] = in ? ZU[idx] : 0.0;
     }
-    const int t = row_tab(idx);
-    const double lb = tab[t], ub = tab[NROWTAB + t];
-    viol = fmax(viol, fmax(tab[2 * NROWTAB + t] - g, g - tab[3 * NROWTAB + t]));
-    const double s = w.S[idx];
-    double sg = 0, rs = -y;
-    if (isfinite(lb)) {
-      const double d = s - lb, z = w.ZL[idx];
-      sg += z / d;
-      rs -= z;
-      c0 = fmax(c0, fabs(z * d));
-      cmu = fmax(cmu, fabs(z * d - mu));
-      zs += z;
-      nb += 1.0;
+#pragma unroll
+    for (int u = 0; u < RU; u++) {
+      const int idx = base + u * NT;
+      if (idx >= MR) break;
+      const int kind = row_kind(idx, K);
+      if (kind == ROW_FREE) continue;
+      const double g = gv[u], y = yv[u];
+      ys += fabs(y);
+      if (kind == ROW_EQ) {
+        const double c = fabs(g - (idx < 12 ? drop[idx] : 0.0));
+        prim = fmax(prim, c);
+        viol = fmax(viol, c);
+        SIG[idx] = 0.0;
+        continue;
+      }
+      const int t = row_tab(idx);
+      const double lb = tab[t], ub = tab[NROWTAB + t];
+      viol = fmax(viol, fmax(tab[2 * NROWTAB + t] - g, g - tab[3 * NROWTAB + t]));
+      const double s = sv[u];
+      double sg = 0, rs = -y;
+      if (isfinite(lb)) {
+        const double d = s - lb, z = zl[u];
+        sg += z / d;
+        rs -= z;
+        c0 = fmax(c0, fabs(z * d));
+        cmu = fmax(cmu, fabs(z * d - mu));
+        zs += z;
+        nb += 1.0;
+      }
+      if (isfinite(ub)) {
+        const double d = ub - s, z = zu[u];
+        sg += z / d;
+        rs += z;
+        c0 = fmax(c0, fabs(z * d));
+        cmu = fmax(cmu, fabs(z * d - mu));
+        zs += z;
+        nb += 1.0;
+      }
+      prim = fmax(prim, fabs(g - s));
+      dual = fmax(dual, fabs(rs));
+      SIG[idx] = sg;
     }
-    if (isfinite(ub)) {
-      const double d = ub - s, z = w.ZU[idx];
-      sg += z / d;
-      rs += z;
-      c0 = fmax(c0, fabs(z * d));
-      cmu = fmax(cmu, fabs(z * d - mu));
-      zs += z;
-      nb += 1.0;
-    }
-    prim = fmax(prim, fabs(g - s));
-    dual = fmax(dual, fabs(rs));
-    w.SIG[idx] = sg;
   }
   double v[8] = {dual, prim, c0, cmu, ys, zs, viol, nb};
   block_reduce<R_MAX, R_MAX, R_MAX, R_MAX, R_SUM, R_SUM, R_MAX, R_SUM>(red, v);
@@ -615,14 +669,30 @@ __device__ __noinline__ double compl_at(const KParams& P, const Ws& w, const dou
 // yhat = sigma (g - s) - mu/(s-lb) + mu/(ub-s)
 __device__ __noinline__ void row_yhat(const KParams& P, const Ws& w, const double* tab, double mu) {
   const int K = P.K, MR = P.MR;
-  for (int idx = TID; idx < MR; idx += NT) {
-    if (row_kind(idx, K) != ROW_INEQ) { w.YH[idx] = 0.0; continue; }
-    const int t = row_tab(idx);
-    const double lb = tab[t], ub = tab[NROWTAB + t], s = w.S[idx];
-    double yh = w.SIG[idx] * (w.G[idx] - s);
-    if (isfinite(lb)) yh -= mu / (s - lb);
-    if (isfinite(ub)) yh += mu / (ub - s);
-    w.YH[idx] = yh;
+  const double* __restrict__ G = w.G;
+  const double* __restrict__ S = w.S;
+  const double* __restrict__ SIG = w.SIG;
+  double* __restrict__ YH = w.YH;
+  for (int base = TID; base < MR; base += RU * NT) {
+    double gv[RU], sv[RU], sg[RU];
+#pragma unroll
+    for (int u = 0; u < RU; u++) {
+      const int idx = base + u * NT;
+      const bool in = idx < MR;
+      gv[u] = in ? G[idx] : 0.0; sv[u] = in ? S[idx] : 0.0; sg[u] = in ? SIG[idx] : 0.0;
+    }
+#pragma unroll
+    for (int u = 0; u < RU; u++) {
+      const int idx = base + u * NT;
+      if (idx >= MR) break;
+      if (row_kind(idx, K) != ROW_INEQ) { YH[idx] = 0.0; continue; }
+      const int t = row_tab(idx);
+      const double lb = tab[t], ub = tab[NROWTAB + t], s = sv[u];
+      double yh = sg[u] * (gv[u] - s);
+      if (isfinite(lb)) yh -= mu / (s - lb);
+      if (isfinite(ub)) yh += mu / (ub - s);
+      YH[idx] = yh;
+    }
   }
 }
 
@@ -636,12 +706,15 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
     const int k = item / 36, v = item - k * 36;
     const double* Jk = w.JL + (long long)k * NJ_PAD;
     const double* yk = w.Y + 36 + RK * k;
-    double a = 0.0;
+    double a = 0.0, a1 = 0.0;
     {
       const int p0 = t_cptr[v], p1 = t_cptr[v + 1];
-      for (int p = p0; p < p1; p++) {
-        const int term = t_cterms[p];
-        a += Jk[term & 1023] * yk[term >> 10];
+      for (int p = p0; p < p1; p += 4) {  // (lists padded to fours with null terms)
+        const int u0 = t_cterms[p], u1 = t_cterms[p + 1], u2 = t_cterms[p + 2], u3 = t_cterms[p + 3];
+        a += Jk[u0 & 1023] * yk[u0 >> 10];
+        a1 += Jk[u1 & 1023] * yk[u1 >> 10];
+        a += Jk[u2 & 1023] * yk[u2 >> 10];
+        a1 += Jk[u3 & 1023] * yk[u3 >> 10];
       }
     }
     if (v >= 24 && has_run_cost(P)) a += 2.0 * P.pb.Qf[(v - 24) % 3] * w.x[12 * N + 24 * k + 12 + (v - 24)] * (P.pb.T / (double)(N - 1));
@@ -650,14 +723,18 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
         const double* Jp = Jk - NJ_PAD;
         const double* yp = yk - RK;
         const int p0 = t_cptr[36 + v], p1 = t_cptr[36 + v + 1];
-        for (int p = p0; p < p1; p++) {
-          const int term = t_cterms[p];
-          a += Jp[term & 1023] * yp[term >> 10];
+        for (int p = p0; p < p1; p += 4) {
+          const int u0 = t_cterms[p], u1 = t_cterms[p + 1], u2 = t_cterms[p + 2], u3 = t_cterms[p + 3];
+          a += Jp[u0 & 1023] * yp[u0 >> 10];
+          a1 += Jp[u1 & 1023] * yp[u1 >> 10];
+          a += Jp[u2 & 1023] * yp[u2 >> 10];
+          a1 += Jp[u3 & 1023] * yp[u3 >> 10];
         }
       } else if (v < 12) {
         a += w.Y[v];  // initial-state rows act on X_0
       }
     }
+    a += a1;
     dmax = fmax(dmax, fabs(a));
   }
   if (tid < 12) {  // terminal state: last knot's X+ columns, objective gradient and terminal rows
@@ -666,7 +743,7 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
     double a = 0.0;
     const int p0 = t_cptr[36 + tid], p1 = t_cptr[36 + tid + 1];
     for (int p = p0; p < p1; p++) {
-      const int term = t_cterms[p];
+      const int term = t_cterms[p];  // (null terms add 0 * y_0)
       a += Jk[term & 1023] * yk[term >> 10];
     }
     const int r1 = tid < 6 ? 12 + tid : 24 + (tid - 6);
@@ -750,8 +827,8 @@ __device__ void build_tables(const KParams& P, double* tab) {
 }
 
 // ---------------------------------------------------------------- one scenario
-__device__ void solve_one(const KParams& P, const Ws& w_slot, double* smem, long long b) {
-  Ws w = w_slot;  // local copy: x / xt and G / GT are swapped instead of copied when a trial point is accepted
+__device__ void solve_one(const KParams& P, Ws& w, double* smem, long long b) {
+  // w (shared memory): x / xt and G / GT are swapped instead of copied when a trial point is accepted
   const int N = P.N, K = P.K, nx = P.nx, MR = P.MR, tid = TID;
   const landing_options& opt = P.opt;
   const double kappa_eps = 10.0, kappa_mu = 0.2, theta_mu = 1.5, tau_min = 0.99;
@@ -941,30 +1018,54 @@ __device__ void solve_one(const KParams& P, const Ws& w_slot, double* smem, long
       nfilt++;
     }
     // accept the trial point (x <-> xt, G <-> GT by pointer)
-    { double* t = w.x; w.x = w.xt; w.xt = t; t = w.G; w.G = w.GT; w.GT = t; }
+    __syncthreads();
+    if (tid == 0) { double* t = w.x; w.x = w.xt; w.xt = t; t = w.G; w.G = w.GT; w.GT = t; }
+    __syncthreads();
     f = ft;
     slog_cur = phb; theta_cur = tht; have_cur = true;
-    for (int idx = tid; idx < MR; idx += NT) {
-      const int kind = row_kind(idx, K);
-      if (kind == ROW_FREE) continue;
-      const double y = w.Y[idx];
-      w.Y[idx] = y + alpha * (w.YN[idx] - y);
-      if (kind == ROW_EQ) continue;
-      const int t = row_tab(idx);
-      const double lb = tab[t], ub = tab[NROWTAB + t];
-      const double s = w.S[idx] + alpha * w.DS[idx];
-      w.S[idx] = s;
-      if (isfinite(lb)) {
-        const double d = s - lb;
-        double z = w.ZL[idx] + si.a_du * w.DZL[idx];
-        z = fmax(fmin(z, kappa_sigma * mu / d), mu / (kappa_sigma * d));
-        w.ZL[idx] = z;
-      }
-      if (isfinite(ub)) {
-        const double d = ub - s;
-        double z = w.ZU[idx] + si.a_du * w.DZU[idx];
-        z = fmax(fmin(z, kappa_sigma * mu / d), mu / (kappa_sigma * d));
-        w.ZU[idx] = z;
+    {
+      double* __restrict__ Yp = w.Y;
+      double* __restrict__ Sp = w.S;
+      double* __restrict__ ZLp = w.ZL;
+      double* __restrict__ ZUp = w.ZU;
+      const double* __restrict__ YNp = w.YN;
+      const double* __restrict__ DSp = w.DS;
+      const double* __restrict__ DZLp = w.DZL;
+      const double* __restrict__ DZUp = w.DZU;
+      for (int base = tid; base < MR; base += RU * NT) {
+        double yv[RU], yn[RU], sv[RU], ds[RU], zl[RU], zu[RU], dzl[RU], dzu[RU];
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+          const int idx = base + u * NT;
+          const bool in = idx < MR;
+          yv[u] = in ? Yp[idx] : 0.0; yn[u] = in ? YNp[idx] : 0.0; sv[u] = in ? Sp[idx] : 0.0; ds[u] = in ? DSp[idx] : 0.0;
+          zl[u] = in ? ZLp[idx] : 0.0; zu[u] = in ? ZUp[idx] : 0.0; dzl[u] = in ? DZLp[idx] : 0.0; dzu[u] = in ? DZUp[idx] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < RU; u++) {
+          const int idx = base + u * NT;
+          if (idx >= MR) break;
+          const int kind = row_kind(idx, K);
+          if (kind == ROW_FREE) continue;
+          Yp[idx] = yv[u] + alpha * (yn[u] - yv[u]);
+          if (kind == ROW_EQ) continue;
+          const int t = row_tab(idx);
+          const double lb = tab[t], ub = tab[NROWTAB + t];
+          const double s = sv[u] + alpha * ds[u];
+          Sp[idx] = s;
+          if (isfinite(lb)) {
+            const double d = s - lb;
+            double z = zl[u] + si.a_du * dzl[u];
+            z = fmax(fmin(z, kappa_sigma * mu / d), mu / (kappa_sigma * d));
+            ZLp[idx] = z;
+          }
+          if (isfinite(ub)) {
+            const double d = ub - s;
+            double z = zu[u] + si.a_du * dzu[u];
+            z = fmax(fmin(z, kappa_sigma * mu / d), mu / (kappa_sigma * d));
+            ZUp[idx] = z;
+          }
+        }
       }
     }
     __syncthreads();
@@ -994,17 +1095,30 @@ __device__ void solve_one(const KParams& P, const Ws& w_slot, double* smem, long
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_solve(KParams P) {
+// The kernel parameters and the scratch pointers are read by every phase through references handed to the
+// (deliberately not inlined) phase functions.  As a by-value kernel parameter / local struct they would live in LOCAL
+// memory (a 3.4 kB stack frame) and be reloaded after every store -- ncu: 2.5 x more local than global loads, long-scoreboard
+// stalls on lines that touch nothing but P.* -- so each CTA keeps one copy of both in SHARED memory.
+__global__ void __launch_bounds__(NT, CTAS_PER_SM) k_solve(const __grid_constant__ KParams Pg) {
   extern __shared__ double smem[];
   __shared__ long long s_next;
+  __shared__ KParams sP;
+  __shared__ Ws sW;
+  {
+    static_assert(sizeof(KParams) % 4 == 0, "copied as 32-bit words");
+    const int* src = reinterpret_cast<const int*>(&Pg);
+    int* dst = reinterpret_cast<int*>(&sP);
+    for (int i = TID; i < (int)(sizeof(KParams) / 4); i += NT) dst[i] = src[i];
+  }
+  __syncthreads();
+  const KParams& P = sP;
   build_tables(P, smem + SM_TAB);
-  build_tile_tables(reinterpret_cast<unsigned short*>(smem + SM_TL));
   {
     int* tbl = reinterpret_cast<int*>(smem + SM_TBL);
     for (int i = TID; i < P.tab.sm_count; i += NT) tbl[i] = __ldg(P.tab.sm_src + i);
   }
+  if (TID == 0) sW = carve(P.scratch + (long long)blockIdx.x * P.slot, P.N);
   __syncthreads();
-  const Ws w = carve(P.scratch + (long long)blockIdx.x * P.slot, P.N);
   for (;;) {
     if (TID == 0) {
       const long long q = atomicAdd(P.counter, 1);
@@ -1014,7 +1128,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_solve(KParams P) {
     const long long b = s_next;
     __syncthreads();
     if (b >= P.B) break;
-    solve_one(P, w, smem, b);
+    solve_one(P, sW, smem, b);
   }
 }
 

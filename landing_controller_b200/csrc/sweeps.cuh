@@ -10,14 +10,25 @@
 #pragma once
 // (textually included inside namespace srb { namespace { ... } } by solver_dev.cuh)
 
-// ---- static work tables (built once per CTA in shared memory)
-//   [0,78)    symmetric G'(Pxx G) tiles (ti >= tj), 3x3, G-column tile coordinates 0..11
-//   [78,126)  cross tiles G' Pxc: (ti 0..11, tc 0..3)
-//   [ch_off(b), ch_off(b+1))  trailing work items of block step b (see partial_cholesky)
-#ifndef SRB_NB
-#define SRB_NB 4
-#endif
-constexpr int NB = SRB_NB;                    // pivot block size
+// ---- FP64 tensor-core tiles.  The dense work of a stage (T = P W, M += W'T, the trailing updates of the blocked
+// factorisation) runs as mma.sync.m8n8k4.f64 (DMMA in SASS; measured 37.1 TFLOP/s on B200 = the DFMA peak,
+// tools/ubench_dmma.cu) at an eighth of the issue slots and a fraction of the shared-memory operand traffic of a DFMA
+// loop: the 49 x 48 stage matrix (48 variables + the gradient row) lives in the REGISTERS of the eight warps as 8 x 8
+// accumulator tiles for the whole stage; only the current 8-column panel passes through shared memory.
+// Fragment layout (lane = 4 g + t): A[g][t] (8 x 4, row), B[t][g] (4 x 8, col), C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+// the 27 tiles (I, J), J <= I, of the lower triangle of the 56 x 48 padded stage matrix (tile row 6 = gradient row),
+// column by column; warp w owns tiles w, w + 8, w + 16, w + 24: every trailing update is spread over all warps
+constexpr int NTILE = 27;
+__constant__ unsigned char c_tile[32] = {
+    0x00, 0x01, 0x02, 0x03, 0x04, 0x05, 0x06, 0x11, 0x12, 0x13, 0x14, 0x15, 0x16, 0x22, 0x23, 0x24,
+    0x25, 0x26, 0x33, 0x34, 0x35, 0x36, 0x44, 0x45, 0x46, 0x55, 0x56, 0xff, 0xff, 0xff, 0xff, 0xff};  // J << 4 | I
+// k-steps (groups of four rows of W = [G^ ; E]) with structural non-zeros in column tile J of W: the c+ columns
+// (12..23) are zero in G^ (rows 0..11) and carry the identity E (rows 12..23)
+__device__ __forceinline__ unsigned w_mask(int J) { return (unsigned)((0x07070730'0f07ull >> (8 * J)) & 0xffu); }
+constexpr int PNB = 8;  // panel width = tile width
 // the Riccati factors are written once per stage and read once by the forward sweep: streaming stores (evict-first) keep
 // the L2 for the row arrays and the iterate, which every pass of an iteration touches
 #ifdef SRB_NO_STREAM_STORES
@@ -25,41 +36,6 @@ constexpr int NB = SRB_NB;                    // pivot block size
 #else
 #define ST_STREAM(p, v) __stcs((p), (v))
 #endif
-constexpr int NBLK = NS / NB;                 // block steps
-// (row r | column group g << 8): r in [i0, 48] (48 = gradient row), columns i0 + 4g .. i0 + 4g + 3, i0 + 4g <= r;
-// ordered group by group: a warp reads ONE column group (broadcast) and consecutive rows (conflict-free)
-__host__ __device__ constexpr int ch_count(int b) {
-  const int i0 = NB * (b + 1), ng = (NW - i0) / 4;
-  int n = 0;
-  for (int g = 0; g < ng; g++) n += (NW + 1) - (i0 + 4 * g);
-  return n;
-}
-__host__ __device__ constexpr int ch_off(int b) {
-  int o = 126;
-  for (int i = 0; i < b; i++) o += ch_count(i);
-  return o;
-}
-constexpr int TL_COUNT = ch_off(NBLK);
-static_assert(NBLK <= 6 && NB % 4 == 0, "c_ch_off lists the offsets of up to six block steps; column groups are 4 wide");
-__constant__ int c_ch_off[7] = {ch_off(0), ch_off(1), ch_off(2), ch_off(3), ch_off(4), ch_off(5), ch_off(6)};
-static_assert(TL_COUNT <= TL_WORDS * 4, "work table does not fit its shared-memory region");
-
-__device__ void build_tile_tables(unsigned short* tl) {
-  const int tid = TID;
-  if (tid == 0) {
-    int n = 0;
-    for (int ti = 0; ti < 12; ti++)
-      for (int tj = 0; tj <= ti; tj++) tl[n++] = (unsigned short)(ti | (tj << 8));
-    for (int ti = 0; ti < 12; ti++)
-      for (int tc = 0; tc < 4; tc++) tl[n++] = (unsigned short)(ti | (tc << 8));
-  } else if (tid <= NBLK) {
-    const int b = tid - 1, i0 = NB * (b + 1);
-    int n = ch_off(b);
-    const int ng = (NW - i0) / 4;
-    for (int g = 0; g < ng; g++)
-      for (int r = i0 + 4 * g; r <= NW; r++) tl[n++] = (unsigned short)(r | (g << 8));
-  }
-}
 
 __device__ __forceinline__ void cp_async16(double* dst_smem, const double* src) {  // 16 bytes, L2 only
   const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem);
@@ -81,8 +57,6 @@ __device__ __forceinline__ void prefetch_lists(const Ws& w, int k, double* lb) {
   cp_async_commit();
 }
 
-// G-column tile (0..11: X,c,f) -> tile index in elimination order
-__device__ __forceinline__ int rot_tile(int t) { return t < 8 ? t + 8 : t - 8; }
 
 // 1/sqrt(e) for a positive, normal e: MUFU.RSQ64H seed (22 bits) + one third-order correction; 52 cycles on the
 // dependent chain instead of the library's 66 (tools/ubench_fp64.cu), max relative error 2.7e-16.
@@ -96,96 +70,6 @@ __device__ __forceinline__ double rsqrt_pos(double a) {
   const double q = fma(r, 1.5, 1.0), yr = y0 * r;
   return fma(yr, q, y0);
 #endif
-}
-
-// Blocked partial Cholesky of the lower-stored 48x48 matrix M (+ gradient row qh), 24 pivots.
-// Per block step: (1) the NB x NB diagonal block is factored in registers (right-looking: every pivot hangs on a
-// chain of ~6 FP64 operations) and, fused with it column by column, each panel row (rows below the block; row 48 =
-// gradient) is solved against L_D^T; (2) all threads update the trailing lower triangle.
-// false -> a pivot was not positive (wrong inertia).
-__device__ __forceinline__ bool partial_cholesky(double* M, double* qh, const unsigned short* tl, int* s_bad, Prof& pf) {
-  const int tid = TID;
-#ifdef SRB_CHOL_UNROLL
-#pragma unroll
-#else
-#pragma unroll 1  // rolled: the unrolled stage loop body (40 KB of code) does not stay in the instruction cache
-#endif
-  for (int b = 0; b < NBLK; b++) {
-    const int p0 = NB * b, i0 = p0 + NB;
-    double L[NB][NB];
-    if (tid < 64) {
-      // every thread of the two panel warps repeats the small factorisation (cheaper than a broadcast through shared
-      // memory); the other six warps skip it, so the FP64 pipes of their sub-partitions stay free for the co-resident CTA
-      double x[NB];
-#pragma unroll
-      for (int i = 0; i < NB; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) L[i][j] = M[(p0 + i) * LDM + p0 + j];
-      const bool panel = tid < NW + 1 - i0;
-      double* arow = (i0 + tid < NW) ? (M + (i0 + tid) * LDM + p0) : (qh + p0);
-#pragma unroll
-      for (int j = 0; j < NB; j++) x[j] = panel ? arow[j] : 0.0;
-      bool pd = true;
-#pragma unroll
-      for (int j = 0; j < NB; j++) {
-        const double e = L[j][j];
-        pd = pd && (e > 1e-14);
-        const double r = rsqrt_pos(e);
-        L[j][j] = r;  // the diagonal keeps 1/l_jj (what the solves need)
-        const double xj = x[j] * r;
-        x[j] = xj;
-#pragma unroll
-        for (int i = j + 1; i < NB; i++) L[i][j] *= r;
-#pragma unroll
-        for (int i = j + 1; i < NB; i++) {
-#pragma unroll
-          for (int l = j + 1; l <= i; l++) L[i][l] -= L[i][j] * L[l][j];
-          x[i] -= xj * L[i][j];
-        }
-      }
-      if (panel) {
-#pragma unroll
-        for (int j = 0; j < NB; j++) arow[j] = x[j];
-      }
-      if (!pd && tid == 0) *s_bad = 1;
-    }
-    __syncthreads();
-    if (*s_bad) return false;  // block-uniform
-    pf.lap(PH_C_DIAG);
-    if (tid == 63) {  // the block's own factor (nobody reads the diagonal block during the trailing update)
-#pragma unroll
-      for (int i = 0; i < NB; i++)
-#pragma unroll
-        for (int j = 0; j <= i; j++) M[(p0 + i) * LDM + p0 + j] = L[i][j];
-    }
-#ifdef SRB_CHOL_UNROLL
-    const int cnt = ch_count(b);
-    const unsigned short* list = tl + ch_off(b);
-#else
-    const int cnt = c_ch_off[b + 1] - c_ch_off[b];
-    const unsigned short* list = tl + c_ch_off[b];
-#endif
-    // M[r][c] -= panel_r . panel_c for c in the item's column group, c <= r
-    for (int i = tid; i < cnt; i += NT) {
-      const int e = list[i], r = e & 255, c0 = i0 + 4 * (e >> 8);
-      const double* xr = (r < NW) ? (M + r * LDM + p0) : (qh + p0);
-      const double* xc = M + c0 * LDM + p0;
-      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
-#pragma unroll
-      for (int q = 0; q < NB; q++) {
-        const double u = xr[q];
-        s0 += u * xc[q]; s1 += u * xc[LDM + q]; s2 += u * xc[2 * LDM + q]; s3 += u * xc[3 * LDM + q];
-      }
-      double* o = (r < NW) ? (M + r * LDM + c0) : (qh + c0);
-      o[0] -= s0;
-      if (c0 + 1 <= r) o[1] -= s1;
-      if (c0 + 2 <= r) o[2] -= s2;
-      if (c0 + 3 <= r) o[3] -= s3;
-    }
-    __syncthreads();
-    pf.lap(PH_C_TRAIL);
-  }
-  return true;
 }
 
 // ---------------------------------------------------------------- condensing pre-pass (parallel over stages)
@@ -214,7 +98,7 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
     const int j = k & 3;
     return smem + (j == 0 ? SM_LB0 : (j == 1 ? SM_M : (j == 2 ? SM_M + LB_SIZE : SM_P)));
   };
-  static_assert(2 * LB_SIZE <= NW * LDM && LB_SIZE <= LB_REGION && LB_SIZE <= NS * LDP + 2 * 12 * LDG, "ring buffers fit");
+  static_assert(2 * LB_SIZE <= NW * LDC && LB_SIZE <= LB_REGION && LB_SIZE <= NS * LDP + 2 * NS * LDC, "ring buffers fit");
   for (int k = 0; k < 3; k++) {
     if (k < K) prefetch_lists(w, k, ring(k)); else cp_async_commit();
   }
@@ -278,29 +162,49 @@ __device__ __forceinline__ void prefetch_ct(const Ws& w, int k, double* cb) {
 }
 
 // ---------------------------------------------------------------- backward sweep
-// Condenses every stage from the entry lists, factors it and propagates P, p.  false -> not PD.
+// Factors every stage and propagates P, p.  false -> not PD (wrong inertia).
+//
+// One stage, all 256 threads (DMMA = mma.sync.m8n8k4.f64, tiles of the 49 x 48 stage matrix in registers):
+//   S1  condensed sums -> Mc (the 278 structural targets; everything else of Mc stays zero for the whole sweep),
+//       structural entries of G^ -> W, defects r
+//   S2  T = P_{k+1} W                                   (DMMA, 54 tile products)  ->  shared memory
+//   S3  M = Mc + W'T, gradient row q + W't              (DMMA, 62 + 19)           ->  accumulator tiles in registers
+//   S4  three block steps of 8 pivots: the panel (one row per thread of warps 0-1; the 8 x 8 diagonal block is factored
+//       redundantly in the registers of every panel thread, right-looking, fused column by column with the triangular
+//       solve of the thread's row) -> shared memory; trailing update of the register tiles (DMMA, k = 8)
+//   S5  Schur complement = P_k, p_k from the tiles; L | Yt | yv from the panel buffer to the scratch (forward sweep)
+__device__ __forceinline__ void store_tile_ms(double* Ms, int I, int J, int g, int t, double c0, double c1) {
+  if (I < 6 || g == 0) *reinterpret_cast<double2*>(Ms + (8 * I + g) * LDMS + 8 * J + 2 * t) = make_double2(c0, c1);
+}
+
 __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, double* smem, double dwreg) {
-  const int N = P.N, K = P.K, tid = TID;
-  double* M = smem + SM_M;
+  const int N = P.N, K = P.K, tid = TID, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  double* Mc = smem + SM_M;
   double* Pn = smem + SM_P;
-  double* Gs = smem + SM_G;
+  double* Wm = smem + SM_W;
   double* Ts = smem + SM_T;
+  double* Ms = smem + SM_MS;
   double* V = smem + SM_V;
-  const unsigned short* tl = reinterpret_cast<const unsigned short*>(smem + SM_TL);
   const int* tbl = reinterpret_cast<const int*>(smem + SM_TBL);
   const SolverTables& tb = P.tab;
   __shared__ int s_ok, s_bad;
   if (TID == 0) s_bad = 0;  // (visible after the barriers below)
   const int* t_g = tbl + tb.o_g;
   const int* t_uabh = tbl + tb.o_uabh;
-  // this thread's GEMM tile
-  int g_ti = 0, g_tj = 0;
-  if (tid < 126) { const int e = tl[tid]; g_ti = e & 255; g_tj = e >> 8; }
+  // this warp's accumulator tiles
+  int tI[4], tJ[4];
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const int e = c_tile[warp + 8 * q];
+    tI[q] = e == 0xff ? -1 : (e & 15);
+    tJ[q] = e == 0xff ? 0 : (e >> 4);
+  }
   prefetch_ct(w, K - 1, smem + SM_LB0 + ((K - 1) & 1) * CT_STRIDE);
-  // terminal block P_K, p_K; G's zero pattern is set once (only its structural entries change)
+  // Mc: zero outside the condensing targets; W: zero outside the structural entries of G^, identity E; terminal P_K, p_K
+  for (int i = tid; i < NW * LDC; i += NT) Mc[i] = 0.0;
   for (int i = tid; i < NS * LDP; i += NT) Pn[i] = 0.0;
-  for (int i = tid; i < 12 * LDG; i += NT) Gs[i] = 0.0;
-  if (tid < NS) V[V_PN + tid] = 0.0;
+  for (int i = tid; i < NS * LDC; i += NT) Wm[i] = 0.0;
+  if (tid < NS) { V[V_PN + tid] = 0.0; V[V_Z + tid] = 0.0; }
   __syncthreads();
   if (tid < 12) {
     const int r1 = tid < 6 ? 12 + tid : 24 + (tid - 6), r2 = r1 + 6;
@@ -308,6 +212,8 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
     const double ref = tid < 6 ? P.pb.q_term_ref[tid] : P.pb.qd_term_ref[tid - 6];
     Pn[tid * LDP + tid] = 2.0 * P.pb.QN[tid] + w.SIG[r1] + w.SIG[r2] + dwreg;
     V[V_PN + tid] = 2.0 * P.pb.QN[tid] * (q - ref) + w.YH[r1] + w.YH[r2];
+  } else if (tid < 24) {
+    Wm[tid * LDC + tid] = 1.0;  // E: c+ (stage variable 12 + j) is component 12 + j of the next stage's state
   }
   __syncthreads();
   for (int i = tid; i < 288; i += NT) w.PX[(long long)K * 288 + i] = Pn[(i / 24) * LDP + (i % 24)];
@@ -319,169 +225,241 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
     pf.count(PH_B_STAGES);
     const double* cb = smem + SM_LB0 + (k & 1) * CT_STRIDE;  // condensed data of this stage (condense_all)
     cp_async_wait_all();
-    __syncthreads();  // condensed data of stage k is in shared memory; P_{k+1}, p_{k+1} complete
+    __syncthreads();  // condensed data of stage k is in shared memory; P_{k+1}, p_{k+1} complete; panel buffer free
     pf.lap(PH_B_WAIT);
     if (k > 0) prefetch_ct(w, k - 1, smem + SM_LB0 + ((k - 1) & 1) * CT_STRIDE);
-    // P1. dynamics Jacobian G (structural entries), defects r
+    // S1. condensed sums (+ delta_w on the (f, X, c) diagonal, dummy c+ of the last stage), G^, defects r
+#pragma unroll
+    for (int rnd = 0; rnd < 2; rnd++) {
+      const int i = tid + NT * rnd;
+      if (i < tb.n_u) {
+        const int ab = t_uabh[i] & 4095, a = ab / NW, b2 = ab - a * NW;
+        double acc = cb[i];
+        if (a == b2) acc += (a >= 12 && a < 24) ? (k == K - 1 ? 1.0 : 0.0) : dwreg;
+        Mc[a * LDC + b2] = acc;
+      }
+    }
     if (tid < tb.n_g) {
-      const int t = t_g[tid] >> 10;
-      Gs[(t / 36) * LDG + (t % 36)] = cb[CT_G + tid];
+      const int e = t_g[tid] >> 10, row = e / 36, v = e - 36 * row;  // v: G column (X, c, f) -> elimination order
+      Wm[row * LDC + (v < 24 ? v + 24 : v - 24)] = cb[CT_G + tid];
     } else if (tid >= 224 && tid < 236) {
       V[V_R + tid - 224] = cb[CT_R + tid - 224];
     }
     __syncthreads();
     pf.lap(PH_B_P1);
-    // P2. T = Pxx G (12 x 36; thread (i, jj) -> columns jj, jj+9, jj+18, jj+27: conflict free), t = Pxx r + p_x
-    if (tid < 108) {
-      const int i = tid / 9, jj = tid - i * 9;
-      double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+    // S2. T = P W (24 x 48); t = P [r; 0] + p.  Warp w: tiles w, w + 8, w + 16 (< 18), their products interleaved
+    {
+      int oI[3], oJ[3];
+      unsigned mk[3];
+      double c2[3][2];
 #pragma unroll
-      for (int l = 0; l < 12; l++) {
-        const double pv = Pn[i * LDP + l];
-        const double* g = Gs + l * LDG + jj;
-        s0 += pv * g[0]; s1 += pv * g[9]; s2 += pv * g[18]; s3 += pv * g[27];
+      for (int q = 0; q < 3; q++) {
+        const int tile = warp + NWARP * q, I = tile / 6;
+        oI[q] = I; oJ[q] = tile - 6 * I;
+        mk[q] = tile < 18 ? w_mask(oJ[q]) : 0u;
+        c2[q][0] = 0.0; c2[q][1] = 0.0;
       }
-      double* t = Ts + i * LDG + jj;
-      t[0] = s0; t[9] = s1; t[18] = s2; t[27] = s3;
-    } else if (tid < 120) {
-      const int i = tid - 108;
-      double s = V[V_PN + i];
 #pragma unroll
-      for (int l = 0; l < 12; l++) s += Pn[i * LDP + l] * V[V_R + l];
-      V[V_T + i] = s;
+      for (int s2 = 0; s2 < 6; s2++)
+#pragma unroll
+        for (int q = 0; q < 3; q++)
+          if (mk[q] >> s2 & 1)
+            dmma(c2[q][0], c2[q][1], Pn[(8 * oI[q] + g) * LDP + 4 * s2 + t], Wm[(4 * s2 + t) * LDC + 8 * oJ[q] + g]);
+#pragma unroll
+      for (int q = 0; q < 3; q++)
+        if (mk[q]) *reinterpret_cast<double2*>(Ts + (8 * oI[q] + g) * LDC + 8 * oJ[q] + 2 * t) = make_double2(c2[q][0], c2[q][1]);
+    }
+    if (warp == 7 && lane < NS) {
+      double a0 = V[V_PN + lane], a1 = 0.0;
+#pragma unroll
+      for (int l = 0; l < 12; l += 2) {
+        a0 += Pn[lane * LDP + l] * V[V_R + l];
+        a1 += Pn[lane * LDP + l + 1] * V[V_R + l + 1];
+      }
+      V[V_T + lane] = a0 + a1;
     }
     __syncthreads();
     pf.lap(PH_B_P2);
-    // P3. M (lower, elimination order) = [G'PxxG, G'Pxc; ., Pcc]; qh = q + G't (+ p_c + Pcx r)
-    if (tid < 126) {
-      double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
-      const double* ga = Gs + 3 * g_ti;
-      const bool sym = tid < 78;
-      const double* bb = sym ? (Ts + 3 * g_tj) : (Pn + 12 + 3 * g_tj);
-      const int ldb = sym ? LDG : LDP;
+    // S3. accumulator tiles: M = Mc + W'T (rows 0..47), q + W't (row 48 = lane group 0 of tile row 6); the products of
+    // the warp's (up to) four tiles are interleaved k-step by k-step
+    double c[4][2];
+    {
+      const double *pa[4], *pb[4];
+      int sa[4];
+      unsigned mk[4];
 #pragma unroll
-      for (int l = 0; l < 12; l++) {
-        const double a0 = ga[l * LDG], a1 = ga[l * LDG + 1], a2 = ga[l * LDG + 2];
-        const double b0 = bb[l * ldb], b1 = bb[l * ldb + 1], b2 = bb[l * ldb + 2];
-        acc[0][0] += a0 * b0; acc[0][1] += a0 * b1; acc[0][2] += a0 * b2;
-        acc[1][0] += a1 * b0; acc[1][1] += a1 * b1; acc[1][2] += a1 * b2;
-        acc[2][0] += a2 * b0; acc[2][1] += a2 * b1; acc[2][2] += a2 * b2;
+      for (int q = 0; q < 4; q++) {
+        const int I = tI[q], J = tJ[q];
+        const bool valid = I >= 0, isrow = I == 6;
+        mk[q] = valid ? w_mask(isrow ? J : I) : 0u;
+        // A operand: column 8I+g of W (rows 4s+t) | gradient row: t (lane group 0), zero for the other groups
+        pa[q] = isrow ? (V + (g == 0 ? V_T : V_Z) + t) : (Wm + t * LDC + 8 * (valid ? I : 0) + g);
+        sa[q] = isrow ? 4 : 4 * LDC;
+        pb[q] = (isrow ? Wm : Ts) + t * LDC + 8 * J + g;
+        double2 m2 = make_double2(0.0, 0.0);
+        if (valid && !isrow) m2 = *reinterpret_cast<const double2*>(Mc + (8 * I + g) * LDC + 8 * J + 2 * t);
+        else if (isrow && g == 0) m2 = *reinterpret_cast<const double2*>(cb + CT_Q + 8 * J + 2 * t);
+        c[q][0] = m2.x; c[q][1] = m2.y;
       }
-      const int ri = 3 * rot_tile(g_ti), rj = sym ? 3 * rot_tile(g_tj) : 12 + 3 * g_tj;
-      if (ri > rj) {
 #pragma unroll
-        for (int a = 0; a < 3; a++)
+      for (int s2 = 0; s2 < 6; s2++)
 #pragma unroll
-          for (int c = 0; c < 3; c++) M[(ri + a) * LDM + rj + c] = acc[a][c];
-      } else if (ri < rj) {
+        for (int q = 0; q < 4; q++)
+          if (mk[q] >> s2 & 1) dmma(c[q][0], c[q][1], pa[q][s2 * sa[q]], pb[q][s2 * 4 * LDC]);
 #pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-          for (int c = 0; c < 3; c++) M[(rj + c) * LDM + ri + a] = acc[a][c];
-      } else {
-#pragma unroll
-        for (int a = 0; a < 3; a++)
-#pragma unroll
-          for (int c = 0; c <= a; c++) M[(ri + a) * LDM + rj + c] = acc[a][c];
-      }
-    } else if (tid >= 128 && tid < 206) {  // Pcc, lower triangle
-      int i = 0, rem = tid - 128;
-      while (rem > i) { rem -= i + 1; i++; }
-      M[(12 + i) * LDM + 12 + rem] = Pn[(12 + i) * LDP + 12 + rem];
-    } else if (tid >= 208) {
-      const int m = tid - 208;  // elimination-order index
-      double s = cb[CT_Q + m];
-      if (m >= 12 && m < 24) {
-        const int j = m - 12;
-        s += V[V_PN + 12 + j];
-#pragma unroll
-        for (int l = 0; l < 12; l++) s += Pn[(12 + j) * LDP + l] * V[V_R + l];
-      } else {
-        const int g = m < 12 ? m + 24 : m - 24;  // G column of this variable
-#pragma unroll
-        for (int l = 0; l < 12; l++) s += Gs[l * LDG + g] * V[V_T + l];
-      }
-      V[V_QH + m] = s;
+      for (int q = 0; q < 4; q++)
+        if (tI[q] >= 0 && tJ[q] == 0) store_tile_ms(Ms, tI[q], 0, g, t, c[q][0], c[q][1]);
     }
     __syncthreads();
     pf.lap(PH_B_P3);
-    // P4. add the condensed sums (+ delta_w on the (f, X, c) diagonal, dummy c+ of the last stage)
+    // S4. eliminate the controls: three block steps of 8 pivots
+#pragma unroll 1
+    for (int b = 0; b < NS / PNB; b++) {
+      const int p0 = PNB * b, i0 = p0 + PNB;
+      if (tid < 64) {
+        double L[PNB][PNB], x[PNB];
 #pragma unroll
-    for (int rnd = 0; rnd < 2; rnd++) {
-      const int t = tid + NT * rnd;
-      if (t < tb.n_u) {
-        const int ab = t_uabh[t] & 4095, a = ab / NW, b2 = ab - a * NW;
-        double acc = cb[t];
-        if (a == b2) acc += (a >= 12 && a < 24) ? (k == K - 1 ? 1.0 : 0.0) : dwreg;
-        M[a * LDM + b2] += acc;
+        for (int i = 0; i < PNB; i++)
+#pragma unroll
+          for (int j = 0; j <= i; j++) L[i][j] = Ms[(p0 + i) * LDMS + p0 + j];
+        const bool panel = tid < NW + 1 - i0;
+        double* arow = Ms + (panel ? i0 + tid : NW) * LDMS + p0;
+#pragma unroll
+        for (int j = 0; j < PNB; j++) x[j] = arow[j];
+        bool pd = true;
+#pragma unroll
+        for (int j = 0; j < PNB; j++) {
+          const double e = L[j][j];
+          pd = pd && (e > 1e-14);
+          const double r = rsqrt_pos(e);
+          L[j][j] = r;  // the diagonal keeps 1/l_jj (what the solves need)
+          const double xj = x[j] * r;
+          x[j] = xj;
+#pragma unroll
+          for (int i = j + 1; i < PNB; i++) L[i][j] *= r;
+#pragma unroll
+          for (int i = j + 1; i < PNB; i++) {
+#pragma unroll
+            for (int l = j + 1; l <= i; l++) L[i][l] -= L[i][j] * L[l][j];
+            x[i] -= xj * L[i][j];
+          }
+        }
+        if (panel) {
+#pragma unroll
+          for (int j = 0; j < PNB; j++) arow[j] = x[j];
+        }
+        if (!pd && tid == 0) s_bad = 1;
+        __syncthreads();  // (all 256 threads meet here or at the barrier of the else branch)
+        if (tid == 63) {  // the block's own factor: nobody reads the diagonal block any more
+#pragma unroll
+          for (int i = 0; i < PNB; i++)
+#pragma unroll
+            for (int j = 0; j <= i; j++) Ms[(p0 + i) * LDMS + p0 + j] = L[i][j];
+        }
+      } else {
+        __syncthreads();
       }
-    }
-    __syncthreads();
-    pf.lap(PH_B_P4);
-    // P5. eliminate the controls
-    if (!partial_cholesky(M, V + V_QH, tl, &s_bad, pf)) {
-      cp_async_wait_all();  // no prefetch may still be in flight when the sweep is retried
-      __syncthreads();
-      return false;
-    }
-    // P6. P_k, p_k, yv and what the forward sweep needs.  Thread (row = tid / 8, three columns from 3 (tid % 8)):
-    // no divisions, every loop fully unrolled, consecutive threads on consecutive addresses.
-    {
-      const int i = tid >> 3, c = 3 * (tid & 7);
-      double* FY = w.FY + (long long)k * 1152;
-      if (i < NS) {  // P_k from the lower triangle of the Schur complement (rows 24..47 of M)
+      if (s_bad) {  // block-uniform
+        cp_async_wait_all();  // no prefetch may still be in flight when the sweep is retried
+        __syncthreads();
+        return false;
+      }
+      pf.lap(PH_C_DIAG);
+      // trailing update of the register tiles: C -= X_I X_J' over the 8 panel columns (loads of all tiles first)
+      {
+        double a0[4], a1[4], b0[4], b1[4];
+        bool act[4];
 #pragma unroll
-        for (int d = 0; d < 3; d++) {
-          const int j = c + d, a = i < j ? j : i, b2 = i < j ? i : j;
-          const double v = M[(24 + a) * LDM + 24 + b2];
-          Pn[i * LDP + j] = v;
-          if (i < 12) ST_STREAM(&w.PX[(long long)k * 288 + i * NS + j], v);
+        for (int q = 0; q < 4; q++) {
+          const int I = tI[q], J = tJ[q];
+          act[q] = I > b && J > b;  // (warp-uniform)
+          const bool arow_ok = act[q] && (I < 6 || g == 0);
+          const double* xa = Ms + (arow_ok ? 8 * I + g : 0) * LDMS + p0 + t;
+          const double* xb = Ms + (8 * (act[q] ? J : 0) + g) * LDMS + p0 + t;
+          a0[q] = arow_ok ? -xa[0] : 0.0; a1[q] = arow_ok ? -xa[4] : 0.0;
+          b0[q] = xb[0]; b1[q] = xb[4];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (act[q]) dmma(c[q][0], c[q][1], a0[q], b0[q]);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (act[q]) dmma(c[q][0], c[q][1], a1[q], b1[q]);
+      }
+      if (b + 1 < NS / PNB) {
+        // the tiles of column b + 1 go to the panel buffer's columns i0 .. i0 + 7: disjoint from the columns
+        // p0 .. p0 + 7 that the updates above read and that thread 63 writes, so no barrier in between
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          if (tI[q] > b && tJ[q] == b + 1) store_tile_ms(Ms, tI[q], b + 1, g, t, c[q][0], c[q][1]);
+      }
+      __syncthreads();
+      pf.lap(PH_C_TRAIL);
+    }
+    // S5. P_k, p_k from the Schur-complement tiles; L | Yt | yv, r to the scratch for the forward sweep
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int I = tI[q], J = tJ[q];
+      if (I < 3 || J < 3) continue;
+#pragma unroll
+      for (int e = 0; e < 2; e++) {
+        const int col = 8 * J + 2 * t + e - 24;
+        const double v = c[q][e];
+        if (I < 6) {
+          const int row = 8 * I + g - 24;
+          if (col <= row) {
+            Pn[row * LDP + col] = v;
+            Pn[col * LDP + row] = v;
+            if (row < 12) ST_STREAM(&w.PX[(long long)k * 288 + row * NS + col], v);
+            if (col < 12) ST_STREAM(&w.PX[(long long)k * 288 + col * NS + row], v);
+          }
+        } else if (g == 0) {
+          V[V_PN + col] = v;
+          w.PV[k * 24 + col] = v;
         }
       }
+    }
+    {
+      const int i = tid >> 3, c3 = 3 * (tid & 7);
+      double* FY = w.FY + (long long)k * 1152;
       // rows 0-23: L (strict lower, 1/l_ii on the diagonal); rows 24-47: Yt
 #pragma unroll
-      for (int d = 0; d < 3; d++) ST_STREAM(&FY[i * NS + c + d], M[i * LDM + c + d]);
+      for (int d = 0; d < 3; d++) ST_STREAM(&FY[i * NS + c3 + d], Ms[i * LDMS + c3 + d]);
       if (i < 16) {
 #pragma unroll
-        for (int d = 0; d < 3; d++) ST_STREAM(&FY[(32 + i) * NS + c + d], M[(32 + i) * LDM + c + d]);
+        for (int d = 0; d < 3; d++) ST_STREAM(&FY[(32 + i) * NS + c3 + d], Ms[(32 + i) * LDMS + c3 + d]);
       }
-      if (tid >= 224 && tid < 224 + NS) {
-        const int t = tid - 224;
-        V[V_PN + t] = V[V_QH + 24 + t];
-        w.PV[k * 24 + t] = V[V_QH + 24 + t];
-        w.yvf[k * 24 + t] = V[V_QH + t];
-      } else if (tid >= 192 && tid < 204) {
-        w.rf[k * 12 + tid - 192] = V[V_R + tid - 192];
-      }
+      if (tid >= 224 && tid < 224 + NS) w.yvf[k * 24 + tid - 224] = Ms[NW * LDMS + tid - 224];
+      else if (tid >= 192 && tid < 204) w.rf[k * 12 + tid - 192] = V[V_R + tid - 192];
     }
     pf.lap(PH_B_P6);
   }
   // free initial foot positions: Cholesky of P_0's (c,c) block (12 x 12) by warp 0, 1/l_ii on the diagonal
   __syncthreads();
   if (tid == 0) s_ok = 1;
-  for (int idx = tid; idx < 144; idx += NT) M[(idx / 12) * LDM + (idx % 12)] = Pn[(12 + idx / 12) * LDP + 12 + (idx % 12)];
+  double* M = Mc;
+  for (int idx = tid; idx < 144; idx += NT) M[(idx / 12) * LDC + (idx % 12)] = Pn[(12 + idx / 12) * LDP + 12 + (idx % 12)];
   __syncthreads();
   if (tid < 32) {
-    const int lane = tid;
     bool ok = true;
     for (int j = 0; j < 12 && ok; j++) {
       double v = 0.0;
       if (lane >= j && lane < 12) {
-        v = M[lane * LDM + j];
-        for (int l = 0; l < j; l++) v -= M[lane * LDM + l] * M[j * LDM + l];
+        v = M[lane * LDC + j];
+        for (int l = 0; l < j; l++) v -= M[lane * LDC + l] * M[j * LDC + l];
       }
       const double d = __shfl_sync(FULL, v, j);
       if (!(d > 1e-14)) { ok = false; break; }
       const double rs = rsqrt(d);
-      if (lane == j) M[j * LDM + j] = rs;
-      else if (lane > j && lane < 12) M[lane * LDM + j] = v * rs;
+      if (lane == j) M[j * LDC + j] = rs;
+      else if (lane > j && lane < 12) M[lane * LDC + j] = v * rs;
       __syncwarp();
     }
     if (!ok && lane == 0) s_ok = 0;
   }
   __syncthreads();
   if (!s_ok) return false;
-  for (int idx = tid; idx < 144; idx += NT) w.L0[idx] = M[(idx / 12) * LDM + (idx % 12)];
+  for (int idx = tid; idx < 144; idx += NT) w.L0[idx] = M[(idx / 12) * LDC + (idx % 12)];
   __syncthreads();  // Pn still holds P_0, V_PN p_0 for the forward start
   return true;
 }
@@ -489,7 +467,7 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
 // ---------------------------------------------------------------- forward sweep
 // forward-stage buffer (doubles): FY 48x24 (L | Yt) | J list 388 | yv 24 | r 12 ; G (12x37) is rebuilt per stage
 constexpr int FB_FY = 0, FB_J = 1152, FB_YV = FB_J + NJ_PAD, FB_R = FB_YV + NS, FB_SIZE = FB_R + 12;
-static_assert(FB_SIZE <= NW * LDM && FB_SIZE <= 2 * 12 * LDG + LB_REGION, "forward buffers alias the backward regions");
+static_assert(FB_SIZE <= NW * LDC && FB_SIZE <= 2 * NS * LDC, "forward buffers alias the backward regions");
 
 __device__ __forceinline__ void prefetch_factors(const Ws& w, int k, double* fb) {
   const int tid = TID;
@@ -545,6 +523,8 @@ __device__ __noinline__ void forward_sweep(const KParams& P, const Ws& w, double
   prefetch_factors(w, 0, fbuf[0]);
   double* Gs = Pn;
   for (int i = tid; i < 12 * LDG; i += NT) Gs[i] = 0.0;
+  Prof pf{P.prof, 0};
+  pf.start();
   for (int k = 0; k < K; k++) {
     const bool last = (k == K - 1);
     const double* fb = fbuf[k & 1];
@@ -552,6 +532,8 @@ __device__ __noinline__ void forward_sweep(const KParams& P, const Ws& w, double
     const double* Ys = fb + FB_FY + NS * NS;   // Yt[i][c]
     cp_async_wait_all();
     __syncthreads();  // factors of stage k in shared memory, xi complete, previous G no longer read
+    pf.lap(PH_F_WAIT);
+    if (k == 0) { pf.lap(PH_CAL); pf.lap(PH_CAL); pf.lap(PH_CAL); pf.lap(PH_CAL); }  // (cost of the instrumentation itself)
     if (!last) prefetch_factors(w, k + 1, fbuf[(k + 1) & 1]);
     // rhs = -(Y xi + yv): thread (c, part) sums 6 terms, the 4 parts sit in neighbouring lanes | G | dx
     if (tid < 96) {
@@ -571,6 +553,7 @@ __device__ __noinline__ void forward_sweep(const KParams& P, const Ws& w, double
       w.dx[12 * N + 24 * k + i] = xi[12 + i];
     }
     __syncthreads();
+    pf.lap(PH_F_RHS);
     if (warp == 0) {
       // u = L^-T rhs (diagonal of Ls holds 1/l_ii)
       double my = lane < NS ? rhs[lane] : 0.0;
@@ -583,6 +566,7 @@ __device__ __noinline__ void forward_sweep(const KParams& P, const Ws& w, double
       if (lane < NS) u[lane] = my;
       if (lane < 12) w.dx[12 * N + 24 * k + 12 + lane] = my;
       __syncwarp();
+      pf.lap(PH_F_SOLVE);
       // next state: lanes (row, half) sum 18 terms each
       double xn = 0.0;
       if (lane < NS) {
@@ -599,6 +583,7 @@ __device__ __noinline__ void forward_sweep(const KParams& P, const Ws& w, double
       __syncwarp();
       if (lane < NS && (lane & 1) == 0) xi[lane >> 1] = xn;
       if (lane >= 12 && lane < NS) xi[lane] = last ? 0.0 : u[lane];
+      pf.lap(PH_F_NEXT);
     }
   }
   __syncthreads();

@@ -22,9 +22,23 @@ class IpResult(ctypes.Structure):
                 ("compl_inf", ctypes.c_double), ("mu", ctypes.c_double), ("restarts", ctypes.c_int)]
 
 
-def _lib():
+_FAST = {}
+
+
+def _lib(fast=False):
+    if fast:
+        if "lib" not in _FAST:
+            from oracle_lib import build_oracle_fast
+            path, how = build_oracle_fast()
+            _FAST["lib"], _FAST["how"] = ctypes.CDLL(path), how
+        return _FAST["lib"]
     lib = ctypes.CDLL(build_oracle())
     return lib
+
+
+def fast_build_flags():
+    _lib(fast=True)
+    return _FAST["how"]
 
 
 def default_options(**kw):
@@ -47,9 +61,9 @@ def default_problem(**kw):
     return pb
 
 
-def solve_cpu(N, drops, opt=None, pb=None, threads=0):
-    """drops [B,12] -> dict(x [B,nx], status, iters, f, viol, n_factor)."""
-    lib = _lib()
+def solve_cpu(N, drops, opt=None, pb=None, threads=0, fast=False):
+    """drops [B,12] -> dict(x [B,nx], status, iters, f, viol, n_factor).  fast: the -O3 -march=native build (timing only)."""
+    lib = _lib(fast)
     drops = np.ascontiguousarray(drops, dtype=np.float64)
     B = drops.shape[0]
     nx = 36 * N - 24

@@ -31,6 +31,21 @@ def build_oracle(force=False):
     return ORACLE_SO
 
 
+FAST_SO = os.path.join(ORACLE_DIR, "liboracle_fast.so")
+
+
+def build_oracle_fast():
+    """The -O3 -march=native build used by the TIMED CPU arm of bench.py (never by the parity tests): always rebuilt on
+    the host that runs the bench, because -march=native code from another machine may not run here.  Falls back to the
+    bit-reproducible build (and says so) when there is no compiler."""
+    try:
+        subprocess.check_call(["make", "-B", "-C", ORACLE_DIR, "liboracle_fast.so"], stdout=subprocess.DEVNULL,
+                              stderr=subprocess.DEVNULL)
+        return FAST_SO, "gcc -O3 -march=native -fopenmp (built on this host)"
+    except Exception:
+        return build_oracle(), "gcc -O2 -ffp-contract=off -fopenmp (no compiler on this host for the -O3 build)"
+
+
 class Plan(ctypes.Structure):
     _fields_ = [("N", ctypes.c_int), ("nx", ctypes.c_int), ("np", ctypes.c_int), ("m", ctypes.c_int),
                 ("nnzJ", ctypes.c_int), ("nnzH", ctypes.c_int),
