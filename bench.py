@@ -2,13 +2,14 @@
 """bench.py -- converged landing NLPs/sec on the BASELINE.json workload.
 
 One "step" = one pass of the hot path over one batch: solve every drop condition of the sweep
-(SRB landing sweep, 1k synthetic drop conditions on a height x pitch x roll x forward-velocity grid,
-N = 30 knots; BASELINE.json configs[1]) with the batched interior-point kernel.  Under torchrun each
-rank solves its own 1k block of a (1k x n_gpus) grid (weak scaling, no data-path collective) and the
-step ends with ONE NCCL all-gather of the per-scenario result records (x*, f*, status, iters).
+(SRB landing sweep on a height x pitch x roll x forward-velocity grid of drop conditions) with the batched
+interior-point kernel.  Under torchrun each rank solves its interleaved shard of the sweep (no data-path
+collective) and the step ends with ONE NCCL all-gather of the per-scenario result records (x*, f*, status, iters),
+in the device-resident arm and in the end-to-end arm alike.
 
     python bench.py [--gpus N] [--steps K] [--warmup W]        # this repo's CUDA path
-    python bench.py --impl reference ...                        # the CPU path on the host cores
+    python bench.py --impl reference ...                        # the CPU path on the host cores (same config object)
+    one GPU: BASELINE configs[1] (1k grid, N = 30); under torchrun: configs[2], the FIXED 16k x N = 50 sweep strong-scaled
 
 Prints ONE JSON line (rank 0).
 """
@@ -25,18 +26,50 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-KNOTS = 30
-BATCH = 1024
 METRIC = "converged landing NLPs/sec (FP64, batch)"
 UNIT = "NLP/s"
 
+# BASELINE.json configs -> concrete workloads.  One GPU runs configs[1]; under torchrun (N > 1) the FIXED
+# 16384-drop N = 50 sweep of configs[2] is strong-scaled over the ranks (interleaved shards), which is the workload the
+# >= 100 x target is quoted on.  `--config` overrides.
+CONFIGS = {
+    "1k": dict(knots=30, total=1024, scaling="weak",
+               workload="BASELINE configs[1]: SRB landing sweep, 1024 grid drop conditions (height x pitch x roll x v_x, v_z=-3), N=30 knots"),
+    "16k": dict(knots=50, total=16384, scaling="strong",
+                workload="BASELINE configs[2]: SRB landing sweep, 16384 grid drop conditions (height x pitch x roll x v_x, v_z=-3), N=50 knots, strong-scaled over the GPUs"),
+}
 
-def workload(n_gpus, rank, batch):
+
+def pick_config(args, world):
+    name = args.config if args.config != "auto" else ("1k" if world == 1 else "16k")
+    cfg = dict(CONFIGS[name])
+    cfg["name"] = name
+    if args.knots:
+        cfg["knots"] = args.knots
+    if args.batch:
+        cfg["total"] = args.batch * (world if cfg["scaling"] == "weak" else 1)
+    elif cfg["scaling"] == "weak":
+        cfg["total"] = cfg["total"] * world
+    return cfg
+
+
+def config_dict(cfg, world):
+    """The `config` object of the JSON line: identical in the GPU arm and the reference arm of one (config, N)."""
+    return {"workload": cfg["workload"], "knots": cfg["knots"], "global_batch": cfg["total"],
+            "batch_per_gpu": cfg["total"] // world,
+            "parallelism": "scenario-sharded x%d (interleaved shards of the %d-scenario sweep), one all-gather of the result records"
+                           % (world, cfg["total"]),
+            "options": "tol 1e-4, constr_viol_tol 1e-3, max_iter 3000 (generate_landingCtrller_IPOPT.m:232-236)",
+            "l2": "GPU arm: the per-scenario solver scratch of the 296 resident CTAs (%.2f GB) exceeds the 126 MB L2 and "
+                  "every step rewrites all of it; no flush needed" % (1e-9 * scratch_bytes(cfg["knots"], 296))}
+
+
+def workload(cfg, world, rank):
     import landing_controller_b200 as lc
-    allb = lc.grid_sweep(batch * n_gpus)
+    allb = lc.grid_sweep(cfg["total"])
     # interleaved shards: the iteration count grows along the axes of the grid, contiguous blocks would give the last
     # rank the hard end of the sweep
-    return allb[lc.shard_indices(batch * n_gpus, n_gpus, rank, "interleaved")].copy()
+    return allb[lc.shard_indices(cfg["total"], world, rank, "interleaved")].copy()
 
 
 def iter_bytes(N):
@@ -130,66 +163,95 @@ def measured_peaks():
 
 
 def cpu_run(N, drops, threads):
+    """The timed CPU arm: oracle/ip_ref.c built -O3 -march=native on this host (the reference builds its C with gcc -O3,
+    generate_landingCtrller_IPOPT.m:296), OpenMP over scenarios."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_ip import solve_cpu
     t = time.perf_counter()
-    r = solve_cpu(N, drops, threads=threads)
+    r = solve_cpu(N, drops, threads=threads, fast=True)
     dt = time.perf_counter() - t
     return r, dt
+
+
+def cpu_sample(cfg, drops, want):
+    """Bounded strided sample of a sweep for the CPU arm (about 5-15 s of work on 16 host threads per step)."""
+    n = want or (1024 if cfg["knots"] <= 30 else 512)
+    n = min(n, len(drops))
+    stride = max(1, len(drops) // n)
+    return drops[::stride][:n], stride
+
+
+def cpu_flags():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_ip import fast_build_flags
+    return fast_build_flags()
 
 
 def run_reference(args):
     """The reference's CPU path for the hot path, on the host cores.  IPOPT/MUMPS are not available
     (SURVEY.md 8c), so this is the CPU restatement (oracle/: generated-function restatement +
-    interior-point "IPOPT substitute"), OpenMP over scenarios with all host threads."""
+    interior-point "IPOPT substitute"), OpenMP over scenarios with all host threads, on a bounded strided sample of the
+    SAME workload (same config object) as the GPU arm of this --gpus value."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
+    cfg = pick_config(args, world)
+    N = cfg["knots"]
     cores = os.cpu_count() or 1
-    sample = args.cpu_sample or args.batch  # default: the whole sweep (about 10 s on 16 host threads)
-    drops = workload(1, 0, args.batch)
-    sub = drops[:: max(1, len(drops) // sample)][:sample]
+    drops = workload(cfg, 1, 0)  # the whole sweep
+    sub, stride = cpu_sample(cfg, drops, args.cpu_sample)
     for _ in range(min(args.warmup, 1)):
-        cpu_run(KNOTS, sub[:cores], cores)
+        cpu_run(N, sub[:cores], cores)
     tot_t, tot_c, tot_it = 0.0, 0, 0
     for _ in range(args.steps):
-        r, dt = cpu_run(KNOTS, sub, cores)
+        r, dt = cpu_run(N, sub, cores)
         tot_t += dt
         tot_c += int((r["status"] == 0).sum())
         tot_it += int(r["iters"].sum())
     val = tot_c / tot_t
+    sample = ("%d of %d scenarios per step (every %d-th), %d steps; IPOPT substitute (oracle/ip_ref.c, %s), OpenMP over scenarios"
+              % (len(sub), cfg["total"], stride, args.steps, cpu_flags()))
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "SRB landing sweep, grid drop conditions, N=%d knots; %d-scenario strided sample of the %d-scenario sweep per step"
-                   % (KNOTS, len(sub), args.batch), "knots": KNOTS, "batch": len(sub)},
-        "kkt_iters_per_s": tot_it / tot_t,
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": "%d of %d scenarios per step (every %d-th), %d steps; IPOPT substitute (oracle/ip_ref.c), OpenMP over scenarios"
-                         % (len(sub), args.batch, max(1, len(drops) // sample), args.steps)},
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+        "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config_dict(cfg, world),
+        "kkt_iters_per_s": tot_it / tot_t, "converged_fraction": tot_c / float(len(sub) * args.steps),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
 
 
+def iter_stats(its, st):
+    its = np.asarray(its, dtype=np.float64)
+    q = lambda f: float(np.percentile(its, f))
+    return {"mean": float(its.mean()), "p50": q(50), "p90": q(90), "p99": q(99), "max": float(its.max()),
+            "status_counts": {str(k): int(v) for k, v in zip(*np.unique(np.asarray(st), return_counts=True))}}
+
+
 def main():
-    global KNOTS
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--batch", type=int, default=BATCH)
-    ap.add_argument("--knots", type=int, default=KNOTS, help="knots per trajectory (BASELINE configs: 30; 50 for the 16k sweep)")
-    ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios in the cpu_baseline sample (0 = auto)")
+    ap.add_argument("--config", default="auto", choices=["auto", "1k", "16k"],
+                    help="auto: BASELINE configs[1] on one GPU, configs[2] (fixed 16k x N=50 sweep, strong-scaled) under torchrun")
+    ap.add_argument("--batch", type=int, default=0, help="override: scenarios per GPU (weak configs) / in total (strong)")
+    ap.add_argument("--knots", type=int, default=0, help="override: knots per trajectory")
+    ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios in the CPU sample (0 = auto)")
+    ap.add_argument("--no-eval-kernels", action="store_true", help="skip the evaluation-kernel roofline lines")
+    ap.add_argument("--no-one-gpu-base", action="store_true",
+                    help="N > 1: skip the 1-GPU solve of the same fixed workload on rank 0 (strong-scaling base)")
     args = ap.parse_args()
-    KNOTS = args.knots
     if args.impl == "reference":
         run_reference(args)
         return
 
+    import ctypes
     import torch
     import torch.distributed as dist
     import landing_controller_b200 as lc
@@ -203,45 +265,64 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, N = args.batch, KNOTS
+    cfg = pick_config(args, world)
+    N = cfg["knots"]
     solver = lc.LandingSolver(N=N, device=local_rank)
     nx = solver.dims["nx"]
-    drops_h = workload(world, rank, B)
+    drops_h = workload(cfg, world, rank)
+    B = len(drops_h)
+    Bmax = -(-cfg["total"] // world)  # shards differ by at most one scenario: records are padded for the all-gather
 
     # device-resident arm: inputs already in HBM when the timed region starts
     drops_d = torch.tensor(drops_h, device=dev)
-    rec = torch.zeros(B, nx + 3, dtype=torch.float64, device=dev)  # result record [x*, f*, status, iters]
+    rec = torch.zeros(Bmax, nx + 3, dtype=torch.float64, device=dev)  # result record [x*, f*, status, iters]
     x_d = torch.zeros(B, nx, dtype=torch.float64, device=dev)
     f_d = torch.zeros(B, dtype=torch.float64, device=dev)
     st_d = torch.zeros(B, dtype=torch.int32, device=dev)
     it_d = torch.zeros(B, dtype=torch.int32, device=dev)
-    gathered = torch.zeros(world * B, nx + 3, dtype=torch.float64, device=dev) if world > 1 else None
+    gathered = torch.zeros(world * Bmax, nx + 3, dtype=torch.float64, device=dev) if world > 1 else None
     lib_stream = torch.cuda.ExternalStream(solver.stream_ptr, device=dev)
 
-    def step_device():
-        solver.solve_device(drops_d, x_d, f_d, st_d, it_d)
-        if world > 1:
-            with torch.cuda.stream(lib_stream):
-                rec[:, :nx] = x_d
-                rec[:, nx] = f_d
-                rec[:, nx + 1] = st_d.double()
-                rec[:, nx + 2] = it_d.double()
-                dist.all_gather_into_tensor(gathered, rec)
+    def gather():
+        # ONE NCCL all-gather of the per-scenario result records, on the solver's stream (north_star)
+        with torch.cuda.stream(lib_stream):
+            rec[:B, :nx] = x_d
+            rec[:B, nx] = f_d
+            rec[:B, nx + 1] = st_d.double()
+            rec[:B, nx + 2] = it_d.double()
+            dist.all_gather_into_tensor(gathered, rec)
 
-    # end-to-end arm: pinned host buffers through the C ABI, copies inside the timed region
-    pin = lambda *s, dt=torch.float64: torch.empty(*s, dtype=dt).pin_memory()
+    def step_device():
+        solver.solve_device(drops_d, x_d, f_d, st_d, it_d, order_streams=False)
+        if world > 1:
+            gather()
+
+    # end-to-end arm: HOST buffers (pinned), host<->device copies inside the timed region.
+    #   one GPU : the reference-facing C-ABI call landing_solve_batch(LANDING_HOST) does the copies itself
+    #   N GPUs  : drops host -> device, solve, all-gather, the WHOLE sweep's records device -> host on every rank
+    pin = lambda *sh, dt=torch.float64: torch.empty(*sh, dtype=dt).pin_memory()
     drops_p = pin(B, 12)
     drops_p.copy_(torch.from_numpy(drops_h))
     x_p, f_p, v_p = pin(B, nx), pin(B), pin(B)
     st_p, it_p = pin(B, dt=torch.int32), pin(B, dt=torch.int32)
     io = lc.api.SolveIO(lc.api._ptr(drops_p), None, lc.api._ptr(x_p), lc.api._ptr(f_p), None, lc.api._ptr(v_p),
                         lc.api._ptr(st_p, lc.api._ip), lc.api._ptr(it_p, lc.api._ip))
-    import ctypes
+    gathered_p = pin(world * Bmax, nx + 3) if world > 1 else None
+    drops_e = torch.zeros(B, 12, dtype=torch.float64, device=dev)
 
     def step_e2e():
-        rc = solver.lib.landing_solve_batch(solver.ctx, B, lc.HOST, ctypes.byref(solver.problem),
-                                            ctypes.byref(solver.options), ctypes.byref(io))
-        assert rc == 0, solver.lib.landing_last_error()
+        if world == 1:
+            rc = solver.lib.landing_solve_batch(solver.ctx, B, lc.HOST, ctypes.byref(solver.problem),
+                                                ctypes.byref(solver.options), ctypes.byref(io))
+            assert rc == 0, solver.lib.landing_last_error()
+        else:
+            with torch.cuda.stream(lib_stream):
+                drops_e.copy_(drops_p, non_blocking=True)
+            solver.solve_device(drops_e, x_d, f_d, st_d, it_d, order_streams=False)
+            gather()
+            with torch.cuda.stream(lib_stream):
+                gathered_p.copy_(gathered, non_blocking=True)
+            solver.synchronize()
 
     def barrier():
         torch.cuda.synchronize()
@@ -280,82 +361,121 @@ def main():
         dist.all_reduce(stats)
     conv_per_step, iters_per_step = float(stats[0].item()), float(stats[1].item())
     value = conv_per_step * args.steps / (ms * 1e-3)
+    if world > 1:
+        g = gathered.cpu().numpy().reshape(world, Bmax, nx + 3)
+        all_its = np.concatenate([g[r, :len(lc.shard_indices(cfg["total"], world, r)), nx + 2] for r in range(world)])
+        all_st = np.concatenate([g[r, :len(lc.shard_indices(cfg["total"], world, r)), nx + 1] for r in range(world)])
+    else:
+        all_its, all_st = its, st
 
     for _ in range(min(args.warmup, 1)):
         step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-    st_e = st_p.numpy()
-    conv_e = torch.tensor([float((st_e == 0).sum())], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(conv_e)
-    e2e_value = float(conv_e.item()) * args.steps / (ms_e2e * 1e-3)
+    if world == 1:
+        conv_e = float((st_p.numpy() == 0).sum())
+        h2d, d2h = B * 12 * 8, B * (nx + 2) * 8 + B * 8
+    else:
+        ge = gathered_p.numpy().reshape(world, Bmax, nx + 3)
+        conv_e = float(sum((ge[r, :len(lc.shard_indices(cfg["total"], world, r)), nx + 1] == 0).sum() for r in range(world)))
+        h2d, d2h = B * 12 * 8, world * Bmax * (nx + 3) * 8
+    e2e_value = conv_e * args.steps / (ms_e2e * 1e-3)
+
+    # strong-scaling base: the same fixed workload solved by ONE GPU (rank 0) in the same run
+    one_gpu = None
+    if world > 1 and not args.no_one_gpu_base:
+        if rank == 0:
+            full = torch.tensor(workload(cfg, 1, 0), device=dev)
+            Bf = full.shape[0]
+            xf = torch.zeros(Bf, nx, dtype=torch.float64, device=dev)
+            ff = torch.zeros(Bf, dtype=torch.float64, device=dev)
+            sf = torch.zeros(Bf, dtype=torch.int32, device=dev)
+            itf = torch.zeros(Bf, dtype=torch.int32, device=dev)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(lib_stream):
+                e0.record()
+            solver.solve_device(full, xf, ff, sf, itf, order_streams=False)
+            with torch.cuda.stream(lib_stream):
+                e1.record()
+            torch.cuda.synchronize()
+            t1 = e0.elapsed_time(e1)
+            one_gpu = {"n_gpus": 1, "value": float((sf == 0).sum().item()) / (t1 * 1e-3), "unit": UNIT, "ms_per_step": t1,
+                       "note": "the whole %d-scenario sweep on rank 0's GPU alone, one step, same run" % Bf}
+        dist.barrier()
 
     if rank == 0:
         hbm_peak, peak_src = measured_peaks()
-        kernel_ms = ms / args.steps  # one launch per step; the all-gather (N>1) rides on the same stream
+        kernel_ms = ms / args.steps  # one k_solve launch per step; the all-gather (N>1) rides on the same stream
         local_iters = float(its.sum())
-        achieved = iter_bytes(N) * local_iters / (kernel_ms * 1e-3) / 1e9
+        hbm_ach = iter_bytes(N) * local_iters / (kernel_ms * 1e-3) / 1e9
         fp64_peak = solver.fp64_peak_tflops()
         fp64_ach = iter_flops(N) * local_iters / (kernel_ms * 1e-3) / 1e12
         tr = ncu_traffic()
+        tr_ok = tr and tr.get("knots") == N and tr.get("batch") == B
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "SRB landing sweep, %d grid drop conditions per GPU (height x pitch x roll x v_x, v_z=-3), N=%d knots"
-                       % (B, N), "knots": N, "batch_per_gpu": B, "global_batch": B * world,
-                       "parallelism": "scenario-sharded x%d (interleaved shards of the %d-scenario grid), one all-gather of results"
-                                      % (world, B * world),
-                       "l2": "per-scenario solver scratch of the 296 resident CTAs (%.2f GB) exceeds the 126 MB L2 and "
-                             "every step rewrites all of it; no flush needed" % (1e-9 * scratch_bytes(N, 296)),
-                       "options": "tol 1e-4, constr_viol_tol 1e-3, max_iter 3000 (generate_landingCtrller_IPOPT.m:232-236)"},
-            "converged_per_step": conv_per_step, "scenarios_per_step": B * world,
+            "config": config_dict(cfg, world),
+            "converged_per_step": conv_per_step, "scenarios_per_step": cfg["total"],
             "kkt_iters_per_s": iters_per_step * args.steps / (ms * 1e-3),
+            "iters": iter_stats(all_its, all_st),
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * 12 * 8,
-                    "d2h_bytes_per_step": B * (nx + 2) * 8 + B * 8, "ms_per_step": ms_e2e / args.steps},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak,
-                         "traffic": (tr or {}).get("dram_bytes_per_launch"), "traffic_source": (tr or {}).get("source"),
-                         "peak_source": peak_src,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps,
+                    "path": ("landing_solve_batch(LANDING_HOST): pinned host buffers through the C ABI" if world == 1 else
+                             "per rank: drops host->device, landing_solve_batch(LANDING_DEVICE), NCCL all-gather of the "
+                             "records, whole sweep device->host")},
+            # the interior-point kernel is FP64-pipe bound by design: the binding line leads
+            "roofline": {"bound": "fp64", "achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": fp64_ach / fp64_peak if fp64_peak else None,
+                         "peak_source": "measured in this run (landing_fp64_peak: DFMA micro-kernel, CUDA events; "
+                                        "MEASURED_PEAKS.json has no FP64 entry)",
+                         "traffic": (tr or {}).get("dram_bytes_per_launch") if tr_ok else None,
+                         "traffic_source": (tr or {}).get("source") if tr_ok else None,
                          "kernel": "k_solve", "units_per_launch": local_iters,
-                         "bytes_per_unit": iter_bytes(N), "flops_per_unit": iter_flops(N),
-                         "fp64": {"achieved": fp64_ach, "peak": fp64_peak, "unit": "TFLOP/s",
-                                  "frac": fp64_ach / fp64_peak if fp64_peak else None,
-                                  "peak_source": "measured in this run (landing_fp64_peak: DFMA micro-kernel, CUDA events)"},
-                         "note": "one launch per step = all interior-point iterations of the batch; unit = one KKT "
-                                 "iteration of one scenario; the kernel is FP64-latency bound (DESIGN.md 2.3), the hbm "
-                                 "line uses the algorithmic bytes of SURVEY 8d-ii, the fp64 line the algorithmic flops"},
+                         "flops_per_unit": iter_flops(N), "bytes_per_unit": iter_bytes(N),
+                         "hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": hbm_ach / hbm_peak, "peak_source": peak_src},
+                         "note": "one launch per step = all interior-point iterations of the rank's scenarios; unit = one "
+                                 "KKT iteration of one scenario; achieved = algorithmic flops (one factorisation per "
+                                 "iteration, DESIGN.md 2.3) / CUDA-event time; the hbm line uses the algorithmic bytes of "
+                                 "SURVEY 8d-ii"},
         }
-        # the evaluation kernels (HBM-bound rows a-3..a-5 of SURVEY 8): 16k scenarios, SoA, a few milliseconds
-        try:
-            sys.path.insert(0, os.path.join(ROOT, "tools"))
-            from bench_eval import cpu_reference, measure
-            keys = ("function", "N", "B", "layout", "ms", "achieved", "peak", "unit", "frac", "evals_per_s")
-            line["roofline"]["eval_kernels"] = [
-                {k: r[k] for k in keys} for r in measure(N, 16384, 10, "soa", solver=solver, device=local_rank)]
-            # the size the reference ships generated C for (N = 21), with the reference's own compiled functions
-            # timed on the host cores beside it (oracle/_ref, kind "reference")
-            ref = cpu_reference()
-            s21 = lc.LandingSolver(N=21, device=local_rank)
-            rows = [{k: r[k] for k in keys} for r in measure(21, 16384, 10, "soa", solver=s21, device=local_rank)]
-            s21.close()
-            for r in rows:
-                r["cpu_baseline"] = ref.get(r["function"]) if ref else None
-            line["roofline"]["eval_kernels_n21"] = rows
-        except Exception as e:  # reported, never hidden
-            line["roofline"]["eval_kernels"] = {"error": repr(e)}
-        # CPU baseline on the host cores (bounded sample of the same workload)
-        cores = os.cpu_count() or 1
-        ns = args.cpu_sample or B  # default: the whole sweep of rank 0 (about 10 s on 16 host threads)
-        sub = drops_h[:: max(1, B // ns)][:ns]
-        r, dt = cpu_run(N, sub, cores)
-        line["cpu_baseline"] = {
-            "value": float((r["status"] == 0).sum()) / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "kkt_iters_per_s": float(r["iters"].sum()) / dt,
-            "sample": "%d of %d scenarios (every %d-th), %.1f s; IPOPT substitute oracle/ip_ref.c, OpenMP over scenarios"
-                      % (len(sub), B, max(1, B // ns), dt)}
+        if one_gpu:
+            line["one_gpu_same_workload"] = one_gpu
+            line["strong_scaling_efficiency_vs_one_gpu"] = value / (world * one_gpu["value"])
+        if world == 1 and not args.no_eval_kernels:
+            # the evaluation kernels (HBM-bound rows a-3..a-6 of SURVEY 8): 16k scenarios, SoA, a few milliseconds
+            try:
+                sys.path.insert(0, os.path.join(ROOT, "tools"))
+                from bench_eval import cpu_reference, measure
+                keys = ("function", "N", "B", "layout", "ms", "achieved", "peak", "unit", "frac", "evals_per_s")
+                line["roofline"]["eval_kernels"] = [
+                    {k: r[k] for k in keys} for r in measure(N, 16384, 10, "soa", solver=solver, device=local_rank)]
+                # the size the reference ships generated C for (N = 21), with the reference's own compiled functions
+                # timed on the host cores beside it (oracle/_ref, kind "reference")
+                ref = cpu_reference()
+                s21 = lc.LandingSolver(N=21, device=local_rank)
+                rows = [{k: r[k] for k in keys} for r in measure(21, 16384, 10, "soa", solver=s21, device=local_rank)]
+                s21.close()
+                for r in rows:
+                    r["cpu_baseline"] = ref.get(r["function"]) if ref else None
+                line["roofline"]["eval_kernels_n21"] = rows
+            except Exception as e:  # reported, never hidden
+                line["roofline"]["eval_kernels"] = {"error": repr(e)}
+        if world == 1:
+            # CPU baseline on the host cores (bounded sample of the same workload; rank 0 at N = 1 only)
+            cores = os.cpu_count() or 1
+            sub, stride = cpu_sample(cfg, drops_h, args.cpu_sample)
+            cpu_run(N, sub[:cores], cores)  # (builds the -O3 library, warms the threads)
+            r, dt = cpu_run(N, sub, cores)
+            line["cpu_baseline"] = {
+                "value": float((r["status"] == 0).sum()) / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                "kkt_iters_per_s": float(r["iters"].sum()) / dt,
+                "sample": "%d of %d scenarios (every %d-th), %.1f s; IPOPT substitute oracle/ip_ref.c (%s), OpenMP over scenarios"
+                          % (len(sub), B, stride, dt, cpu_flags())}
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

@@ -97,6 +97,11 @@ typedef struct landing_problem {
    * analysis/eval_SRBM_CCC.m:49-52: QX = Qc = 0, Qf = (1e-4, 1e-4, 1e-3), box 0.05/0.05/0.27).
    * Defaults {0,0,0} and {0.15, 0.15, 0.30} = generate_landingCtrller_IPOPT.m:83-85,150-155. */
   double Qf[3], kin_box[3];
+  /* Knot spacings dt[0..N-2] (HOST pointer, read during the call), or NULL for the uniform T/(N-1).  The reference's
+   * callers pass dt as a vector: uniform in the generator's own test call (generate_landingCtrller_IPOPT.m:195,319-327),
+   * NON-uniform in the sweep / MPC callers: dt_val = [0.05 0.02x15 0.05 0.05 0.1 0.2] for N = 21
+   * (generate_data/generate_training_data_automated.m:28,130-136; main_scripts/landing_optimization.m:28,305-311). */
+  const double *dt;
 } landing_problem;
 
 void landing_problem_default(landing_problem *pb);
@@ -119,7 +124,7 @@ typedef struct landing_options {
   double bound_push;         /* 0.5 */
   double bound_frac;         /* 0.5 */
   double bound_relax_factor; /* 1e-6 */
-  int max_soc;               /* 4 */
+  int max_soc;               /* 4 -- ACCEPTED BUT UNUSED: no second-order correction is implemented (see below) */
   /* Jamming watchdog (this library's substitute for IPOPT's restoration phase, which the restatement does not
    * have): when the accepted primal step length stays below jam_alpha for jam_iters consecutive iterations the
    * iterate is re-centred exactly as after a failed line search (slacks pushed back inside their bounds,
@@ -133,6 +138,12 @@ typedef struct landing_options {
   int reserved[5];
 } landing_options;
 
+/* IPOPT options the reference sets (generate_landingCtrller_IPOPT.m:232-263) that this solver does NOT implement:
+ * mu_strategy = adaptive / mu_oracle = probing (monotone Fiacco-McCormick update instead), max_soc (no second-order
+ * correction), min/max_refinement_steps (no iterative refinement of the Riccati solve), nlp_scaling_method =
+ * gradient-based (never triggers at the reference's initial guesses: max |J(x0)| <= 50), acceptable_tol /
+ * acceptable_iter (only the strict tolerances terminate), and IPOPT's restoration phase (replaced by re-centring with
+ * the watchdog above).  DESIGN.md section 3 lists the measured consequences. */
 void landing_options_default(landing_options *opt);
 
 /* Solve B independent landing NLPs, one per drop condition (replaces one call of the
@@ -172,6 +183,15 @@ int landing_tvlqr_batch(landing_ctx *ctx, long long B, int memspace, const landi
 /* Measured FP64 FMA throughput of the context's device in TFLOP/s (a DFMA micro-kernel timed with CUDA
  * events): the roofline denominator of the interior-point kernel, which is FP64-pipe bound by design. */
 int landing_fp64_peak(landing_ctx *ctx, double *tflops);
+
+/* STREAM CONTRACT.  Every context owns one non-blocking CUDA stream (landing_stream).  Calls with LANDING_HOST buffers
+ * copy in, run and copy out on it and return after synchronising it.  Calls with LANDING_DEVICE buffers only ENQUEUE work
+ * on it and return immediately: the caller orders its own streams against landing_stream(ctx) -- inputs produced on
+ * another stream need an event wait before the call, consumers an event wait after it (cudaStreamWaitEvent), or call
+ * landing_synchronize().  A context is not thread-safe (one host thread at a time per context); different contexts,
+ * also on the same device, may be used concurrently from different threads.  Every call leaves the calling thread's
+ * current CUDA device as it found it. */
+int landing_synchronize(landing_ctx *ctx);
 
 /* number of kernel launches issued by this context so far (bench accounting) */
 long long landing_launch_count(const landing_ctx *ctx);

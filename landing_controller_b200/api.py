@@ -42,7 +42,7 @@ class Problem(ctypes.Structure):
         ("c_ref", ctypes.c_double * 12), ("QN", ctypes.c_double * 12),
         ("mu", ctypes.c_double), ("l_leg_max", ctypes.c_double), ("f_max", ctypes.c_double),
         ("mass", ctypes.c_double), ("Ib", ctypes.c_double * 3), ("Ib_inv", ctypes.c_double * 3),
-        ("Qf", ctypes.c_double * 3), ("kin_box", ctypes.c_double * 3)]
+        ("Qf", ctypes.c_double * 3), ("kin_box", ctypes.c_double * 3), ("dt", _dp)]
 
 
 class Options(ctypes.Structure):
@@ -92,6 +92,15 @@ def load_library(path=LIB_PATH):
     lib.landing_stream.restype = ctypes.c_void_p
     lib.landing_stream.argtypes = [ctypes.c_void_p]
     lib.landing_dims_for.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
+    lib.landing_problem_default.argtypes = [ctypes.POINTER(Problem)]
+    lib.landing_problem_default.restype = None
+    lib.landing_options_default.argtypes = [ctypes.POINTER(Options)]
+    lib.landing_options_default.restype = None
+    lib.landing_tvlqr_default.argtypes = [ctypes.POINTER(Tvlqr)]
+    lib.landing_tvlqr_default.restype = None
+    lib.landing_tvlqr_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.POINTER(Tvlqr),
+                                        _dp, _dp, _dp]
+    lib.landing_synchronize.argtypes = [ctypes.c_void_p]
     return lib
 
 
@@ -107,6 +116,8 @@ def sparsity_for(N, which, lib=None):
     """CasADi CCS array of which = 0 jac_g, 1 hess_l (upper), 2 x, 3 p, 4 scalar, 5 g. No GPU needed."""
     lib = lib or load_library()
     s = lib.landing_sparsity_for(N, which)
+    if not s:
+        raise ValueError("landing_sparsity_for(N=%d, which=%d): need N >= 3 and which in 0..5" % (N, which))
     ncol = s[1]
     nnz = s[2 + ncol]
     return np.ctypeslib.as_array(s, shape=(2 + ncol + 1 + nnz,)).copy()
@@ -138,6 +149,21 @@ class LandingSolver:
         self.lib.landing_problem_default(ctypes.byref(self.problem))
         self.options = Options()
         self.lib.landing_options_default(ctypes.byref(self.options))
+
+    def set_dt(self, dt=None):
+        """Knot spacings dt[0..N-2] (non-uniform grids of the reference's sweep / MPC callers,
+        generate_training_data_automated.m:28), or None for the uniform T/(N-1).  Also sets T = sum(dt)."""
+        if dt is None:
+            self._dt = None
+            self.problem.dt = None
+            return self
+        dt = np.ascontiguousarray(dt, dtype=np.float64)
+        if dt.shape != (self.N - 1,):
+            raise ValueError("dt must have N-1 = %d entries" % (self.N - 1))
+        self._dt = dt  # keeps the host array alive: the library reads it during each call
+        self.problem.dt = dt.ctypes.data_as(_dp)
+        self.problem.T = float(dt.sum())
+        return self
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -228,6 +254,10 @@ class LandingSolver:
         Nlpsol does after the solve (nlpsol.cpp:609-625): one nlp_grad evaluation at (x*, lam_f = 1, lam_g*);
         lam_x = -grad_gamma_x is ~0 here (the reference passes no variable bounds), lam_p = -grad_gamma_p."""
         want_lam = want_lam or want_lam_p
+        if want_lam_p and any(self.problem.Qf[i] != 0.0 for i in range(3)):
+            # lam_x / lam_p come from nlp_grad of the landingCtrller_IPOPT functions, which have no running GRF cost
+            raise ValueError("want_lam_p is defined for the landingCtrller_IPOPT problem only (problem.Qf must be 0): "
+                             "the generated functions behind nlp_grad do not contain the running cost of the CCC variant")
         drops = np.ascontiguousarray(drops, dtype=np.float64)
         B = drops.shape[0]
         d = self.dims
@@ -266,14 +296,27 @@ class LandingSolver:
                     "landing_tvlqr_batch")
         return (P, K) if want_K else P
 
-    def solve_device(self, drops, x_star, f_star, status, iters, viol=None, lam_g=None, x0=None):
-        """All arguments are CUDA torch tensors already resident in HBM (no copies)."""
+    def synchronize(self):
+        self._check(self.lib.landing_synchronize(self.ctx), "landing_synchronize")
+
+    def solve_device(self, drops, x_star, f_star, status, iters, viol=None, lam_g=None, x0=None, order_streams=True):
+        """All arguments are CUDA torch tensors already resident in HBM (no copies).  The library only ENQUEUES on its
+        own stream (include/landing_b200.h, stream contract): with order_streams the library stream first waits for the
+        caller's current torch stream (the producers of the inputs) and the caller's stream then waits for the library
+        stream, so that the call behaves like any other op on the current stream."""
         B = drops.shape[0]
+        if order_streams:
+            import torch
+            lib_stream = torch.cuda.ExternalStream(self.stream_ptr, device=drops.device)
+            cur = torch.cuda.current_stream(drops.device)
+            lib_stream.wait_stream(cur)
         io = SolveIO(_ptr(drops), _ptr(x0), _ptr(x_star), _ptr(f_star), _ptr(lam_g), _ptr(viol),
                      _ptr(status, _ip), _ptr(iters, _ip))
         self._check(self.lib.landing_solve_batch(self.ctx, B, DEVICE, ctypes.byref(self.problem),
                                                  ctypes.byref(self.options), ctypes.byref(io)),
                     "landing_solve_batch")
+        if order_streams:
+            cur.wait_stream(lib_stream)
 
 
 def contact_set(x, N, thresh=1.0):

@@ -22,6 +22,15 @@ int fail(int code, const std::string& msg) {
     if (e_ != cudaSuccess)                                                                    \
       return fail(LANDING_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));      \
   } while (0)
+// restores the calling thread's current device when an entry point returns
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) cudaSetDevice(dev); else prev = -1;
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
 }  // namespace
 
 struct landing_ctx {
@@ -38,7 +47,25 @@ struct landing_ctx {
   void* tr = nullptr;
   size_t tr_bytes = 0;
   SolverWorkspace ws;
+  // knot spacings of the current call: pinned host staging + device copy (landing_problem.dt or uniform)
+  double* h_dt = nullptr;
+  double* d_dt = nullptr;
 };
+
+// dt[0..N-2] of this call on the device (stream-ordered): the caller's vector or the uniform T/(N-1)
+static int stage_dt(landing_ctx* c, const landing_problem* pb) {
+  const int K = c->N - 1;
+  if (!c->h_dt) CU(cudaMallocHost(&c->h_dt, sizeof(double) * K));
+  if (!c->d_dt) CU(cudaMalloc(&c->d_dt, sizeof(double) * K));
+  CU(cudaStreamSynchronize(c->stream));  // the previous call's copy out of h_dt has completed
+  for (int k = 0; k < K; k++) {
+    const double h = pb->dt ? pb->dt[k] : pb->T / (double)K;
+    if (!(h > 0.0)) return fail(LANDING_ERR_ARG, "landing_problem: knot spacings must be positive");
+    c->h_dt[k] = h;
+  }
+  CU(cudaMemcpyAsync(c->d_dt, c->h_dt, sizeof(double) * K, cudaMemcpyHostToDevice, c->stream));
+  return LANDING_OK;
+}
 
 static int ensure_tr(landing_ctx* c, size_t bytes) {
   if (bytes <= c->tr_bytes) return LANDING_OK;
@@ -61,6 +88,8 @@ static int ensure_stage(landing_ctx* c, size_t bytes) {
 }
 
 extern "C" {
+
+void landing_destroy(landing_ctx* c);
 
 const char* landing_last_error(void) { return g_err.c_str(); }
 
@@ -95,19 +124,24 @@ int landing_create(int N, int device, landing_ctx** out) {
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(LANDING_ERR_NOGPU, "landing_create: no CUDA device (this library has no CPU path)");
   if (device < 0 || device >= ndev) return fail(LANDING_ERR_ARG, "landing_create: bad device index");
-  CU(cudaSetDevice(device));
+  DeviceGuard guard_(device);
   landing_ctx* c = new landing_ctx();
   c->N = N;
   c->device = device;
   c->plan = get_plan(N);
   const HostPlan& pl = *c->plan;
-  CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   const size_t nj = pl.jmap.size(), nh = pl.hmap.size();
-  CU(cudaMalloc(&c->d_maps, sizeof(int) * (nj + nh + 36 + 12)));
-  CU(cudaMemcpy(c->d_maps, pl.jmap.data(), sizeof(int) * nj, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(c->d_maps + nj, pl.hmap.data(), sizeof(int) * nh, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(c->d_maps + nj + nh, pl.jbnd, sizeof(int) * 36, cudaMemcpyHostToDevice));
-  CU(cudaMemcpy(c->d_maps + nj + nh + 36, pl.hterm, sizeof(int) * 12, cudaMemcpyHostToDevice));
+  // (any failure below releases what was created: no leaked context, stream or device memory)
+  cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_maps, sizeof(int) * (nj + nh + 36 + 12));
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_maps, pl.jmap.data(), sizeof(int) * nj, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_maps + nj, pl.hmap.data(), sizeof(int) * nh, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_maps + nj + nh, pl.jbnd, sizeof(int) * 36, cudaMemcpyHostToDevice);
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_maps + nj + nh + 36, pl.hterm, sizeof(int) * 12, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) {
+    landing_destroy(c);
+    return fail(LANDING_ERR_CUDA, std::string("landing_create: ") + cudaGetErrorString(e));
+  }
   c->dpl = DevicePlan{pl.N, pl.nx, pl.np, pl.m, pl.nnzJ, pl.nnzH, pl.off,
                       c->d_maps, c->d_maps + nj, c->d_maps + nj + nh, c->d_maps + nj + nh + 36};
   *out = c;
@@ -116,11 +150,13 @@ int landing_create(int N, int device, landing_ctx** out) {
 
 void landing_destroy(landing_ctx* c) {
   if (!c) return;
-  cudaSetDevice(c->device);
+  DeviceGuard guard_(c->device);
   solver_free(c->ws);
   if (c->stage) cudaFree(c->stage);
   if (c->tr) cudaFree(c->tr);
   if (c->d_maps) cudaFree(c->d_maps);
+  if (c->d_dt) cudaFree(c->d_dt);
+  if (c->h_dt) cudaFreeHost(c->h_dt);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -136,9 +172,16 @@ const long long* landing_sparsity(const landing_ctx* c, int which) {
 
 long long landing_launch_count(const landing_ctx* c) { return c ? c->launches : 0; }
 
+int landing_synchronize(landing_ctx* c) {
+  if (!c) return fail(LANDING_ERR_ARG, "landing_synchronize: null ctx");
+  DeviceGuard guard_(c->device);
+  CU(cudaStreamSynchronize(c->stream));
+  return LANDING_OK;
+}
+
 int landing_fp64_peak(landing_ctx* c, double* tflops) {
   if (!c || !tflops) return fail(LANDING_ERR_ARG, "landing_fp64_peak: null argument");
-  CU(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
   std::string err;
   const int rc = fp64_peak_run(c->stream, tflops, &err);
   if (rc != LANDING_OK) return fail(rc, err);
@@ -170,6 +213,7 @@ void landing_problem_default(landing_problem* pb) {
   pb->f_max = 200.0;
   for (int i = 0; i < 3; i++) pb->Qf[i] = 0.0;
   pb->kin_box[0] = 0.15; pb->kin_box[1] = 0.15; pb->kin_box[2] = 0.30;
+  pb->dt = nullptr;  // uniform T/(N-1)
   // composite rigid-body inertia at q_home (get_mass_matrix.m:19-54, generate_landingCtrller_IPOPT.m:99-104)
   pb->mass = 8.251999999999999;
   pb->Ib[0] = 0.05757729852959269; pb->Ib[1] = 0.23400899479539086; pb->Ib[2] = 0.2796738482657981;
@@ -197,7 +241,7 @@ void landing_options_default(landing_options* o) {
 int landing_eval_batch(landing_ctx* c, long long B, int memspace, int layout, const landing_eval_io* io) {
   if (!c || !io || B < 0) return fail(LANDING_ERR_ARG, "landing_eval_batch: bad arguments");
   if (B == 0) return LANDING_OK;
-  CU(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
   const DevicePlan& pl = c->dpl;
   const long long nx = pl.nx, np = pl.np, m = pl.m, nj = pl.nnzJ, nh = pl.nnzH;
   // sizes (doubles) of the 4 inputs and 7 outputs
@@ -311,7 +355,7 @@ int landing_tvlqr_batch(landing_ctx* c, long long B, int memspace, const landing
                         double* P_out, double* K_out) {
   if (!c || !par || !x_star || B < 0 || par->n_steps < 1) return fail(LANDING_ERR_ARG, "landing_tvlqr_batch: bad arguments");
   if (B == 0) return LANDING_OK;
-  CU(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
   const long long nx = c->dpl.nx, ns = par->n_steps;
   TvlqrArgs a{};
   a.N = c->N; a.nx = nx; a.par = *par;
@@ -339,7 +383,7 @@ int landing_tvlqr_batch(landing_ctx* c, long long B, int memspace, const landing
 int landing_bounds_batch(landing_ctx* c, long long B, int memspace, int layout, const double* p,
                          double* lbg, double* ubg) {
   if (!c || !p || !lbg || !ubg || B <= 0) return fail(LANDING_ERR_ARG, "landing_bounds_batch: bad arguments");
-  CU(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
   const DevicePlan& pl = c->dpl;
   const double* dp = p;
   double *dl = lbg, *du = ubg;
@@ -366,7 +410,7 @@ int landing_bounds_batch(landing_ctx* c, long long B, int memspace, int layout, 
 int landing_build_batch(landing_ctx* c, long long B, int memspace, int layout, const landing_problem* pb,
                         const double* drops, double* p, double* x0) {
   if (!c || !pb || !drops || B <= 0) return fail(LANDING_ERR_ARG, "landing_build_batch: bad arguments");
-  CU(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
   const DevicePlan& pl = c->dpl;
   const double* dd = drops;
   double *dp = p, *dx = x0;
@@ -379,7 +423,11 @@ int landing_build_batch(landing_ctx* c, long long B, int memspace, int layout, c
     dp = p ? s + 12 * B : nullptr;
     dx = x0 ? s + 12 * B + B * pl.np : nullptr;
   }
-  c->launches += launch_build(pl, B, *pb, dd, make_view(dp, pl.np, B, layout), make_view(dx, pl.nx, B, layout),
+  {
+    const int rc = stage_dt(c, pb);
+    if (rc) return rc;
+  }
+  c->launches += launch_build(pl, B, *pb, c->d_dt, dd, make_view(dp, pl.np, B, layout), make_view(dx, pl.nx, B, layout),
                               c->stream);
   CU(cudaGetLastError());
   if (memspace == LANDING_HOST) {
@@ -395,12 +443,14 @@ int landing_solve_batch(landing_ctx* c, long long B, int memspace, const landing
   if (!c || !pb || !io || B < 0) return fail(LANDING_ERR_ARG, "landing_solve_batch: bad arguments");
   if (B == 0) return LANDING_OK;  // an empty sweep is a no-op (the reference's sweep loops simply do not iterate)
   if (!io->drops) return fail(LANDING_ERR_ARG, "landing_solve_batch: drops is NULL");
-  CU(cudaSetDevice(c->device));
+  DeviceGuard guard_(c->device);
   landing_options o;
   if (opt) o = *opt; else landing_options_default(&o);
   std::string err;
   int launches = 0;
-  int rc = solver_run(c->ws, c->dpl, B, memspace, *pb, o, *io, c->stream, &launches, &err);
+  int rc = stage_dt(c, pb);
+  if (rc) return rc;
+  rc = solver_run(c->ws, c->dpl, B, memspace, *pb, c->d_dt, o, *io, c->stream, &launches, &err);
   c->launches += launches;
   if (rc) return fail(rc, err);
   return LANDING_OK;

@@ -314,7 +314,7 @@ struct ProblemDev {
 };
 
 // p and x0 from drop conditions (generate_landingCtrller_IPOPT.m:199-208,336)
-__global__ void __launch_bounds__(TPB) k_build(DevicePlan pl, long long B, ProblemDev P,
+__global__ void __launch_bounds__(TPB) k_build(DevicePlan pl, long long B, ProblemDev P, const double* __restrict__ dtv,
                                                const double* __restrict__ drops, View p, View x0) {
   const long long b = (long long)blockIdx.x * TPB + threadIdx.x;
   const int k = blockIdx.y, N = pl.N;  // k in [0, N]: knot columns, k == N -> scalar parameters
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(TPB) k_build(DevicePlan pl, long long B, Probl
     if (x0.p) x0.at(12 * k + i, b) = xr[i];
   }
   if (k < N - 1) {
-    if (p.p) p.at(o.dt + k, b) = pb.T / (double)(N - 1);
+    if (p.p) p.at(o.dt + k, b) = dtv[k];
     if (x0.p)
       for (int l = 0; l < 4; l++)
         for (int i = 0; i < 3; i++) {
@@ -433,11 +433,11 @@ int launch_bounds(const DevicePlan& pl, long long B, CView p, View lbg, View ubg
   return 1;
 }
 
-int launch_build(const DevicePlan& pl, long long B, const landing_problem& pb, const double* drops,
+int launch_build(const DevicePlan& pl, long long B, const landing_problem& pb, const double* dtv, const double* drops,
                  View p, View x0, cudaStream_t st) {
   const dim3 grid((unsigned)((B + TPB - 1) / TPB), (unsigned)pl.N + 1);
   ProblemDev P{pb};
-  k_build<<<grid, TPB, 0, st>>>(pl, B, P, drops, p, x0);
+  k_build<<<grid, TPB, 0, st>>>(pl, B, P, dtv, drops, p, x0);
   return 1;
 }
 

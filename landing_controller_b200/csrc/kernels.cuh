@@ -58,7 +58,7 @@ int launch_tvlqr(const TvlqrArgs& a, long long B, cudaStream_t st);
 // returns number of kernel launches issued
 int launch_eval(const EvalArgs& a, cudaStream_t st);
 int launch_bounds(const DevicePlan& pl, long long B, CView p, View lbg, View ubg, cudaStream_t st);
-int launch_build(const DevicePlan& pl, long long B, const landing_problem& pb, const double* drops,
+int launch_build(const DevicePlan& pl, long long B, const landing_problem& pb, const double* dtv, const double* drops,
                  View p, View x0, cudaStream_t st);
 
 }  // namespace srb

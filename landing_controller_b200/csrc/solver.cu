@@ -267,7 +267,7 @@ void solver_free(SolverWorkspace& ws) {
 }
 
 int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memspace,
-               const landing_problem& pb, const landing_options& opt, const landing_solve_io& io,
+               const landing_problem& pb, const double* dtv, const landing_options& opt, const landing_solve_io& io,
                cudaStream_t st, int* launches, std::string* err) {
   const int N = pl.N;
   if (N - 1 > 1023 / 1) { *err = "landing_solve_batch: N too large"; return LANDING_ERR_ARG; }
@@ -275,7 +275,8 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
     *err = "landing_solve_batch: x_star, f_star, status and iters are required";
     return LANDING_ERR_ARG;
   }
-  if (!ws.tab.dev) {
+  if (!ws.ready) {
+    solver_free(ws);  // (a previous attempt may have failed half way)
     HostTables T = build_tables_host();
     CUS(cudaMalloc(&ws.tab.dev, sizeof(int) * T.all.size()));
     CUS(cudaMemcpy(ws.tab.dev, T.all.data(), sizeof(int) * T.all.size(), cudaMemcpyHostToDevice));
@@ -295,6 +296,7 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
     CUS(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_TOTAL * sizeof(double))));
     if (const char* e = getenv("LANDING_CARVEOUT"))  // experiments: shared-memory carve-out in percent
       CUS(cudaFuncSetAttribute(k_solve, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
+    ws.ready = true;  // only now: a failure above leaves the workspace to be set up again by the next call
   }
   const long long slot = slot_doubles(N);
   const long long nslots = (long long)ws.n_sm * CTAS_PER_SM;
@@ -309,7 +311,7 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
   const long long nx = pl.nx, m = pl.m;
   KParams P{};
   P.N = N; P.K = N - 1; P.nx = pl.nx; P.MR = 36 + RK * (N - 1);
-  P.B = B; P.pb = pb; P.opt = opt;
+  P.B = B; P.pb = pb; P.pb.dt = nullptr; P.dtv = dtv; P.opt = opt;
   P.opt.reserved[0] = pl.m;  // m, for the dual scaling s_d
   P.counter = ws.counter; P.scratch = ws.scratch; P.slot = slot; P.tab = ws.tab;
   if (memspace == LANDING_HOST) {

@@ -65,6 +65,7 @@ struct KParams {
   landing_options opt;
   const double* drops;
   const double* x0;
+  const double* dtv;  // knot spacings dt[0..K-1] (device)
   double *x_star, *f_star, *lam_g, *viol;
   int *status, *iters;
   int* counter;
@@ -227,7 +228,7 @@ __device__ __forceinline__ void load_knot(const KParams& P, const double* x, int
     kn.f[i] = x[12 * N + 24 * k + 12 + i];
     kn.cn[i] = last ? 0.0 : x[12 * N + 24 * (k + 1) + i];
   }
-  kn.h = P.pb.T / (double)(N - 1);
+  kn.h = __ldg(P.dtv + k);
   kn.mu = P.pb.mu;
   kn.mass = P.pb.mass;
 #pragma unroll
@@ -304,11 +305,10 @@ __device__ __forceinline__ bool has_run_cost(const KParams& P) {
 // this thread's share of sum_k sum_j Qf[j%3] f_kj^2 dt (dx == nullptr) or of its directional derivative along dx
 __device__ __noinline__ double run_cost_part(const KParams& P, const double* x, const double* dx) {
   const int N = P.N;
-  const double h = P.pb.T / (double)(N - 1);
   double acc = 0.0;
   for (int item = TID; item < P.K * 12; item += NT) {
     const int k = item / 12, j = item - 12 * k, iv = 12 * N + 24 * k + 12 + j;
-    const double q = P.pb.Qf[j % 3] * h * x[iv];
+    const double q = P.pb.Qf[j % 3] * __ldg(P.dtv + k) * x[iv];
     acc += dx ? 2.0 * q * dx[iv] : q * x[iv];
   }
   return acc;
@@ -717,7 +717,7 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
         a1 += Jk[u3 & 1023] * yk[u3 >> 10];
       }
     }
-    if (v >= 24 && has_run_cost(P)) a += 2.0 * P.pb.Qf[(v - 24) % 3] * w.x[12 * N + 24 * k + 12 + (v - 24)] * (P.pb.T / (double)(N - 1));
+    if (v >= 24 && has_run_cost(P)) a += 2.0 * P.pb.Qf[(v - 24) % 3] * w.x[12 * N + 24 * k + 12 + (v - 24)] * __ldg(P.dtv + k);
     if (v < NS) {
       if (k > 0) {  // what knot k-1 contributes to (X_k, c_k) through its X+ / c+ columns
         const double* Jp = Jk - NJ_PAD;

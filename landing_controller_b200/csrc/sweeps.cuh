@@ -91,8 +91,8 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
   const int* t_uptr = tbl + tb.o_uptr;
   const int* t_uterms = tbl + tb.o_uterms;
   const bool run = has_run_cost(P);
-  const double hh = 2.0 * P.pb.T / (double)(P.N - 1), rq0 = P.pb.Qf[0] * hh, rq1 = P.pb.Qf[1] * hh, rq2 = P.pb.Qf[2] * hh;
-  auto run2h = [&](int j) { return j % 3 == 0 ? rq0 : (j % 3 == 1 ? rq1 : rq2); };  // 2 Qf dt of force component j
+  const double rq0 = 2.0 * P.pb.Qf[0], rq1 = 2.0 * P.pb.Qf[1], rq2 = 2.0 * P.pb.Qf[2];
+  auto run2q = [&](int j) { return j % 3 == 0 ? rq0 : (j % 3 == 1 ? rq1 : rq2); };  // 2 Qf of force component j (times dt_k)
   // 4-deep ring of list buffers over regions that are idle before the sweeps: list region | stage matrix (2) | P,G,T
   auto ring = [&](int k) {
     const int j = k & 3;
@@ -127,7 +127,7 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
         }
         if (run) {  // Hessian diagonal of the running GRF cost (force variables are m = 0..11)
           const int ab = abh & 4095, ta = ab / NW;
-          if (ta < 12 && ab == ta * NW + ta) a0 += run2h(ta);
+          if (ta < 12 && ab == ta * NW + ta) a0 += run2q(ta) * __ldg(P.dtv + k);
         }
         ST_STREAM(&ct[it], a0 + a1);
       } else if (it < tb.n_u + NW) {
@@ -139,7 +139,7 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
           a0 += YHs[u0 >> 10] * Js[u0 & 1023];
           a1 += YHs[u1 >> 10] * Js[u1 & 1023];
         }
-        if (run && m < 12) a0 += run2h(m) * w.x[12 * P.N + 24 * k + 12 + m];  // gradient of the running GRF cost
+        if (run && m < 12) a0 += run2q(m) * __ldg(P.dtv + k) * w.x[12 * P.N + 24 * k + 12 + m];  // gradient of the running GRF cost
         ST_STREAM(&ct[CT_Q + m], a0 + a1);
       } else if (it < tb.n_u + NW + tb.n_g) {
         const int n = it - tb.n_u - NW;

@@ -48,8 +48,15 @@ def grid_sweep(B=1024, vz=-3.0):
     return d
 
 
-def random_sweep(B, seed=0, large_tilt=False):
-    """Seeded random drops after generate_training_data_automated.m:44-60 (BASELINE config 4)."""
+# knot spacings of the reference's sweep / MPC callers for N = 21 (generate_training_data_automated.m:28,
+# main_scripts/landing_optimization.m:28): dense around touchdown, coarse at the end of the horizon
+SWEEP_DT = np.array([0.05] + [0.02] * 15 + [0.05, 0.05, 0.1, 0.2])
+SWEEP_N = 21
+
+
+def random_sweep(B, seed=0, large_tilt=False, dt1=0.05):
+    """Seeded random drops after generate_training_data_automated.m:44-60 (BASELINE config 4).
+    dt1 = dt_val(1) of the caller, which enters the drop-height rule (:28,58)."""
     rng = np.random.default_rng(seed)
     d = np.zeros((B, 12))
     lim = (np.pi / 2 - 0.1) if large_tilt else np.pi / 3
@@ -59,12 +66,12 @@ def random_sweep(B, seed=0, large_tilt=False):
     d[:, 6:9] = rng.uniform(-0.5, 0.5, (B, 3))
     d[:, 9:11] = rng.uniform(-1.75, 1.75, (B, 2))
     d[:, 11] = rng.uniform(-6.0, -3.0, B)
-    # z0 = 0.35 + |min_l (R hip_l)_z| + |dt*vz|  (:52-60); hip_z = 0, dt = 0.03
+    # z0 = 0.35 + |min_l (R hip_l)_z| + |dt_val(1)*vz|  (:52-60); hip_z = 0
     sr, cr = np.sin(d[:, 3]), np.cos(d[:, 3])
     sp, cp = np.sin(d[:, 4]), np.cos(d[:, 4])
     hip = np.array([[0.19, -0.1], [0.19, 0.1], [-0.19, -0.1], [-0.19, 0.1]])
     hz = -sp[:, None] * hip[None, :, 0] + (sr * cp)[:, None] * hip[None, :, 1]
-    d[:, 2] = 0.35 + np.abs(hz.min(axis=1)) + np.abs(0.03 * d[:, 11])
+    d[:, 2] = 0.35 + np.abs(hz.min(axis=1)) + np.abs(dt1 * d[:, 11])
     return d
 
 
@@ -91,6 +98,41 @@ def apply_sweep_parameters(pb):
     pb.l_leg_max = 0.4
     pb.f_max = 500.0
     return pb
+
+
+def rot_xyz(rpy):
+    """rpyToRotMat_xyz.m:2 -- rx(r)' ry(p)' rz(y)' of spatial_v2 = R_x(r) R_y(p) R_z(y): the convention the sweep callers
+    use to place the reference feet (NOT the ZYX convention of the NLP's dynamics)."""
+    r, p, y = rpy
+    cr, sr, cp, sp, cy, sy = np.cos(r), np.sin(r), np.cos(p), np.sin(p), np.cos(y), np.sin(y)
+    Rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]])
+    Ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]])
+    Rz = np.array([[cy, -sy, 0], [sy, cy, 0], [0, 0, 1]])
+    return Rx @ Ry @ Rz
+
+
+def sweep_initial_guess(drops, pb, N):
+    """x0 = [Xref(:); Uref(:)] exactly as the sweep callers build it (generate_training_data_automated.m:105-136):
+    Xref = per-row linspace(init, term_ref, N); reference feet = Xref_pos + R_xyz(Xref_rpy) c_ref (ROTATED with the
+    reference attitude, unlike the generator's own test call); forces 0.  Returns [B, 36N-24]."""
+    drops = np.asarray(drops, dtype=np.float64)
+    B = drops.shape[0]
+    qt = np.array([pb.q_term_ref[i] for i in range(6)])
+    qdt = np.array([pb.qd_term_ref[i] for i in range(6)])
+    c_ref = np.array([pb.c_ref[i] for i in range(12)])
+    x0 = np.zeros((B, 36 * N - 24))
+    for b in range(B):
+        X = np.zeros((12, N))
+        for i in range(6):
+            X[i] = np.linspace(drops[b, i], qt[i], N)
+            X[6 + i] = np.linspace(drops[b, 6 + i], qdt[i], N)
+        U = np.zeros((24, N - 1))
+        for k in range(N - 1):
+            R = rot_xyz(X[3:6, k])
+            for leg in range(4):
+                U[3 * leg:3 * leg + 3, k] = X[0:3, k] + R @ c_ref[3 * leg:3 * leg + 3]
+        x0[b] = np.concatenate([X.T.ravel(), U.T.ravel()])
+    return x0
 
 
 CCC_N = 41

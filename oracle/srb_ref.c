@@ -805,6 +805,7 @@ void srb_problem_default(srb_problem *pb) {
   static const double sgn[12] = {1, -1, 1, 1, 1, 1, -1, -1, 1, -1, 1, 1};
   static const double cr[3] = {0.2, 0.1, -0.2};
   pb->T = 0.6;
+  pb->dt = NULL;
   for (int i = 0; i < 6; i++) {
     pb->q_min[i] = qmin[i]; pb->q_max[i] = qmax[i];
     pb->qd_min[i] = qdmin[i]; pb->qd_max[i] = qdmax[i];
@@ -834,7 +835,7 @@ void srb_build_p_x0(const srb_plan *pl, const srb_problem *pb, const double *q_i
           (k == N - 1) ? pb->qd_term_ref[i] : qd_init[i] + (pb->qd_term_ref[i] - qd_init[i]) * t;
     }
   }
-  for (int k = 0; k < N - 1; k++) p[pl->o_dt + k] = pb->T / (double)(N - 1);
+  for (int k = 0; k < N - 1; k++) p[pl->o_dt + k] = pb->dt ? pb->dt[k] : pb->T / (double)(N - 1);
   for (int i = 0; i < 6; i++) {
     p[pl->o_qmin + i] = pb->q_min[i]; p[pl->o_qmax + i] = pb->q_max[i];
     p[pl->o_qdmin + i] = pb->qd_min[i]; p[pl->o_qdmax + i] = pb->qd_max[i];

@@ -78,6 +78,8 @@ typedef struct srb_problem {
   double c_ref[12];
   double QN[12];
   double mu, l_leg_max, f_max, mass, Ib[3], Ib_inv[3];
+  const double *dt;         /* knot spacings dt[0..N-2], or NULL for the uniform T/(N-1)
+                               (generate_training_data_automated.m:28: [0.05 0.02x15 0.05 0.05 0.1 0.2]) */
 } srb_problem;
 
 void srb_problem_default(srb_problem *pb);

@@ -66,7 +66,18 @@ class Problem(ctypes.Structure):
         "qd_term_max", "q_term_ref", "qd_term_ref")] + [
         ("c_ref", ctypes.c_double * 12), ("QN", ctypes.c_double * 12),
         ("mu", ctypes.c_double), ("l_leg_max", ctypes.c_double), ("f_max", ctypes.c_double),
-        ("mass", ctypes.c_double), ("Ib", ctypes.c_double * 3), ("Ib_inv", ctypes.c_double * 3)]
+        ("mass", ctypes.c_double), ("Ib", ctypes.c_double * 3), ("Ib_inv", ctypes.c_double * 3),
+        ("dt", c_dp)]
+
+    def set_dt(self, dt):
+        """knot spacings (keeps the array alive); None = uniform"""
+        if dt is None:
+            self._dt, self.dt = None, None
+        else:
+            self._dt = np.ascontiguousarray(dt, dtype=np.float64)
+            self.dt = self._dt.ctypes.data_as(c_dp)
+            self.T = float(self._dt.sum())
+        return self
 
 
 class Oracle:

@@ -67,3 +67,30 @@ def test_warm_start_flavour_restarts_from_a_previous_solution():
     assert (warm["status"] == 0).all() and (ref["status"] == 0).all()
     assert np.max(np.abs(warm["f"] - ref["f"])) <= 1e-4
     assert warm["iters"].sum() < ref["iters"].sum()
+
+
+def test_nonuniform_dt_of_the_sweep_callers():
+    """The reference's sweep callers pass dt_val = [0.05 0.02x15 0.05 0.05 0.1 0.2] (generate_training_data_automated.m:28);
+    the restatement takes dt from p like the generated functions do."""
+    import landing_controller_b200 as lc
+    from oracle_ip import default_problem, solve_cpu_x0
+    from oracle_lib import Oracle
+    N = lc.SWEEP_N
+    pb = lc.apply_sweep_parameters(default_problem()).set_dt(lc.SWEEP_DT)
+    assert abs(pb.T - 0.75) < 1e-12
+    drops = lc.random_sweep(6, seed=5)
+    assert np.allclose(drops[:, 2] - 0.35 - np.abs(0.05 * drops[:, 11]),
+                       np.abs(lc.random_sweep(6, seed=5, dt1=0.0)[:, 2] - 0.35), atol=1e-12)  # z0 rule uses dt_val(1)
+    o = Oracle(N)
+    p, x0d = o.build_p_x0(pb, drops[0, :6], drops[0, 6:])
+    assert np.array_equal(p[o.plan.contents.o_dt:o.plan.contents.o_dt + N - 1], lc.SWEEP_DT)
+    x0 = lc.sweep_initial_guess(drops, pb, N)
+    # level attitude -> the rotated reference feet equal the unrotated ones
+    lvl = drops.copy(); lvl[:, 3:6] = 0
+    assert np.allclose(lc.sweep_initial_guess(lvl[:1], pb, N)[0][12 * N:12 * N + 12],
+                       o.build_p_x0(pb, lvl[0, :6], lvl[0, 6:])[1][12 * N:12 * N + 12], atol=1e-12)
+    r = solve_cpu_x0(N, drops, x0, None, pb)
+    # these drops (v_z down to -6 m/s, coarse last steps of 0.1 / 0.2 s) are much harder than the grid sweeps: the
+    # restatement converges on 55-85 % of them depending on the initial guess (DESIGN.md 3); the rest end at a point of
+    # local infeasibility (status 2) where IPOPT would enter its restoration phase
+    assert (r["status"] == 0).sum() >= 3 and set(r["status"]) <= {0, 2}
