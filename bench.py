@@ -201,6 +201,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     drops = workload(cfg, 1, 0)  # the whole sweep
     sub, stride = cpu_sample(cfg, drops, args.cpu_sample)
+    flags = cpu_flags()  # (builds the -O3 library before anything is timed)
     for _ in range(min(args.warmup, 1)):
         cpu_run(N, sub[:cores], cores)
     tot_t, tot_c, tot_it = 0.0, 0, 0
@@ -211,7 +212,7 @@ def run_reference(args):
         tot_it += int(r["iters"].sum())
     val = tot_c / tot_t
     sample = ("%d of %d scenarios per step (every %d-th), %d steps; IPOPT substitute (oracle/ip_ref.c, %s), OpenMP over scenarios"
-              % (len(sub), cfg["total"], stride, args.steps, cpu_flags()))
+              % (len(sub), cfg["total"], stride, args.steps, flags))
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
