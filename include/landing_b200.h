@@ -162,6 +162,18 @@ typedef struct landing_solve_io {
 int landing_solve_batch(landing_ctx *ctx, long long B, int memspace, const landing_problem *pb,
                         const landing_options *opt, const landing_solve_io *io);
 
+/* One sweep on SEVERAL GPUs of this process (the scenario batch shards naturally, no data-path collective):
+ * scenario b is solved on devices[b % n_devices] (interleaved shards: the iteration count grows along the axes of a grid
+ * sweep), one host thread and one context per device, and the result records [x*, f*, status, iters, viol, lam_g] of the
+ * WHOLE sweep are gathered into the caller's HOST arrays in global scenario order -- the library-level counterpart of
+ * the NCCL all-gather a process-per-GPU launch does (bench.py).  A device index may be listed more than once (several
+ * contexts, i.e. several independent work queues, on one GPU).  io: HOST pointers, same meaning as above. */
+typedef struct landing_multi landing_multi;
+int landing_multi_create(int n_knots, int n_devices, const int *devices, landing_multi **m);
+void landing_multi_destroy(landing_multi *m);
+int landing_solve_batch_multi(landing_multi *m, long long B, const landing_problem *pb,
+                              const landing_options *opt, const landing_solve_io *io);
+
 /* Time-varying LQR pass along solved trajectories (replaces, for a batch, quadruped_SRBM_NLP.m:428-497 with
  * srbm-utilities/generateVariationalDynamics.m:9-62 and generateRiccatiIntegrator.m:24,49-53): P(t_k), k = 0..n_steps-1,
  * t_k = k dt, from P(t_{n_steps-1}) = F by explicit Euler steps of Pdot = A'P + PA - P B R^-1 B'P + Q, and the gains

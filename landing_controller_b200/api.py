@@ -101,6 +101,11 @@ def load_library(path=LIB_PATH):
     lib.landing_tvlqr_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.POINTER(Tvlqr),
                                         _dp, _dp, _dp]
     lib.landing_synchronize.argtypes = [ctypes.c_void_p]
+    lib.landing_multi_create.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_int),
+                                         ctypes.POINTER(ctypes.c_void_p)]
+    lib.landing_multi_destroy.argtypes = [ctypes.c_void_p]
+    lib.landing_solve_batch_multi.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.POINTER(Problem),
+                                              ctypes.POINTER(Options), ctypes.POINTER(SolveIO)]
     return lib
 
 
@@ -317,6 +322,50 @@ class LandingSolver:
                     "landing_solve_batch")
         if order_streams:
             cur.wait_stream(lib_stream)
+
+
+class MultiGpuSolver:
+    """One sweep on several GPUs of this process (landing_solve_batch_multi): interleaved shards, one host thread per
+    device, results gathered in global scenario order in host memory."""
+
+    def __init__(self, N, devices, lib_path=LIB_PATH):
+        self.lib = load_library(lib_path)
+        self.N, self.devices = N, list(devices)
+        self.handle = ctypes.c_void_p()
+        arr = (ctypes.c_int * len(self.devices))(*self.devices)
+        rc = self.lib.landing_multi_create(N, len(self.devices), arr, ctypes.byref(self.handle))
+        if rc != 0:
+            raise RuntimeError("landing_multi_create failed (%d): %s" % (rc, self.lib.landing_last_error().decode()))
+        self.dims = dims_for(N, self.lib)
+        self.problem, self.options = Problem(), Options()
+        self.lib.landing_problem_default(ctypes.byref(self.problem))
+        self.lib.landing_options_default(ctypes.byref(self.options))
+
+    def solve(self, drops, want_lam=False):
+        drops = np.ascontiguousarray(drops, dtype=np.float64)
+        B, d = drops.shape[0], self.dims
+        out = dict(x=np.zeros((B, d["nx"])), f=np.zeros(B), viol=np.zeros(B),
+                   status=np.full(B, 9, dtype=np.int32), iters=np.zeros(B, dtype=np.int32))
+        if want_lam:
+            out["lam_g"] = np.zeros((B, d["m"]))
+        io = SolveIO(_ptr(drops), None, _ptr(out["x"]), _ptr(out["f"]), _ptr(out.get("lam_g")), _ptr(out["viol"]),
+                     _ptr(out["status"], _ip), _ptr(out["iters"], _ip))
+        rc = self.lib.landing_solve_batch_multi(self.handle, B, ctypes.byref(self.problem), ctypes.byref(self.options),
+                                                ctypes.byref(io))
+        if rc != 0:
+            raise RuntimeError("landing_solve_batch_multi failed (%d): %s" % (rc, self.lib.landing_last_error().decode()))
+        return out
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.landing_multi_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def contact_set(x, N, thresh=1.0):

@@ -3,7 +3,10 @@
 // every entry point that produces numbers needs a CUDA device and fails loudly without one.
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <string>
+#include <thread>
+#include <vector>
 
 #include "kernels.cuh"
 #include "solver.cuh"
@@ -453,6 +456,108 @@ int landing_solve_batch(landing_ctx* c, long long B, int memspace, const landing
   rc = solver_run(c->ws, c->dpl, B, memspace, *pb, c->d_dt, o, *io, c->stream, &launches, &err);
   c->launches += launches;
   if (rc) return fail(rc, err);
+  return LANDING_OK;
+}
+
+// ---------------------------------------------------------------- several GPUs, one process
+struct landing_multi {
+  int N = 0;
+  std::vector<landing_ctx*> ctx;
+  struct Shard {  // pinned host staging of one device's shard (grow-only)
+    long long cap = 0, cap_lam = 0, cap_x0 = 0;
+    double *drops = nullptr, *x = nullptr, *f = nullptr, *viol = nullptr, *lam = nullptr, *x0 = nullptr;
+    int *status = nullptr, *iters = nullptr;
+  };
+  std::vector<Shard> sh;
+};
+
+int landing_multi_create(int N, int n_devices, const int* devices, landing_multi** out) {
+  if (!out || !devices || n_devices < 1) return fail(LANDING_ERR_ARG, "landing_multi_create: bad arguments");
+  std::unique_ptr<landing_multi> m(new landing_multi());
+  m->N = N;
+  m->sh.resize(n_devices);
+  for (int d = 0; d < n_devices; d++) {
+    landing_ctx* c = nullptr;
+    const int rc = landing_create(N, devices[d], &c);
+    if (rc) {
+      for (landing_ctx* q : m->ctx) landing_destroy(q);
+      return rc;
+    }
+    m->ctx.push_back(c);
+  }
+  *out = m.release();
+  return LANDING_OK;
+}
+
+void landing_multi_destroy(landing_multi* m) {
+  if (!m) return;
+  for (size_t d = 0; d < m->ctx.size(); d++) {
+    DeviceGuard guard_(m->ctx[d]->device);
+    landing_multi::Shard& s = m->sh[d];
+    for (void* p : {(void*)s.drops, (void*)s.x, (void*)s.f, (void*)s.viol, (void*)s.lam, (void*)s.x0, (void*)s.status, (void*)s.iters})
+      if (p) cudaFreeHost(p);
+    landing_destroy(m->ctx[d]);
+  }
+  delete m;
+}
+
+int landing_solve_batch_multi(landing_multi* m, long long B, const landing_problem* pb, const landing_options* opt,
+                              const landing_solve_io* io) {
+  if (!m || !pb || !io || B < 0) return fail(LANDING_ERR_ARG, "landing_solve_batch_multi: bad arguments");
+  if (B == 0) return LANDING_OK;
+  if (!io->drops || !io->x_star || !io->f_star || !io->status || !io->iters)
+    return fail(LANDING_ERR_ARG, "landing_solve_batch_multi: drops, x_star, f_star, status and iters are required");
+  const int G = (int)m->ctx.size();
+  const long long nx = 36LL * m->N - 24, mr = 104LL * m->N - 92;
+  std::vector<int> rcs(G, LANDING_OK);
+  std::vector<std::string> errs(G);
+  auto work = [&](int d) {
+    landing_ctx* c = m->ctx[d];
+    landing_multi::Shard& s = m->sh[d];
+    const long long Bd = (B - d + G - 1) / G;  // scenarios d, d + G, ...
+    if (Bd <= 0) return;
+    DeviceGuard guard_(c->device);
+    auto grow = [&](auto*& p, long long n) {
+      if (p) cudaFreeHost(p);
+      p = nullptr;
+      return cudaMallocHost((void**)&p, sizeof(*p) * (size_t)n) == cudaSuccess;
+    };
+    bool ok = true;
+    if (Bd > s.cap) {
+      ok = grow(s.drops, 12 * Bd) && grow(s.x, nx * Bd) && grow(s.f, Bd) && grow(s.viol, Bd) && grow(s.status, Bd) &&
+           grow(s.iters, Bd);
+      s.cap = ok ? Bd : 0;
+    }
+    if (ok && io->lam_g && Bd > s.cap_lam) { ok = grow(s.lam, mr * Bd); s.cap_lam = ok ? Bd : 0; }
+    if (ok && io->x0 && Bd > s.cap_x0) { ok = grow(s.x0, nx * Bd); s.cap_x0 = ok ? Bd : 0; }
+    if (!ok) { rcs[d] = LANDING_ERR_CUDA; errs[d] = "landing_solve_batch_multi: pinned host allocation failed"; return; }
+    for (long long i = 0; i < Bd; i++) {
+      const long long b = d + i * G;
+      std::memcpy(s.drops + 12 * i, io->drops + 12 * b, sizeof(double) * 12);
+      if (io->x0) std::memcpy(s.x0 + nx * i, io->x0 + nx * b, sizeof(double) * nx);
+    }
+    landing_solve_io sio{};
+    sio.drops = s.drops; sio.x0 = io->x0 ? s.x0 : nullptr;
+    sio.x_star = s.x; sio.f_star = s.f; sio.lam_g = io->lam_g ? s.lam : nullptr; sio.viol = s.viol;
+    sio.status = s.status; sio.iters = s.iters;
+    rcs[d] = landing_solve_batch(c, Bd, LANDING_HOST, pb, opt, &sio);
+    if (rcs[d]) { errs[d] = landing_last_error(); return; }
+    for (long long i = 0; i < Bd; i++) {  // gather: this device's records into the whole sweep's arrays
+      const long long b = d + i * G;
+      std::memcpy(io->x_star + nx * b, s.x + nx * i, sizeof(double) * nx);
+      io->f_star[b] = s.f[i];
+      io->status[b] = s.status[i];
+      io->iters[b] = s.iters[i];
+      if (io->viol) io->viol[b] = s.viol[i];
+      if (io->lam_g) std::memcpy(io->lam_g + mr * b, s.lam + mr * i, sizeof(double) * mr);
+    }
+  };
+  std::vector<std::thread> th;
+  for (int d = 1; d < G; d++) th.emplace_back(work, d);
+  work(0);
+  for (auto& t : th) t.join();
+  for (int d = 0; d < G; d++)
+    if (rcs[d]) return fail(rcs[d], errs[d]);
   return LANDING_OK;
 }
 

@@ -188,8 +188,8 @@ class CasadiLib:
         s = getattr(self.lib, fn + "_sparsity_out")(i)
         return s[2 + s[1]]
 
-    def call(self, fn, args, skip=()):
-        """args: list of arrays (or None).  Returns (rc, [outputs])."""
+    def call(self, fn, args, skip=(), mem=0):
+        """args: list of arrays (or None).  Returns (rc, [outputs]).  mem: memory object from F_checkout."""
         n_in = getattr(self.lib, fn + "_n_in")()
         n_out = getattr(self.lib, fn + "_n_out")()
         assert len(args) == n_in
@@ -201,7 +201,7 @@ class CasadiLib:
         getattr(self.lib, fn + "_work")(*[ctypes.byref(s) for s in szs])
         iw = (ctypes.c_longlong * max(1, szs[2].value))()
         w = (ctypes.c_double * max(1, szs[3].value))()
-        rc = getattr(self.lib, fn)(argv, resv, iw, w, 0)
+        rc = getattr(self.lib, fn)(argv, resv, iw, w, mem)
         return rc, outs
 
 

@@ -40,6 +40,45 @@ def test_casadi_abi_against_reference_golden(dropin, golden):
         assert rc == 0 and rel(gx, c["gx"]) < TOL and rel(gp, c["gp"]) < TOL and rel(g, c["g"]) < TOL
 
 
+def test_casadi_abi_is_reentrant_with_checked_out_memory_objects(dropin, golden):
+    """CasADi evaluates one function from several threads, each with its own memory object: checkout -> F(.., mem) ->
+    release (function_internal.cpp:721-733).  Every memory object owns a CUDA stream and staging buffers."""
+    import threading
+    for fn in dropin.FUNCS:
+        getattr(dropin.lib, fn + "_incref")()
+    n = int(golden["n_cases"])
+    golden = {k: np.array(golden[k]) for k in golden.files}  # (the lazy .npz reader is not thread-safe)
+    errs, mems = [], []
+    gate = threading.Barrier(6)
+
+    def worker(t):
+        try:
+            mem = dropin.lib.nlp_jac_g_checkout()
+            mems.append(mem)
+            gate.wait(timeout=60)  # all six memory objects are checked out before anyone evaluates
+            for rep in range(12):
+                i = (t + rep) % n
+                x, p = golden["c%d_x" % i], golden["c%d_p" % i]
+                rc, (g, J) = dropin.call("nlp_jac_g", [x, p], mem=mem)
+                assert rc == 0 and rel(g, golden["c%d_g" % i]) < TOL and rel(J, golden["c%d_J" % i]) < TOL
+                rc, (H,) = dropin.call("nlp_hess_l", [x, p, golden["c%d_lam_f" % i], golden["c%d_lam_g" % i]], mem=mem)
+                assert rc == 0 and rel(H, golden["c%d_H" % i]) < TOL
+            dropin.lib.nlp_jac_g_release(mem)
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    assert len(set(mems)) == 6  # six distinct memory objects were live at the same time
+    again = dropin.lib.nlp_jac_g_checkout()
+    assert again == min(mems)  # released slots are handed out again
+    dropin.lib.nlp_jac_g_release(again)
+    for fn in dropin.FUNCS:
+        getattr(dropin.lib, fn + "_decref")()
+
+
 def test_casadi_abi_null_handling(dropin, golden):
     """arg[i]==NULL means zeros, res[i]==NULL means skip (landingCtrller_IPOPT.c:69,151)."""
     x, p = golden["c1_x"], golden["c1_p"]
