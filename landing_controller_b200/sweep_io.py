@@ -8,6 +8,10 @@
 * `touchdown_feet_body(sol)` -- feet relative to the CoM in the body frame at touchdown (`foot_positions.m:54-62`).
 * `training_record(drop, x)` -- `training_data.input = [rpy0; qd0]` / `.output = x*`
   (`generate_data/generate_training_data_automated.m:209-214`; the SRB stage has no joint angles).
+* `normalize_training_set / denormalize_sample` -- the NN training-set normalisation of
+  `generate_data/data_normalization.m:42-111` and its inverse `data_denormalization.m:16-41`: z-scores of the inputs, the
+  states, the foot positions (and joint angles when present); ground-reaction forces shifted to each leg's touchdown knot
+  and scaled by body weight; the four touchdown indices appended to every output column.
 """
 import numpy as np
 
@@ -90,3 +94,81 @@ def training_record(drop, x):
     """(input [9], output [nx]) of one sample of the NN training set."""
     drop = np.asarray(drop, dtype=np.float64)
     return np.concatenate([drop[3:6], drop[6:12]]), np.asarray(x, dtype=np.float64).copy()
+
+
+def _blocks(N, n_out):
+    nX, nU = 12 * N, 24 * (N - 1)
+    nJ = n_out - nX - nU
+    if nJ not in (0, 12 * (N - 1)):
+        raise ValueError("output columns must hold [X(:); U(:)] or [X(:); U(:); jpos(:)]")
+    return nX, nU, nJ
+
+
+def normalize_training_set(inputs, outputs, N, mass):
+    """inputs [9, n] (`training_data.input`), outputs [nx (+ 12(N-1)), n] (`training_data.output`, columns
+    [X(:); U(:); jpos(:)], MATLAB column-major reshapes) -> (normalized, stats) after data_normalization.m:42-111.
+    normalized["input"] [9, n]; normalized["output"] [n_out + 4, n] (the four touchdown indices appended, 1-based);
+    stats has the fields of `data_stats.mat` (mean/std of input, X, U, jpos; td_scale; mass).  std is MATLAB's std(.,0,2)
+    (n-1 in the denominator); entries with zero spread (x, y of the first knot: X_norm(1:2,1) = 0, :100) give 0."""
+    inputs = np.asarray(inputs, dtype=np.float64)
+    outputs = np.asarray(outputs, dtype=np.float64)
+    n = inputs.shape[1]
+    nX, nU, nJ = _blocks(N, outputs.shape[0])
+    mean_in, std_in = inputs.mean(axis=1, keepdims=True), inputs.std(axis=1, ddof=1, keepdims=True)
+    mean_out, std_out = outputs.mean(axis=1), outputs.std(axis=1, ddof=1)
+    col = lambda v, r, c: v.reshape(c, r).T  # MATLAB reshape(v, [r c]) of a column-major vector
+    stats = {"mean_input": mean_in, "std_input": std_in,
+             "mean_X": col(mean_out[:nX], 12, N), "std_X": col(std_out[:nX], 12, N),
+             "mean_U": col(mean_out[nX:nX + nU], 24, N - 1), "std_U": col(std_out[nX:nX + nU], 24, N - 1),
+             "td_scale": 1.0, "mass": float(mass)}
+    if nJ:
+        stats["mean_jpos"] = col(mean_out[nX + nU:], 12, N - 1)
+        stats["std_jpos"] = col(std_out[nX + nU:], 12, N - 1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        out = np.zeros((outputs.shape[0] + 4, n))
+        for e in range(n):
+            o = outputs[:, e]
+            X, U = col(o[:nX], 12, N), col(o[nX:nX + nU], 24, N - 1)
+            f = U[12:]
+            Un = np.zeros_like(U)
+            td = np.zeros(4)
+            for leg in range(4):
+                fl = f[3 * leg:3 * leg + 3]
+                hit = np.nonzero(fl[2] > 1)[0]
+                if len(hit) == 0:
+                    raise ValueError("sample %d: leg %d never loads (f_z > 1 N): the reference's find() would be empty" % (e, leg))
+                t0 = int(hit[0])  # 0-based; MATLAB's td_idx = t0 + 1
+                off = np.hstack([fl[:, t0:], np.repeat(fl[:, -1:], t0, axis=1)])
+                Un[12 + 3 * leg:12 + 3 * leg + 3] = off / (mass * 9.81)
+                td[leg] = t0 + 1
+            Xn = (X - stats["mean_X"]) / stats["std_X"]
+            Xn[0:2, 0] = 0.0
+            Un[:12] = (U[:12] - stats["mean_U"][:12]) / stats["std_U"][:12]
+            parts = [Xn.T.ravel(), Un.T.ravel()]
+            if nJ:
+                parts.append(((col(o[nX + nU:], 12, N - 1) - stats["mean_jpos"]) / stats["std_jpos"]).T.ravel())
+            out[:, e] = np.concatenate(parts + [td])
+        normalized = {"input": (inputs - mean_in) / std_in, "output": np.nan_to_num(out, nan=0.0, posinf=0.0, neginf=0.0)}
+    return normalized, stats
+
+
+def denormalize_sample(nn_data, stats, N):
+    """One normalised output column -> (X [12, N], U [24, N-1], jpos [12, N-1] or None), data_denormalization.m:16-41: the
+    z-scores are undone, and each leg's normalised force profile is shifted back to its touchdown knot (zeros before
+    it) and multiplied by body weight."""
+    nn_data = np.asarray(nn_data, dtype=np.float64)
+    nX, nU, nJ = _blocks(N, nn_data.shape[0] - 4)
+    col = lambda v, r, c: v.reshape(c, r).T
+    Xn, Un = col(nn_data[:nX], 12, N), col(nn_data[nX:nX + nU], 24, N - 1)
+    td = np.trunc(nn_data[-4:]).astype(int)  # int8(td_nn)
+    X = Xn * stats["std_X"] + stats["mean_X"]
+    U = np.zeros((24, N - 1))
+    U[:12] = Un[:12] * stats["std_U"][:12] + stats["mean_U"][:12]
+    for leg in range(4):
+        fo = Un[12 + 3 * leg:12 + 3 * leg + 3]
+        t0 = max(int(td[leg]) - 1, 0)
+        U[12 + 3 * leg:12 + 3 * leg + 3] = np.hstack([np.zeros((3, t0)), fo[:, :N - 1 - t0]]) * (stats["mass"] * 9.81)
+    jpos = None
+    if nJ:
+        jpos = col(nn_data[nX + nU:nX + nU + nJ], 12, N - 1) * stats["std_jpos"] + stats["mean_jpos"]
+    return X, U, jpos

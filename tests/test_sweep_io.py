@@ -62,3 +62,35 @@ def test_touchdown_feet_and_training_record():
     drop = d["X"][b][:, 0]
     inp, out = sweep_io.training_record(drop, _x(d["X"][b], d["c"][b], d["f"][b]))
     assert inp.shape == (9,) and np.array_equal(inp[:3], drop[3:6]) and out.shape == (36 * N - 24,)
+
+
+def test_training_set_normalisation_round_trip():
+    """data_normalization.m:42-111 / data_denormalization.m:16-41 on the stored IPOPT solutions (N = 41): z-scores with
+    MATLAB's std, forces shifted to touchdown and scaled by body weight, td appended; the inverse restores the states and
+    foot positions exactly and the forces from each leg's touchdown knot on (earlier columns, all < 1 N in z, become 0)."""
+    d = np.load(FIX)
+    n = len(d["X"])
+    outs = np.array([_x(d["X"][b], d["c"][b], d["f"][b]) for b in range(n)]).T
+    ins = np.array([np.concatenate([d["X"][b][3:6, 0], d["X"][b][6:12, 0]]) for b in range(n)]).T
+    keep = [b for b in range(n) if all((d["f"][b][3 * l + 2] > 1).any() for l in range(4))]
+    outs, ins = outs[:, keep], ins[:, keep]
+    mass = 8.251999999999999  # generate_data/data/data_stats.mat
+    norm, st = sweep_io.normalize_training_set(ins, outs, N, mass)
+    assert norm["input"].shape == ins.shape and norm["output"].shape == (outs.shape[0] + 4, len(keep))
+    assert np.allclose(norm["input"].mean(axis=1), 0, atol=1e-9)
+    assert np.allclose(norm["input"].std(axis=1, ddof=1)[st["std_input"][:, 0] > 0], 1, atol=1e-9)
+    assert st["mean_X"].shape == (12, N) and st["std_U"].shape == (24, N - 1) and st["td_scale"] == 1.0
+    for e in range(0, len(keep), 5):
+        b = keep[e]
+        X, U, jpos = sweep_io.denormalize_sample(norm["output"][:, e], st, N)
+        assert jpos is None
+        td = norm["output"][-4:, e].astype(int)
+        assert np.array_equal(td, d["td"][b].astype(int))           # same touchdown knots as the stored `td`
+        ok = st["std_X"] > 0
+        assert np.allclose(X[ok], d["X"][b][ok], atol=1e-9) and np.allclose(U[:12], d["c"][b], atol=1e-9)
+        for leg in range(4):
+            t0 = td[leg] - 1
+            assert np.allclose(U[12 + 3 * leg:15 + 3 * leg, t0:], d["f"][b][3 * leg:3 * leg + 3, t0:], atol=1e-9)
+            assert np.all(U[12 + 3 * leg:15 + 3 * leg, :t0] == 0)
+        # normalised vertical force of a loaded leg: fractions of body weight
+        assert 0 < norm["output"][12 * N:-4, e].max() < 10
