@@ -35,6 +35,9 @@ UNIT = "NLP/s"
 CONFIGS = {
     "1k": dict(knots=30, total=1024, scaling="weak",
                workload="BASELINE configs[1]: SRB landing sweep, 1024 grid drop conditions (height x pitch x roll x v_x, v_z=-3), N=30 knots"),
+    "single": dict(knots=30, total=1, scaling="weak", formulation="schedule",
+                   workload="BASELINE configs[0]: SRB landing NLP, one drop condition (0.5 m, level, 1 m/s forward), fixed contact "
+                            "schedule (quadruped_SRBM_NLP.m; flight until the ballistic fall reaches 0.28 m, then stance), N=30 knots"),
     "16k": dict(knots=50, total=16384, scaling="strong",
                 workload="BASELINE configs[2]: SRB landing sweep, 16384 grid drop conditions (height x pitch x roll x v_x, v_z=-3), N=50 knots, strong-scaled over the GPUs"),
 }
@@ -64,8 +67,27 @@ def config_dict(cfg, world):
                   "every step rewrites all of it; no flush needed" % (1e-9 * scratch_bytes(cfg["knots"], 296))}
 
 
+def schedule_setup(cfg, solver=None):
+    """configs[0]: the fixed-contact-schedule problem.  Returns (pb, opt) for the CPU arm; configures `solver` (GPU)."""
+    import landing_controller_b200 as lc
+    N, T, z0 = cfg["knots"], 0.6, 0.5
+    cs = lc.ballistic_schedule(N, T, z0)
+    if solver is not None:
+        lc.apply_schedule_parameters(solver.problem)
+        solver.problem.T = T
+        solver.set_schedule(cs, lc.SCHED_QX)
+        return None, None
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_ip import default_options, default_problem
+    pb = lc.apply_schedule_parameters(default_problem())
+    pb.T = T
+    return pb, default_options(run_Qf=lc.SCHED_QF, kin_box=lc.SCHED_KIN_BOX).set_schedule(cs, lc.SCHED_QX)
+
+
 def workload(cfg, world, rank):
     import landing_controller_b200 as lc
+    if cfg.get("formulation") == "schedule":
+        return np.repeat(lc.single_drop(), cfg["total"], axis=0)[rank::world].copy()
     allb = lc.grid_sweep(cfg["total"])
     # interleaved shards: the iteration count grows along the axes of the grid, contiguous blocks would give the last
     # rank the hard end of the sweep
@@ -162,13 +184,14 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_run(N, drops, threads):
+def cpu_run(N, drops, threads, cfg=None):
     """The timed CPU arm: oracle/ip_ref.c built -O3 -march=native on this host (the reference builds its C with gcc -O3,
     generate_landingCtrller_IPOPT.m:296), OpenMP over scenarios."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_ip import solve_cpu
+    pb, opt = schedule_setup(cfg) if cfg and cfg.get("formulation") == "schedule" else (None, None)
     t = time.perf_counter()
-    r = solve_cpu(N, drops, threads=threads, fast=True)
+    r = solve_cpu(N, drops, opt, pb, threads=threads, fast=True)
     dt = time.perf_counter() - t
     return r, dt
 
@@ -203,10 +226,10 @@ def run_reference(args):
     sub, stride = cpu_sample(cfg, drops, args.cpu_sample)
     flags = cpu_flags()  # (builds the -O3 library before anything is timed)
     for _ in range(min(args.warmup, 1)):
-        cpu_run(N, sub[:cores], cores)
+        cpu_run(N, sub[:cores], cores, cfg)
     tot_t, tot_c, tot_it = 0.0, 0, 0
     for _ in range(args.steps):
-        r, dt = cpu_run(N, sub, cores)
+        r, dt = cpu_run(N, sub, cores, cfg)
         tot_t += dt
         tot_c += int((r["status"] == 0).sum())
         tot_it += int(r["iters"].sum())
@@ -239,7 +262,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
-    ap.add_argument("--config", default="auto", choices=["auto", "1k", "16k"],
+    ap.add_argument("--config", default="auto", choices=["auto", "single", "1k", "16k"],
                     help="auto: BASELINE configs[1] on one GPU, configs[2] (fixed 16k x N=50 sweep, strong-scaled) under torchrun")
     ap.add_argument("--batch", type=int, default=0, help="override: scenarios per GPU (weak configs) / in total (strong)")
     ap.add_argument("--knots", type=int, default=0, help="override: knots per trajectory")
@@ -269,6 +292,8 @@ def main():
     cfg = pick_config(args, world)
     N = cfg["knots"]
     solver = lc.LandingSolver(N=N, device=local_rank)
+    if cfg.get("formulation") == "schedule":
+        schedule_setup(cfg, solver)
     nx = solver.dims["nx"]
     drops_h = workload(cfg, world, rank)
     B = len(drops_h)
@@ -447,7 +472,7 @@ def main():
         if one_gpu:
             line["one_gpu_same_workload"] = one_gpu
             line["strong_scaling_efficiency_vs_one_gpu"] = value / (world * one_gpu["value"])
-        if world == 1 and not args.no_eval_kernels:
+        if world == 1 and not args.no_eval_kernels and cfg.get("formulation") != "schedule":
             # the evaluation kernels (HBM-bound rows a-3..a-6 of SURVEY 8): 16k scenarios, SoA, a few milliseconds
             try:
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
@@ -470,8 +495,8 @@ def main():
             # CPU baseline on the host cores (bounded sample of the same workload; rank 0 at N = 1 only)
             cores = os.cpu_count() or 1
             sub, stride = cpu_sample(cfg, drops_h, args.cpu_sample)
-            cpu_run(N, sub[:cores], cores)  # (builds the -O3 library, warms the threads)
-            r, dt = cpu_run(N, sub, cores)
+            cpu_run(N, sub[:cores], cores, cfg)  # (builds the -O3 library, warms the threads)
+            r, dt = cpu_run(N, sub, cores, cfg)
             line["cpu_baseline"] = {
                 "value": float((r["status"] == 0).sum()) / dt, "unit": UNIT, "cores": cores, "kind": "port",
                 "kkt_iters_per_s": float(r["iters"].sum()) / dt,

@@ -102,6 +102,19 @@ typedef struct landing_problem {
    * NON-uniform in the sweep / MPC callers: dt_val = [0.05 0.02x15 0.05 0.05 0.1 0.2] for N = 21
    * (generate_data/generate_training_data_automated.m:28,130-136; main_scripts/landing_optimization.m:28,305-311). */
   const double *dt;
+  /* FORMULATION.  0 (default): the contact-implicit NLP of landingCtrller_IPOPT (generate_landingCtrller_IPOPT.m:90-169).
+   * 1: the fixed-contact-schedule NLP of quadruped_SRBM_NLP.m:84-176 (BASELINE configs[0]) -- solver only:
+   *    f_z <= cs f_max (:148), cs c_z = 0 (:154), cs (c+ - c) = 0 (:155-158) instead of the complementarity / no-slip
+   *    inequalities; no terminal rows (:105-108 are commented out); running cost sum_k dt_k ((X_k - Xref_k)' QX (X_k -
+   *    Xref_k) + f_k' Qf f_k) (:85-92; Qc = 0 in the reference's parameter set :213 and is not implemented) next to the
+   *    terminal cost QN.  cs: HOST pointer to 4 (N-1) ints, cs[4 k + leg] in {0, 1}.  The extra equality rows vanish
+   *    identically where cs = 0 (rank-deficient Jacobian); they are handled the way IPOPT handles that case, by the dual
+   *    regularisation delta_c: sigma = 1 / delta_c in the condensed stage matrix, y+ = y + (J dx + c) / delta_c.
+   *    lam_g is returned in the row layout of formulation 0 (unused rows carry 0). */
+  int formulation;
+  const int *cs;
+  double QX[12];
+  double delta_c; /* 1e-7 */
 } landing_problem;
 
 void landing_problem_default(landing_problem *pb);

@@ -6,4 +6,6 @@ from .sweeps import (SWEEP_DT, SWEEP_N, apply_ccc_parameters, apply_sweep_parame
                      random_sweep, single_drop, sweep_initial_guess)
 from .sharding import (gather_records, pack_records, shard_bounds, shard_indices, unpack_records,  # noqa: F401
                        unshard_order)
+from .schedule import (SCHED_KIN_BOX, SCHED_QF, SCHED_QX, apply_schedule_parameters, ballistic_schedule,  # noqa: F401
+                       reference_schedule)
 from . import sweep_io  # noqa: F401,E402

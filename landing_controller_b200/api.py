@@ -42,7 +42,8 @@ class Problem(ctypes.Structure):
         ("c_ref", ctypes.c_double * 12), ("QN", ctypes.c_double * 12),
         ("mu", ctypes.c_double), ("l_leg_max", ctypes.c_double), ("f_max", ctypes.c_double),
         ("mass", ctypes.c_double), ("Ib", ctypes.c_double * 3), ("Ib_inv", ctypes.c_double * 3),
-        ("Qf", ctypes.c_double * 3), ("kin_box", ctypes.c_double * 3), ("dt", _dp)]
+        ("Qf", ctypes.c_double * 3), ("kin_box", ctypes.c_double * 3), ("dt", _dp),
+        ("formulation", ctypes.c_int), ("cs", _ip), ("QX", ctypes.c_double * 12), ("delta_c", ctypes.c_double)]
 
 
 class Options(ctypes.Structure):
@@ -168,6 +169,24 @@ class LandingSolver:
         self._dt = dt  # keeps the host array alive: the library reads it during each call
         self.problem.dt = dt.ctypes.data_as(_dp)
         self.problem.T = float(dt.sum())
+        return self
+
+    def set_schedule(self, cs=None, QX=None):
+        """Fixed-contact-schedule formulation (quadruped_SRBM_NLP.m; BASELINE configs[0]): cs [N-1, 4] of 0 / 1 and the
+        running state weights QX [12]; None switches back to the contact-implicit formulation."""
+        if cs is None:
+            self._cs, self.problem.cs, self.problem.formulation = None, None, 0
+            for i in range(12):
+                self.problem.QX[i] = 0.0
+            return self
+        cs = np.ascontiguousarray(cs, dtype=np.int32)
+        if cs.shape != (self.N - 1, 4):
+            raise ValueError("cs must have shape (N-1, 4)")
+        self._cs = cs  # keeps the host array alive: the library reads it during each call
+        self.problem.cs = cs.ctypes.data_as(_ip)
+        self.problem.formulation = 1
+        for i in range(12):
+            self.problem.QX[i] = 0.0 if QX is None else float(QX[i])
         return self
 
     def close(self):

@@ -53,6 +53,9 @@ struct landing_ctx {
   // knot spacings of the current call: pinned host staging + device copy (landing_problem.dt or uniform)
   double* h_dt = nullptr;
   double* d_dt = nullptr;
+  // contact schedule of the current call (formulation 1): bit mask per knot
+  unsigned char* h_cs = nullptr;
+  unsigned char* d_cs = nullptr;
 };
 
 // dt[0..N-2] of this call on the device (stream-ordered): the caller's vector or the uniform T/(N-1)
@@ -67,6 +70,20 @@ static int stage_dt(landing_ctx* c, const landing_problem* pb) {
     c->h_dt[k] = h;
   }
   CU(cudaMemcpyAsync(c->d_dt, c->h_dt, sizeof(double) * K, cudaMemcpyHostToDevice, c->stream));
+  if (pb->formulation == 1) {
+    if (!pb->cs) return fail(LANDING_ERR_ARG, "landing_problem: formulation 1 needs the contact schedule cs[4 (N-1)]");
+    if (!(pb->delta_c > 0.0)) return fail(LANDING_ERR_ARG, "landing_problem: delta_c must be positive");
+    if (!c->h_cs) CU(cudaMallocHost(&c->h_cs, K));
+    if (!c->d_cs) CU(cudaMalloc(&c->d_cs, K));
+    for (int k = 0; k < K; k++) {
+      unsigned m = 0;
+      for (int l = 0; l < 4; l++) m |= (pb->cs[4 * k + l] != 0) << l;
+      c->h_cs[k] = (unsigned char)m;
+    }
+    CU(cudaMemcpyAsync(c->d_cs, c->h_cs, K, cudaMemcpyHostToDevice, c->stream));
+  } else if (pb->formulation != 0) {
+    return fail(LANDING_ERR_ARG, "landing_problem: formulation must be 0 or 1");
+  }
   return LANDING_OK;
 }
 
@@ -160,6 +177,8 @@ void landing_destroy(landing_ctx* c) {
   if (c->d_maps) cudaFree(c->d_maps);
   if (c->d_dt) cudaFree(c->d_dt);
   if (c->h_dt) cudaFreeHost(c->h_dt);
+  if (c->d_cs) cudaFree(c->d_cs);
+  if (c->h_cs) cudaFreeHost(c->h_cs);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -217,6 +236,10 @@ void landing_problem_default(landing_problem* pb) {
   for (int i = 0; i < 3; i++) pb->Qf[i] = 0.0;
   pb->kin_box[0] = 0.15; pb->kin_box[1] = 0.15; pb->kin_box[2] = 0.30;
   pb->dt = nullptr;  // uniform T/(N-1)
+  pb->formulation = 0;
+  pb->cs = nullptr;
+  for (int i = 0; i < 12; i++) pb->QX[i] = 0.0;
+  pb->delta_c = 1e-7;
   // composite rigid-body inertia at q_home (get_mass_matrix.m:19-54, generate_landingCtrller_IPOPT.m:99-104)
   pb->mass = 8.251999999999999;
   pb->Ib[0] = 0.05757729852959269; pb->Ib[1] = 0.23400899479539086; pb->Ib[2] = 0.2796738482657981;
@@ -453,7 +476,8 @@ int landing_solve_batch(landing_ctx* c, long long B, int memspace, const landing
   int launches = 0;
   int rc = stage_dt(c, pb);
   if (rc) return rc;
-  rc = solver_run(c->ws, c->dpl, B, memspace, *pb, c->d_dt, o, *io, c->stream, &launches, &err);
+  rc = solver_run(c->ws, c->dpl, B, memspace, *pb, c->d_dt, pb->formulation == 1 ? c->d_cs : nullptr, o, *io, c->stream,
+                  &launches, &err);
   c->launches += launches;
   if (rc) return fail(rc, err);
   return LANDING_OK;

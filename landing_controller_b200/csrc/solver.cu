@@ -267,8 +267,8 @@ void solver_free(SolverWorkspace& ws) {
 }
 
 int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memspace,
-               const landing_problem& pb, const double* dtv, const landing_options& opt, const landing_solve_io& io,
-               cudaStream_t st, int* launches, std::string* err) {
+               const landing_problem& pb, const double* dtv, const unsigned char* csm, const landing_options& opt,
+               const landing_solve_io& io, cudaStream_t st, int* launches, std::string* err) {
   const int N = pl.N;
   if (N - 1 > 1023 / 1) { *err = "landing_solve_batch: N too large"; return LANDING_ERR_ARG; }
   if (!io.x_star || !io.f_star || !io.status || !io.iters) {
@@ -311,7 +311,9 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
   const long long nx = pl.nx, m = pl.m;
   KParams P{};
   P.N = N; P.K = N - 1; P.nx = pl.nx; P.MR = 36 + RK * (N - 1);
-  P.B = B; P.pb = pb; P.pb.dt = nullptr; P.dtv = dtv; P.opt = opt;
+  P.B = B; P.pb = pb; P.pb.dt = nullptr; P.pb.cs = nullptr; P.dtv = dtv; P.csm = csm; P.opt = opt;
+  P.run_qx = 0;
+  for (int i = 0; i < 12; i++) P.run_qx |= (pb.QX[i] != 0.0);
   P.opt.reserved[0] = pl.m;  // m, for the dual scaling s_d
   P.counter = ws.counter; P.scratch = ws.scratch; P.slot = slot; P.tab = ws.tab;
   if (memspace == LANDING_HOST) {

@@ -42,7 +42,8 @@ void solver_free(SolverWorkspace& ws);
 int fp64_peak_run(cudaStream_t st, double* tflops, std::string* err);
 
 int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memspace,
-               const landing_problem& pb, const double* dtv, const landing_options& opt, const landing_solve_io& io,
+               const landing_problem& pb, const double* dtv, const unsigned char* csm, const landing_options& opt,
+               const landing_solve_io& io,
                cudaStream_t st, int* launches, std::string* err);
 
 }  // namespace srb

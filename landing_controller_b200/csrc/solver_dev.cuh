@@ -66,8 +66,10 @@ struct KParams {
   const double* drops;
   const double* x0;
   const double* dtv;  // knot spacings dt[0..K-1] (device)
+  const unsigned char* csm;  // fixed-schedule formulation: contact bit mask of every knot (device), else nullptr
   double *x_star, *f_star, *lam_g, *viol;
   int *status, *iters;
+  int run_qx;  // any QX != 0
   int* counter;
   double* scratch;
   long long slot;  // doubles per CTA slot
@@ -200,14 +202,28 @@ __device__ __forceinline__ bool is_noslip(int rho) { return rho >= 16 && rho < 6
 // dynamics row (0..11: pos,rpy,v,om) <-> state index (pos,rpy,om,v)
 __device__ __forceinline__ int dyn_state(int rho) { return rho < 6 ? rho : (rho < 9 ? rho + 3 : rho - 3); }
 
-// row kinds
-enum { ROW_EQ = 0, ROW_INEQ = 1, ROW_FREE = 2 };
-__device__ __forceinline__ int row_kind(int idx, int K) {
+// row kinds: hard equality (initial state, dynamics: the constraints of the Riccati recursion) | inequality with a slack
+// | free (not a constraint of this formulation / knot) | dual-regularised equality (fixed-schedule rows, ip_ref.h)
+enum { ROW_EQ = 0, ROW_INEQ = 1, ROW_FREE = 2, ROW_EQS = 3 };
+__device__ __forceinline__ int row_kind(const KParams& P, int idx) {
+  const int K = P.K;
   if (idx < 12) return ROW_EQ;
-  if (idx < 36) return ROW_INEQ;
+  const bool sched = P.pb.formulation == 1;
+  if (idx < 36) return sched ? ROW_FREE : ROW_INEQ;
   const int k = (idx - 36) / RK, rho = (idx - 36) - k * RK;
   if (rho < 12) return ROW_EQ;
-  if (k == K - 1 && is_noslip(rho)) return ROW_FREE;
+  if (!sched) return (k == K - 1 && is_noslip(rho)) ? ROW_FREE : ROW_INEQ;
+  const unsigned cs = __ldg(P.csm + k);
+  if (rho < 16) return (cs >> (rho - 12) & 1) ? ROW_INEQ : ROW_EQS;  // f_z in [0, cs f_max]: f_z = 0 in flight
+  if (rho < 64) {
+    const int l = (rho - 16) / 12, j = (rho - 16) - 12 * l;
+    const bool on = cs >> l & 1;
+    if (j == 0) return on ? ROW_EQS : ROW_FREE;                       // cs c_z = 0
+    if (j == 1) return ROW_FREE;
+    if (j < 5) return (on && k < K - 1) ? ROW_EQS : ROW_FREE;         // cs (c+ - c) = 0
+    if (j < 8) return ROW_FREE;
+    return ROW_INEQ;                                                  // kinematic box, leg length
+  }
   return ROW_INEQ;
 }
 __device__ __forceinline__ int row_tab(int idx) { return idx < 36 ? idx : 36 + (idx - 36) % RK; }
@@ -229,6 +245,11 @@ __device__ __forceinline__ void load_knot(const KParams& P, const double* x, int
     kn.cn[i] = last ? 0.0 : x[12 * N + 24 * (k + 1) + i];
   }
   kn.h = __ldg(P.dtv + k);
+  if (P.csm) {
+    const unsigned cs = __ldg(P.csm + k);
+#pragma unroll
+    for (int l = 0; l < 4; l++) kn.csv[l] = (double)(cs >> l & 1);
+  }
   kn.mu = P.pb.mu;
   kn.mass = P.pb.mass;
 #pragma unroll
@@ -273,7 +294,8 @@ __device__ __noinline__ void eval_knot_j(const KParams& P, const Ws& w, const do
     load_knot(P, x, k, kn);
     NoLam nl;
     JSinkP<PART> s{gout + 36 + RK * k, w.JL + (long long)k * NJ_PAD};
-    knot_eval<false, true, true, false>(kn, s, nl);
+    if (P.pb.formulation == 1) knot_eval<false, true, true, false, JSinkP<PART>, NoLam, true>(kn, s, nl);
+    else knot_eval<false, true, true, false>(kn, s, nl);
   }
 }
 template <int PART>
@@ -283,7 +305,8 @@ __device__ __noinline__ void eval_knot_h(const KParams& P, const Ws& w, const do
     load_knot(P, x, k, kn);
     HSinkP<PART> s{w.HL + (long long)k * NH_PAD};
     LamY<false> lam{w.Y + 36 + RK * k};
-    knot_eval<false, false, false, true>(kn, s, lam);
+    if (P.pb.formulation == 1) knot_eval<false, false, false, true, HSinkP<PART>, LamY<false>, true>(kn, s, lam);
+    else knot_eval<false, false, false, true>(kn, s, lam);
   }
 }
 template <int PART>
@@ -293,30 +316,45 @@ __device__ __noinline__ void eval_knot_g(const KParams& P, const double* x, doub
     load_knot(P, x, k, kn);
     NoLam nl;
     GSinkP<PART> s{gout + 36 + RK * k};
-    knot_eval<false, true, false, false>(kn, s, nl);
+    if (P.pb.formulation == 1) knot_eval<false, true, false, false, GSinkP<PART>, NoLam, true>(kn, s, nl);
+    else knot_eval<false, true, false, false>(kn, s, nl);
   }
 }
 
-// running GRF cost of the "CCC" variant (landing_problem.Qf; all zero for the landingCtrller_IPOPT problem)
+// running costs: GRF cost of the "CCC" variant (landing_problem.Qf) and the running state cost of the fixed-schedule
+// formulation (landing_problem.QX, quadruped_SRBM_NLP.m:85-92); all zero for the landingCtrller_IPOPT problem
 __device__ __forceinline__ bool has_run_cost(const KParams& P) {
-  return P.pb.Qf[0] != 0.0 || P.pb.Qf[1] != 0.0 || P.pb.Qf[2] != 0.0;
+  return P.pb.Qf[0] != 0.0 || P.pb.Qf[1] != 0.0 || P.pb.Qf[2] != 0.0 || P.run_qx;
+}
+// Xref of knot k < N-1, component i (linspace of the drop condition towards the terminal reference; the roundings of
+// oracle/srb_ref.c: srb_build_p_x0)
+__device__ __forceinline__ double xref_at(const KParams& P, const double* drop, int k, int i) {
+  const double ref = i < 6 ? P.pb.q_term_ref[i] : P.pb.qd_term_ref[i - 6];
+  return __dadd_rn(drop[i], __dmul_rn(ref - drop[i], (double)k / (double)(P.N - 1)));
 }
 
-// this thread's share of sum_k sum_j Qf[j%3] f_kj^2 dt (dx == nullptr) or of its directional derivative along dx
-__device__ __noinline__ double run_cost_part(const KParams& P, const double* x, const double* dx) {
+// this thread's share of sum_k dt_k (sum_j Qf[j%3] f_kj^2 + sum_i QX_i (X_ki - Xref_ki)^2) (dx == nullptr) or of its
+// directional derivative along dx
+__device__ __noinline__ double run_cost_part(const KParams& P, const double* drop, const double* x, const double* dx) {
   const int N = P.N;
   double acc = 0.0;
   for (int item = TID; item < P.K * 12; item += NT) {
     const int k = item / 12, j = item - 12 * k, iv = 12 * N + 24 * k + 12 + j;
-    const double q = P.pb.Qf[j % 3] * __ldg(P.dtv + k) * x[iv];
+    const double h = __ldg(P.dtv + k);
+    const double q = P.pb.Qf[j % 3] * h * x[iv];
     acc += dx ? 2.0 * q * dx[iv] : q * x[iv];
+    if (P.run_qx) {
+      const int ix = 12 * k + j;
+      const double e = x[ix] - xref_at(P, drop, k, j), qe = P.pb.QX[j] * h * e;
+      acc += dx ? 2.0 * qe * dx[ix] : qe * e;
+    }
   }
   return acc;
 }
 
 // g(x) (and, when LISTS, the J/H entry lists with multipliers Y) for all knots; returns f(x)
 template <bool LISTS>
-__device__ double eval_all(const KParams& P, const Ws& w, const double* x, double* gout, double* red) {
+__device__ double eval_all(const KParams& P, const Ws& w, const double* drop, const double* x, double* gout, double* red) {
   const int N = P.N, tid = TID, warp = tid >> 5, lane = tid & 31;
   if (LISTS) {
     // warps 0..EVP-1: Jacobian lists (part = warp), warps 4..4+EVP-1: Hessian lists; lane = knot
@@ -358,7 +396,7 @@ __device__ double eval_all(const KParams& P, const Ws& w, const double* x, doubl
     const double ref = i < 6 ? P.pb.q_term_ref[i] : P.pb.qd_term_ref[i - 6];
     fl = P.pb.QN[i] * (q - ref) * (q - ref);
   }
-  if (has_run_cost(P)) fl += run_cost_part(P, x, nullptr);  // (block-uniform)
+  if (has_run_cost(P)) fl += run_cost_part(P, drop, x, nullptr);  // (block-uniform)
   return bsum(red, fl);  // (syncs: gout / lists are visible to the whole CTA afterwards)
 }
 
@@ -489,7 +527,7 @@ __device__ __noinline__ void row_steps(const bool MERIT, const KParams& P, const
   cp_async_commit();
   // boundary rows meanwhile (initial-state rows, terminal inequality rows)
   if (tid < 12) si.theta += fabs(w.G[tid] - drop[tid]);
-  else if (tid < 36) {
+  else if (tid < 36 && P.pb.formulation != 1) {  // (the fixed-schedule formulation has no terminal rows)
     const int j = tid - 12, i = (j < 12 ? j % 6 : 6 + (j - 12) % 6);
     row_step(w, tid, tab[tid], tab[NROWTAB + tid], w.dx[12 * (N - 1) + i], mu, tau, si);
   }
@@ -506,9 +544,10 @@ __device__ __noinline__ void row_steps(const bool MERIT, const KParams& P, const
     if (k < K && t < RK) {
       const double* rb = ring(k);
       const int rho = t, idx = 36 + RK * k + rho;
-      if (rho < 12) {
+      const int kind = row_kind(P, idx);
+      if (kind == ROW_EQ) {
         si.theta += fabs(rb[RB_G + rho]);
-      } else if (!(k == K - 1 && is_noslip(rho))) {
+      } else if (kind != ROW_FREE) {
         double jdx = 0.0, jd1 = 0.0;
         const int p0 = t_rptr[rho], p1 = t_rptr[rho + 1];
         for (int p = p0; p < p1; p += 4) {  // (lists padded to fours with null terms; dc+ is zero at the last knot)
@@ -520,7 +559,14 @@ __device__ __noinline__ void row_steps(const bool MERIT, const KParams& P, const
         }
         jdx += jd1;
         pf.lap(PH_X2);
-        row_step_sm(MERIT, w, idx, rb, rho, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
+        if (kind == ROW_EQS) {  // y+ = y + sigma (J dx + c); no slack, no step-length limit
+          const double c = rb[RB_G + rho];
+          si.theta += fabs(c);
+          w.YN[idx] = w.Y[idx] + rb[RB_SIG + rho] * (jdx + c);
+          w.DS[idx] = 0.0; w.DZL[idx] = 0.0; w.DZU[idx] = 0.0;
+        } else {
+          row_step_sm(MERIT, w, idx, rb, rho, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
+        }
         pf.lap(PH_X3);
       }
     }
@@ -559,9 +605,9 @@ __device__ __noinline__ void merit_trial(const KParams& P, const Ws& w, const do
     for (int u = 0; u < RU; u++) {
       const int idx = base + u * NT;
       if (idx >= MR) break;
-      const int kind = row_kind(idx, K);
+      const int kind = row_kind(P, idx);
       if (kind == ROW_FREE) continue;
-      if (kind == ROW_EQ) {
+      if (kind == ROW_EQ || kind == ROW_EQS) {
         th += fabs(gt[u] - (idx < 12 ? drop[idx] : 0.0));
         continue;
       }
@@ -608,15 +654,15 @@ __device__ __noinline__ void row_errors(const KParams& P, const Ws& w, const dou
     for (int u = 0; u < RU; u++) {
       const int idx = base + u * NT;
       if (idx >= MR) break;
-      const int kind = row_kind(idx, K);
+      const int kind = row_kind(P, idx);
       if (kind == ROW_FREE) continue;
       const double g = gv[u], y = yv[u];
       ys += fabs(y);
-      if (kind == ROW_EQ) {
+      if (kind == ROW_EQ || kind == ROW_EQS) {
         const double c = fabs(g - (idx < 12 ? drop[idx] : 0.0));
         prim = fmax(prim, c);
         viol = fmax(viol, c);
-        SIG[idx] = 0.0;
+        SIG[idx] = kind == ROW_EQS ? 1.0 / P.pb.delta_c : 0.0;  // dual-regularised equality: sigma = 1 / delta_c
         continue;
       }
       const int t = row_tab(idx);
@@ -657,7 +703,7 @@ __device__ __noinline__ double compl_at(const KParams& P, const Ws& w, const dou
   const int K = P.K, MR = P.MR;
   double cmu = 0;
   for (int idx = TID; idx < MR; idx += NT) {
-    if (row_kind(idx, K) != ROW_INEQ) continue;
+    if (row_kind(P, idx) != ROW_INEQ) continue;
     const int t = row_tab(idx);
     const double lb = tab[t], ub = tab[NROWTAB + t], s = w.S[idx];
     if (isfinite(lb)) cmu = fmax(cmu, fabs(w.ZL[idx] * (s - lb) - mu));
@@ -685,7 +731,9 @@ __device__ __noinline__ void row_yhat(const KParams& P, const Ws& w, const doubl
     for (int u = 0; u < RU; u++) {
       const int idx = base + u * NT;
       if (idx >= MR) break;
-      if (row_kind(idx, K) != ROW_INEQ) { YH[idx] = 0.0; continue; }
+      const int kind = row_kind(P, idx);
+      if (kind == ROW_EQS) { YH[idx] = w.Y[idx] + sg[u] * gv[u]; continue; }  // yhat = y + sigma c
+      if (kind != ROW_INEQ) { YH[idx] = 0.0; continue; }
       const int t = row_tab(idx);
       const double lb = tab[t], ub = tab[NROWTAB + t], s = sv[u];
       double yh = sg[u] * (gv[u] - s);
@@ -697,7 +745,7 @@ __device__ __noinline__ void row_yhat(const KParams& P, const Ws& w, const doubl
 }
 
 // max |grad f + J' y| (gradient of the Lagrangian w.r.t. x): one (knot, variable) item per thread
-__device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const double* smem, double* red) {
+__device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const double* drop, const double* smem, double* red) {
   const int N = P.N, K = P.K, tid = TID;
   const int* t_cptr = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_cptr;
   const int* t_cterms = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_cterms;
@@ -718,6 +766,7 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
       }
     }
     if (v >= 24 && has_run_cost(P)) a += 2.0 * P.pb.Qf[(v - 24) % 3] * w.x[12 * N + 24 * k + 12 + (v - 24)] * __ldg(P.dtv + k);
+    if (v < 12 && P.run_qx) a += 2.0 * P.pb.QX[v] * (w.x[12 * k + v] - xref_at(P, drop, k, v)) * __ldg(P.dtv + k);
     if (v < NS) {
       if (k > 0) {  // what knot k-1 contributes to (X_k, c_k) through its X+ / c+ columns
         const double* Jp = Jk - NJ_PAD;
@@ -760,7 +809,7 @@ __device__ __noinline__ void init_slacks(const KParams& P, const Ws& w, const do
   const double bp = P.opt.bound_push, bf = P.opt.bound_frac;
   for (int idx = TID; idx < MR; idx += NT) {
     w.Y[idx] = 0.0; w.ZL[idx] = 0.0; w.ZU[idx] = 0.0; w.S[idx] = 0.0;
-    if (row_kind(idx, K) != ROW_INEQ) continue;
+    if (row_kind(P, idx) != ROW_INEQ) continue;
     const int t = row_tab(idx);
     const double l = tab[t], u = tab[NROWTAB + t];
     double sv = w.G[idx];
@@ -868,7 +917,7 @@ __device__ void solve_one(const KParams& P, Ws& w, double* smem, long long b) {
     w.SIG[i] = 0.0; w.YH[i] = 0.0; w.Y[i] = 0.0;
   }
   __syncthreads();
-  double f = eval_all<false>(P, w, w.x, w.G, red);
+  double f = eval_all<false>(P, w, drop, w.x, w.G, red);
   double mu = opt.mu_init;
   init_slacks(P, w, tab, mu);
 
@@ -880,12 +929,12 @@ __device__ void solve_one(const KParams& P, Ws& w, double* smem, long long b) {
   Prof pf{P.prof, 0};
   for (it = 0; it <= opt.max_iter; it++) {
     pf.start();
-    f = eval_all<true>(P, w, w.x, w.G, red);
+    f = eval_all<true>(P, w, drop, w.x, w.G, red);
     pf.lap(PH_EVAL);
     Errs er;
     row_errors(P, w, tab, drop, red, mu, er);
     pf.lap(PH_ERR);
-    const double dual = fmax(er.dual, dual_inf_x(P, w, smem, red));
+    const double dual = fmax(er.dual, dual_inf_x(P, w, drop, smem, red));
     pf.lap(PH_DUAL);
     pf.count(PH_NITER);
     const double s_d = fmax(s_max, (er.ysum + er.zsum) / (double)(P.opt.reserved[0] + er.nzb)) / s_max;
@@ -913,7 +962,7 @@ __device__ void solve_one(const KParams& P, Ws& w, double* smem, long long b) {
     }
     row_yhat(P, w, tab, mu);
     __syncthreads();
-    condense_all(P, w, smem);
+    condense_all(P, w, smem, drop);
     pf.lap(PH_MU);
     const double tau = fmax(tau_min, 1.0 - mu);
     // factorise with inertia correction (IPOPT's delta_w schedule)
@@ -958,7 +1007,7 @@ __device__ void solve_one(const KParams& P, Ws& w, double* smem, long long b) {
         const double ref = tid < 6 ? P.pb.q_term_ref[tid] : P.pb.qd_term_ref[tid - 6];
         d = 2.0 * P.pb.QN[tid] * (q - ref) * w.dx[12 * (N - 1) + tid];
       }
-      if (has_run_cost(P)) d += run_cost_part(P, w.x, w.dx);
+      if (has_run_cost(P)) d += run_cost_part(P, drop, w.x, w.dx);
       dphi += bsum(red, d);
     }
     double alpha = si.a_pr, ft = f, phb = 0.0, tht = 0.0;
@@ -967,7 +1016,7 @@ __device__ void solve_one(const KParams& P, Ws& w, double* smem, long long b) {
     while (alpha > 1e-12 * si.a_pr && ls < 40) {
       for (int i = tid; i < nx; i += NT) w.xt[i] = w.x[i] + alpha * w.dx[i];
       __syncthreads();
-      ft = eval_all<false>(P, w, w.xt, w.GT, red);
+      ft = eval_all<false>(P, w, drop, w.xt, w.GT, red);
       merit_trial(P, w, tab, drop, red, alpha, mu, phb, tht);
       const double pht = ft + mu * phb;
       int filt_ok = 1;
@@ -1045,10 +1094,10 @@ __device__ void solve_one(const KParams& P, Ws& w, double* smem, long long b) {
         for (int u = 0; u < RU; u++) {
           const int idx = base + u * NT;
           if (idx >= MR) break;
-          const int kind = row_kind(idx, K);
+          const int kind = row_kind(P, idx);
           if (kind == ROW_FREE) continue;
           Yp[idx] = yv[u] + alpha * (yn[u] - yv[u]);
-          if (kind == ROW_EQ) continue;
+          if (kind != ROW_INEQ) continue;
           const int t = row_tab(idx);
           const double lb = tab[t], ub = tab[NROWTAB + t];
           const double s = sv[u] + alpha * ds[u];

@@ -37,6 +37,7 @@ constexpr double GRAV_Z = -9.81;            // get_robot_model.m:140
 struct Knot {
   double X[12], c[12], f[12], Xn[12], cn[12];
   double h, mu, mass, Ib[3], Ibinv[3];
+  double csv[4];  // contact schedule of this knot (0 / 1 per leg); read by the SCHED instantiation only
 };
 
 // hip offsets FR, FL, BR, BL: get_robot_params.m:90-91 (hip_z = 0)
@@ -86,7 +87,10 @@ SRB_HD void zcross(const double v[3], double o[3]) {  // z_hat x v
   o[2] = 0.0;
 }
 
-template <bool LAST, bool WG, bool WJ, bool WH, class Sink, class Lam>
+// SCHED: the fixed-contact-schedule formulation (quadruped_SRBM_NLP.m:145-158) in the same row layout: row leg+0 is
+// cs c_z (an equality), rows leg+2..4 are cs (c+ - c) (equalities, linear), rows leg+1 and leg+5..7 are unused (zero);
+// the f_z rows 12..15 are unchanged (their bound becomes cs f_max).
+template <bool LAST, bool WG, bool WJ, bool WH, class Sink, class Lam, bool SCHED = false>
 SRB_HD void knot_eval(const Knot& kn, Sink& out, const Lam& lam) {
   using RW = Rows<LAST>;
   const double h = kn.h, mu = kn.mu;
@@ -157,14 +161,14 @@ SRB_HD void knot_eval(const Knot& kn, Sink& out, const Lam& lam) {
     for (int l = 0; l < 4; l++) {
       const double fz = kn.f[3 * l + 2], cz = kn.c[3 * l + 2];
       out.g(12 + l, fz);
-      out.g(RW::leg(l), cz);
-      out.g(RW::leg(l) + 1, fz * cz);
+      out.g(RW::leg(l), SCHED ? kn.csv[l] * cz : cz);
+      out.g(RW::leg(l) + 1, SCHED ? 0.0 : fz * cz);
       if (!LAST) {
 #pragma unroll
         for (int a = 0; a < 3; a++) {
-          const double ns = fz * (kn.cn[3 * l + a] - kn.c[3 * l + a]);
+          const double ns = (SCHED ? kn.csv[l] : fz) * (kn.cn[3 * l + a] - kn.c[3 * l + a]);
           out.g(RW::leg(l) + 2 + a, ns);
-          out.g(RW::leg(l) + 5 + a, ns);
+          out.g(RW::leg(l) + 5 + a, SCHED ? 0.0 : ns);
         }
       }
       out.g(RW::kin(l), prel[l][0]);
@@ -270,18 +274,19 @@ SRB_HD void knot_eval(const Knot& kn, Sink& out, const Lam& lam) {
       const double fz = kn.f[3 * l + 2], cz = kn.c[3 * l + 2];
       const int L = RW::leg(l), K = RW::kin(l);
       out.j(n++, 12 + l, 24 + 3 * l + 2, 1.0);
-      out.j(n++, L, 12 + 3 * l + 2, 1.0);
-      out.j(n++, L + 1, 12 + 3 * l + 2, fz);
-      out.j(n++, L + 1, 24 + 3 * l + 2, cz);
+      out.j(n++, L, 12 + 3 * l + 2, SCHED ? kn.csv[l] : 1.0);
+      out.j(n++, L + 1, 12 + 3 * l + 2, SCHED ? 0.0 : fz);
+      out.j(n++, L + 1, 24 + 3 * l + 2, SCHED ? 0.0 : cz);
       if (!LAST) {
 #pragma unroll
         for (int rep = 0; rep < 2; rep++)
 #pragma unroll
           for (int a = 0; a < 3; a++) {
             const int row = L + 2 + 3 * rep + a;
-            out.j(n++, row, 12 + 3 * l + a, -fz);
-            out.j(n++, row, 24 + 3 * l + 2, kn.cn[3 * l + a] - kn.c[3 * l + a]);
-            out.j(n++, row, 48 + 3 * l + a, fz);
+            const double wgt = SCHED ? (rep == 0 ? kn.csv[l] : 0.0) : fz;
+            out.j(n++, row, 12 + 3 * l + a, -wgt);
+            out.j(n++, row, 24 + 3 * l + 2, SCHED ? 0.0 : kn.cn[3 * l + a] - kn.c[3 * l + a]);
+            out.j(n++, row, 48 + 3 * l + a, wgt);
           }
       }
 #pragma unroll
@@ -350,7 +355,7 @@ SRB_HD void knot_eval(const Knot& kn, Sink& out, const Lam& lam) {
 #pragma unroll
       for (int a = 0; a < 3; a++) {
         lpa[l][a] = lam(RW::kin(l) + a);
-        lns[l][a] = LAST ? 0.0 : lam(RW::leg(l) + 2 + a) + lam(RW::leg(l) + 5 + a);
+        lns[l][a] = (LAST || SCHED) ? 0.0 : lam(RW::leg(l) + 2 + a) + lam(RW::leg(l) + 5 + a);
       }
     }
     // r_a - r_a
@@ -456,7 +461,7 @@ SRB_HD void knot_eval(const Knot& kn, Sink& out, const Lam& lam) {
       out.h(n++, vc + 1, vf + 2, y[0] - lns[l][1]);
       out.h(n++, vc + 2, vf + 0, y[1]);
       out.h(n++, vc + 2, vf + 1, -y[0]);
-      out.h(n++, vc + 2, vf + 2, lam(RW::leg(l) + 1) - lns[l][2]);
+      out.h(n++, vc + 2, vf + 2, (SCHED ? 0.0 : lam(RW::leg(l) + 1)) - lns[l][2]);
       if (!LAST) {
 #pragma unroll
         for (int a = 0; a < 3; a++) out.h(n++, vf + 2, 48 + 3 * l + a, lns[l][a]);

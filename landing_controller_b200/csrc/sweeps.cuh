@@ -80,7 +80,7 @@ template <int PENDING> __device__ __forceinline__ void cp_async_wait_group() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(PENDING) : "memory");
 }
 
-__device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double* smem) {
+__device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double* smem, const double* drop) {
   const int K = P.K, tid = TID;
   const int* tbl = reinterpret_cast<const int*>(smem + SM_TBL);
   const SolverTables& tb = P.tab;
@@ -128,6 +128,7 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
         if (run) {  // Hessian diagonal of the running GRF cost (force variables are m = 0..11)
           const int ab = abh & 4095, ta = ab / NW;
           if (ta < 12 && ab == ta * NW + ta) a0 += run2q(ta) * __ldg(P.dtv + k);
+          if (P.run_qx && ta >= 24 && ta < 36 && ab == ta * NW + ta) a0 += 2.0 * P.pb.QX[ta - 24] * __ldg(P.dtv + k);
         }
         ST_STREAM(&ct[it], a0 + a1);
       } else if (it < tb.n_u + NW) {
@@ -140,6 +141,8 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
           a1 += YHs[u1 >> 10] * Js[u1 & 1023];
         }
         if (run && m < 12) a0 += run2q(m) * __ldg(P.dtv + k) * w.x[12 * P.N + 24 * k + 12 + m];  // gradient of the running GRF cost
+        if (P.run_qx && m >= 24 && m < 36)  // gradient of the running state cost
+          a0 += 2.0 * P.pb.QX[m - 24] * (w.x[12 * k + m - 24] - xref_at(P, drop, k, m - 24)) * __ldg(P.dtv + k);
         ST_STREAM(&ct[CT_Q + m], a0 + a1);
       } else if (it < tb.n_u + NW + tb.n_g) {
         const int n = it - tb.n_u - NW;

@@ -44,6 +44,10 @@ void ip_options_default(ip_options *o) {
   o->max_restarts = 8;
   o->run_Qf[0] = o->run_Qf[1] = o->run_Qf[2] = 0.0;
   o->kin_box[0] = 0.15; o->kin_box[1] = 0.15; o->kin_box[2] = 0.30;
+  o->formulation = 0;
+  o->cs = NULL;
+  for (int i = 0; i < 12; i++) o->QX[i] = 0.0;
+  o->delta_c = 1e-7;
 }
 
 typedef struct {
@@ -66,7 +70,33 @@ typedef struct {
   int nfilt;
 } ipws;
 
-static int is_eq_row(int N, int i) {
+/* row classes: hard equality (initial state, dynamics: the constraints of the Riccati recursion) | inequality with a
+ * slack | free (not a constraint of this formulation / scenario) | dual-regularised equality (fixed-schedule rows) */
+enum { K_EQ = 0, K_INEQ = 1, K_FREE = 2, K_EQS = 3 };
+static int row_kind_f(int N, int formulation, const int *cs, int i) {
+  const int sched = formulation == 1;
+  if (i < 12) return K_EQ;
+  if (i < 36) return sched ? K_FREE : K_INEQ;
+  const int k = (i - 36) / 104, rho = (i - 36) % 104;
+  if (rho < 12) return K_EQ;
+  if (!sched) return K_INEQ;
+  const int last = (k == N - 2), stride = last ? 6 : 12;
+  const int *c4 = cs + 4 * k;
+  if (rho < 16) return c4[rho - 12] ? K_INEQ : K_EQS;          /* f_z in [0, cs f_max]: f_z = 0 in flight */
+  if (rho < 16 + 4 * stride) {
+    const int l = (rho - 16) / stride, j = (rho - 16) % stride;
+    if (j == 0) return c4[l] ? K_EQS : K_FREE;                 /* cs c_z = 0 */
+    if (j == 1) return K_FREE;                                 /* (f_z c_z row of the contact-implicit form) */
+    if (!last) {
+      if (j < 5) return c4[l] ? K_EQS : K_FREE;                /* cs (c+ - c) = 0 */
+      if (j < 8) return K_FREE;
+    }
+    return K_INEQ;                                             /* kinematic box, leg length */
+  }
+  return K_INEQ;
+}
+#define ROWK(w, i) row_kind_f((w)->N, (w)->opt->formulation, (w)->opt->cs, (i))
+static int is_eq_row(int N, int i) { /* hard equality rows (same in both formulations) */
   (void)N;
   if (i < 12) return 1;
   if (i < 36) return 0;
@@ -112,24 +142,97 @@ static void ws_free(ipws *w) {
 
 /* ---------------------------------------------------------------- evaluation */
 /* running GRF cost sum_k sum_j Qf[j%3] f_kj^2 dt_k (generate_quadruped_SRBM_CCC.m:80-88 with Uref forces 0) */
+static int has_QX(const ipws *w) {
+  for (int i = 0; i < 12; i++) if (w->opt->QX[i] != 0.0) return 1;
+  return 0;
+}
 static double run_cost(const ipws *w, const double *p, const double *x) {
   const int N = w->N;
-  const double *Qf = w->opt->run_Qf;
-  if (Qf[0] == 0.0 && Qf[1] == 0.0 && Qf[2] == 0.0) return 0.0;
+  const double *Qf = w->opt->run_Qf, *QX = w->opt->QX;
+  const int hf = (Qf[0] != 0.0 || Qf[1] != 0.0 || Qf[2] != 0.0), hx = has_QX(w);
+  if (!hf && !hx) return 0.0;
   double c = 0.0;
   for (int k = 0; k < N - 1; k++) {
     const double h = p[w->pl->o_dt + k];
-    for (int j = 0; j < 12; j++) {
-      const double fj = x[12 * N + 24 * k + 12 + j];
-      c += Qf[j % 3] * fj * fj * h;
-    }
+    if (hf)
+      for (int j = 0; j < 12; j++) {
+        const double fj = x[12 * N + 24 * k + 12 + j];
+        c += Qf[j % 3] * fj * fj * h;
+      }
+    if (hx) /* running state cost (quadruped_SRBM_NLP.m:86-90), Xref = p[0 .. 12N) */
+      for (int i = 0; i < 12; i++) {
+        const double e = x[12 * k + i] - p[12 * k + i];
+        c += QX[i] * e * e * h;
+      }
   }
   return c;
+}
+
+/* knot lists of the fixed-schedule formulation: the contact-implicit template with the rows c_z, f_z (c+ - c) replaced
+ * by cs c_z and cs (c+ - c) (linear: no Hessian contribution) -- values, Jacobian entries and multipliers patched */
+static void knot_lists_sched(const ipws *w, const double *x, const double *p, int k, const double *lam_local,
+                             double *gl, double *Jl, double *Hl) {
+  const int N = w->N, last = (k == N - 2), nj = last ? SRB_NJ_LAST : SRB_NJ_INT, stride = last ? 6 : 12;
+  const srb_jpat *jp = last ? w->jpl : w->jpi;
+  const int *c4 = w->opt->cs + 4 * k;
+  double lam[104];
+  const int nrow = last ? 80 : 104;
+  for (int r = 0; r < nrow; r++) lam[r] = lam_local[r];
+  for (int l = 0; l < 4; l++) { /* rows that are linear (or absent) here must not reach the Hessian */
+    const int L = 16 + stride * l;
+    lam[L + 1] = 0.0;
+    if (!last) for (int j = 2; j < 8; j++) lam[L + j] = 0.0;
+  }
+  srb_knot_lists(w->pl, x, p, k, lam, gl, Jl, Hl);
+  const double *U = x + 12 * N + 24 * k;
+  for (int l = 0; l < 4; l++) {
+    const int L = 16 + stride * l;
+    const double cs = (double)c4[l];
+    gl[L] = cs * U[3 * l + 2];
+    gl[L + 1] = 0.0;
+    if (!last)
+      for (int a = 0; a < 3; a++) {
+        gl[L + 2 + a] = cs * (U[24 + 3 * l + a] - U[3 * l + a]);
+        gl[L + 5 + a] = 0.0;
+      }
+  }
+  for (int e = 0; e < nj; e++) {
+    const int r = jp[e].r, v = jp[e].v;
+    if (r < 16 || r >= 16 + 4 * stride) continue;
+    const int l = (r - 16) / stride, j = (r - 16) % stride;
+    const double cs = (double)c4[l];
+    if (j == 0) Jl[e] = cs;                       /* d(cs c_z)/d c_z */
+    else if (j == 1) Jl[e] = 0.0;
+    else if (!last && j < 5) {
+      if (v >= 12 && v < 24) Jl[e] = -cs;         /* c_k */
+      else if (v >= 48) Jl[e] = cs;               /* c_{k+1} */
+      else Jl[e] = 0.0;                           /* f_z */
+    } else if (!last && j < 8) Jl[e] = 0.0;
+  }
 }
 static double eval_g(ipws *w, const double *p, const double *x, double *g) {
   double f;
   srb_f(w->pl, x, p, &f);
   srb_g(w->pl, x, p, g);
+  if (w->opt->formulation == 1) { /* rows of the fixed-schedule formulation (see knot_lists_sched) */
+    const int N = w->N;
+    for (int k = 0; k < N - 1; k++) {
+      const int last = (k == N - 2), stride = last ? 6 : 12;
+      const double *U = x + 12 * N + 24 * k;
+      double *gl = g + 36 + 104 * k;
+      for (int l = 0; l < 4; l++) {
+        const int L = 16 + stride * l;
+        const double cs = (double)w->opt->cs[4 * k + l];
+        gl[L] = cs * U[3 * l + 2];
+        gl[L + 1] = 0.0;
+        if (!last)
+          for (int a = 0; a < 3; a++) {
+            gl[L + 2 + a] = cs * (U[24 + 3 * l + a] - U[3 * l + a]);
+            gl[L + 5 + a] = 0.0;
+          }
+      }
+    }
+  }
   return f + run_cost(w, p, x);
 }
 
@@ -138,8 +241,12 @@ static void merit(const ipws *w, double f, const double *g, const double *s, dou
                   double *theta) {
   double ph = f, th = 0;
   for (int i = 0; i < w->m; i++) {
-    if (is_eq_row(w->N, i)) {
+    const int kind = ROWK(w, i);
+    if (kind == K_FREE) continue;
+    if (kind == K_EQ) {
       th += fabs(g[i] - w->lb[i]);
+    } else if (kind == K_EQS) {
+      th += fabs(g[i]);
     } else {
       th += fabs(g[i] - s[i]);
       if (isfinite(w->lb[i])) ph -= mu * log(s[i] - w->lb[i]);
@@ -162,11 +269,19 @@ static void assemble(ipws *w, const double *p, double mu, double *err, double *c
   int nb = 0;
   /* barrier terms per inequality row */
   for (int i = 0; i < m; i++) {
+    const int kind = ROWK(w, i);
+    if (kind == K_FREE) { w->sig[i] = 0; w->yhat[i] = 0; continue; }
     ys += fabs(w->y[i]);
-    if (is_eq_row(N, i)) {
+    if (kind == K_EQ) {
       prim = fmax(prim, fabs(w->g[i] - w->lb[i]));
       w->sig[i] = 0;
       w->yhat[i] = 0;
+      continue;
+    }
+    if (kind == K_EQS) { /* dual-regularised equality: sigma = 1/delta_c, yhat = y + sigma c */
+      prim = fmax(prim, fabs(w->g[i]));
+      w->sig[i] = 1.0 / w->opt->delta_c;
+      w->yhat[i] = w->y[i] + w->sig[i] * w->g[i];
       continue;
     }
     double sg = 0, yh = 0, rs = -w->y[i];
@@ -217,7 +332,8 @@ static void assemble(ipws *w, const double *p, double mu, double *err, double *c
     double *Jl = w->Jl + k * SRB_NJ_INT, *Hl = w->Hl + k * SRB_NH_INT;
     double gl[104];
     const int rb = 36 + 104 * k;
-    srb_knot_lists(pl, w->x, p, k, w->y + rb, gl, Jl, Hl);
+    if (w->opt->formulation == 1) knot_lists_sched(w, w->x, p, k, w->y + rb, gl, Jl, Hl);
+    else srb_knot_lists(pl, w->x, p, k, w->y + rb, gl, Jl, Hl);
     double *M = w->M + (size_t)k * NW * NW, *G = w->G + k * 12 * 36, *q = w->q + k * NW, *r = w->r + k * 12;
     memset(M, 0, sizeof(double) * NW * NW);
     memset(G, 0, sizeof(double) * 12 * 36);
@@ -257,6 +373,13 @@ static void assemble(ipws *w, const double *p, double mu, double *err, double *c
           q[24 + j] += gj;
           M[(24 + j) * NW + 24 + j] += 2.0 * Qf[j % 3] * h;
           w->gradL[gvar(N, k, 24 + j)] += gj;
+        }
+      if (has_QX(w)) /* running state cost */
+        for (int i = 0; i < 12; i++) {
+          const double gi = 2.0 * w->opt->QX[i] * (w->x[12 * k + i] - p[12 * k + i]) * h;
+          q[i] += gi;
+          M[i * NW + i] += 2.0 * w->opt->QX[i] * h;
+          w->gradL[12 * k + i] += gi;
         }
     }
   }
@@ -483,6 +606,12 @@ static void recover_steps(ipws *w, double mu) {
   }
   for (int i = 0; i < w->m; i++) {
     if (is_eq_row(N, i)) { w->ds[i] = 0; w->dzL[i] = w->dzU[i] = 0; continue; }
+    const int kind = ROWK(w, i);
+    if (kind != K_INEQ) { /* regularised equality: y+ = y + sigma (J dx + c), no slack; free rows: nothing */
+      w->yn[i] = kind == K_EQS ? w->y[i] + w->sig[i] * w->ds[i] : 0.0;
+      w->ds[i] = 0; w->dzL[i] = w->dzU[i] = 0;
+      continue;
+    }
     double yn = w->sig[i] * w->ds[i];
     w->dzL[i] = w->dzU[i] = 0;
     if (isfinite(w->lb[i])) {
@@ -522,7 +651,7 @@ static void init_slacks(ipws *w, const ip_options *opt, double mu) {
   const int N = w->N, m = w->m;
   for (int i = 0; i < m; i++) {
     w->y[i] = 0; w->zL[i] = 0; w->zU[i] = 0; w->s[i] = 0;
-    if (is_eq_row(N, i)) continue;
+    if (is_eq_row(N, i) || ROWK(w, i) != K_INEQ) continue;
     const double l = w->lb[i], u = w->ub[i];
     double sv = w->g[i];
     if (isfinite(l) && isfinite(u)) {
@@ -559,10 +688,17 @@ static int ip_solve_ws(ipws *w, const double *p, const double *x0, const ip_opti
       w->lbo[kin + 1] = -opt->kin_box[1]; w->ubo[kin + 1] = opt->kin_box[1];
       w->lbo[kin + 2] = -opt->kin_box[2]; w->ubo[kin + 2] = 0.0;
     }
+  if (opt->formulation == 1)
+    for (int i = 0; i < m; i++) {
+      const int kind = ROWK(w, i);
+      if (kind == K_FREE) { w->lbo[i] = -HUGE_VAL; w->ubo[i] = HUGE_VAL; }
+      else if (kind == K_EQS) { w->lbo[i] = 0.0; w->ubo[i] = 0.0; }
+    }
   /* relaxed bounds (bound_relax_factor) on inequality rows */
   for (int i = 0; i < m; i++) {
     w->lb[i] = w->lbo[i];
     w->ub[i] = w->ubo[i];
+    if (opt->formulation == 1 && ROWK(w, i) == K_EQS) { w->lb[i] = -HUGE_VAL; w->ub[i] = HUGE_VAL; continue; }
     if (!is_eq_row(N, i)) {
       if (isfinite(w->lb[i])) w->lb[i] -= opt->bound_relax_factor * fmax(1.0, fabs(w->lb[i]));
       if (isfinite(w->ub[i])) w->ub[i] += opt->bound_relax_factor * fmax(1.0, fabs(w->ub[i]));
@@ -667,6 +803,10 @@ static int ip_solve_ws(ipws *w, const double *p, const double *x0, const ip_opti
           const int iv = 12 * N + 24 * k + 12 + j;
           dphi += 2.0 * opt->run_Qf[j % 3] * w->x[iv] * p[w->pl->o_dt + k] * w->dx[iv];
         }
+    if (has_QX(w))
+      for (int k = 0; k < N - 1; k++)
+        for (int i = 0; i < 12; i++)
+          dphi += 2.0 * opt->QX[i] * (w->x[12 * k + i] - p[12 * k + i]) * p[w->pl->o_dt + k] * w->dx[12 * k + i];
     for (int i = 0; i < m; i++) {
       if (is_eq_row(N, i)) continue;
       if (isfinite(w->lb[i])) dphi -= mu * w->ds[i] / (w->s[i] - w->lb[i]);

@@ -40,6 +40,17 @@ typedef struct ip_options {
    * {0.15, 0.15, 0.30} give the IPOPT variant (generate_landingCtrller_IPOPT.m:83-85,150-155). */
   double run_Qf[3];
   double kin_box[3];
+  /* Fixed-contact-schedule formulation (BASELINE configs[0]; quadruped_SRBM_NLP.m:84-176): formulation = 1 replaces the
+   * complementarity / no-slip inequality rows by  f_z <= cs f_max (:148),  cs c_z = 0 (:154),  cs (c+ - c) = 0 (:155-158),
+   * drops the terminal rows (:105-108 are commented out) and adds the running state cost sum_k (X_k - Xref_k)' QX
+   * (X_k - Xref_k) dt_k (:85-92; Qc = 0 in the reference's parameter set :213 and is not implemented).  cs[4 (N-1)]:
+   * cs[4 k + leg] in {0, 1}.  The extra equality rows are handled as IPOPT handles equality rows of a rank-deficient
+   * Jacobian (they vanish identically where cs = 0): dual regularisation delta_c, i.e. sigma = 1 / delta_c in the
+   * condensed stage matrix and y+ = y + (J dx + c) / delta_c. */
+  int formulation;
+  const int *cs;
+  double QX[12];
+  double delta_c; /* 1e-7 */
 } ip_options;
 
 typedef struct ip_result {

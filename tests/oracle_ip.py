@@ -13,7 +13,18 @@ class IpOptions(ctypes.Structure):
                 ("mu_init", ctypes.c_double), ("bound_push", ctypes.c_double), ("bound_frac", ctypes.c_double),
                 ("bound_relax_factor", ctypes.c_double), ("max_soc", ctypes.c_int), ("verbose", ctypes.c_int),
                 ("jam_alpha", ctypes.c_double), ("jam_iters", ctypes.c_int), ("max_restarts", ctypes.c_int),
-                ("run_Qf", ctypes.c_double * 3), ("kin_box", ctypes.c_double * 3)]
+                ("run_Qf", ctypes.c_double * 3), ("kin_box", ctypes.c_double * 3),
+                ("formulation", ctypes.c_int), ("cs", ctypes.POINTER(ctypes.c_int)), ("QX", ctypes.c_double * 12),
+                ("delta_c", ctypes.c_double)]
+
+    def set_schedule(self, cs, QX):
+        """fixed-contact-schedule formulation: cs [N-1, 4] of 0/1 (kept alive), running state weights QX [12]"""
+        self._cs = np.ascontiguousarray(cs, dtype=np.int32)
+        self.cs = self._cs.ctypes.data_as(ctypes.POINTER(ctypes.c_int))
+        self.formulation = 1
+        for i in range(12):
+            self.QX[i] = QX[i]
+        return self
 
 
 class IpResult(ctypes.Structure):
@@ -45,8 +56,8 @@ def default_options(**kw):
     o = IpOptions()
     _lib().ip_options_default(ctypes.byref(o))
     for k, v in kw.items():
-        if k in ("run_Qf", "kin_box"):
-            for i in range(3):
+        if k in ("run_Qf", "kin_box", "QX"):
+            for i in range(len(v)):
                 getattr(o, k)[i] = v[i]
         else:
             setattr(o, k, v)
@@ -71,6 +82,7 @@ def solve_cpu(N, drops, opt=None, pb=None, threads=0, fast=False):
     pb = pb or default_problem()
     x = np.zeros((B, nx))
     res = (IpResult * B)()
+    threads = min(threads or (os.cpu_count() or 1), max(B, 1))
     rc = lib.ip_solve_batch(N, B, _dp(drops), ctypes.byref(pb), ctypes.byref(opt), _dp(x), res,
                             threads or (os.cpu_count() or 1))
     assert rc == 0

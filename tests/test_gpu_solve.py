@@ -395,3 +395,50 @@ def test_library_level_multi_gpu_solve_gathers_the_whole_sweep(solver21):
     assert np.array_equal(r["status"], ref["status"]) and np.array_equal(r["iters"], ref["iters"])
     assert np.array_equal(r["x"], ref["x"]) and np.array_equal(r["f"], ref["f"])  # same kernel, same scenario: bit-equal
     assert np.array_equal(r["lam_g"], ref["lam_g"])
+
+
+def _sched_solver(N, T, z0):
+    from test_oracle_ip import _schedule_problem
+    pb, opt, cs = _schedule_problem(N, T, z0)
+    s = lc.LandingSolver(N=N)
+    lc.apply_schedule_parameters(s.problem)
+    s.problem.T = T
+    s.set_schedule(cs, lc.SCHED_QX)
+    return s, pb, opt, cs
+
+
+@pytest.mark.parametrize("iters", [1, 4])
+def test_fixed_contact_schedule_iterates_match_cpu(iters):
+    """BASELINE configs[0] formulation (quadruped_SRBM_NLP.m:84-176): same algorithm on the GPU and in the CPU
+    restatement, iterate for iterate, including the dual-regularised equality rows and the running state cost."""
+    import copy
+    N = 30
+    s, pb, opt, cs = _sched_solver(N, 0.6, 0.5)
+    drops = np.repeat(lc.single_drop(), 4, axis=0)
+    drops[1, 9] = 0.0; drops[2, 4] = 0.15; drops[3, 10] = 0.4; drops[3, 3] = -0.1
+    s.options.max_iter = iters
+    r = s.solve(drops)
+    s.close()
+    opt.max_iter = iters
+    c = solve_cpu(N, drops, opt, pb)
+    assert np.array_equal(r["iters"], c["iters"])
+    assert np.max(np.abs(r["x"] - c["x"])) < 1e-8
+    assert np.allclose(r["f"], c["f"], rtol=1e-9, atol=1e-12)
+
+
+def test_baseline_config0_fixed_contact_schedule_converges_like_cpu():
+    from test_oracle_ip import _check_schedule_solution
+    N = 30
+    s, pb, opt, cs = _sched_solver(N, 0.6, 0.5)
+    drops = np.repeat(lc.single_drop(), 3, axis=0)
+    drops[1, 9] = 0.0; drops[2, 4] = 0.1
+    r = s.solve(drops)
+    s.close()
+    c = solve_cpu(N, drops, opt, pb)
+    assert np.all(r["status"] == 0) and np.all(c["status"] == 0)
+    assert np.max(np.abs(r["f"] - c["f"])) <= 1e-5 * np.abs(c["f"]).max()
+    assert np.max(np.abs(r["x"] - c["x"])) < 1e-4
+    for b in range(3):
+        _check_schedule_solution(r["x"][b], N, cs)
+    print("config0 (fixed schedule): GPU iters %s CPU iters %s, cost %.6f, max|x_gpu - x_cpu| %.2e"
+          % (r["iters"].tolist(), c["iters"].tolist(), r["f"][0], np.max(np.abs(r["x"] - c["x"]))))

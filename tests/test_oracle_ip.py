@@ -94,3 +94,50 @@ def test_nonuniform_dt_of_the_sweep_callers():
     # restatement converges on 55-85 % of them depending on the initial guess; the rest end at a point of
     # local infeasibility (status 2) where IPOPT would enter its restoration phase
     assert (r["status"] == 0).sum() >= 3 and set(r["status"]) <= {0, 2}
+
+
+def _schedule_problem(N, T, z0):
+    import landing_controller_b200 as lc
+    from oracle_ip import default_options, default_problem
+    pb = lc.apply_schedule_parameters(default_problem())
+    pb.T = T
+    cs = lc.ballistic_schedule(N, T, z0)
+    opt = default_options(run_Qf=lc.SCHED_QF, kin_box=lc.SCHED_KIN_BOX).set_schedule(cs, lc.SCHED_QX)
+    return pb, opt, cs
+
+
+def _check_schedule_solution(x, N, cs, f_max=200.0):
+    X = x[:12 * N].reshape(N, 12)
+    U = x[12 * N:].reshape(N - 1, 24)
+    c, f = U[:, :12].reshape(N - 1, 4, 3), U[:, 12:].reshape(N - 1, 4, 3)
+    on = cs.astype(bool)
+    assert np.all(np.abs(f[~on][:, 2]) <= 1e-5)                       # f_z <= cs f_max, f_z >= 0: no force in flight
+    assert np.all(f[..., 2] >= -1e-5) and np.all(f[..., 2] <= f_max + 1e-3)
+    assert np.all(np.abs(c[on][:, 2]) <= 1e-5)                        # cs c_z = 0: stance feet are on the ground
+    stay = on[:-1]                                                   # cs (c+ - c) = 0: stance feet do not move
+    assert np.all(np.abs((c[1:] - c[:-1])[stay]) <= 1e-5)
+    assert np.all(np.abs(f[..., 0]) <= 0.71 * f[..., 2] + 1e-4) and np.all(np.abs(f[..., 1]) <= 0.71 * f[..., 2] + 1e-4)
+    return X, c, f
+
+
+def test_fixed_contact_schedule_reference_problem_and_config0():
+    """quadruped_SRBM_NLP.m: its own problem (N = 16, T = 0.5, 0.35 m, v_z = -1, two flight knots :29-33,178-180) and
+    BASELINE configs[0] (0.5 m, level, 1 m/s forward, N = 30): converge, and the solution obeys the schedule."""
+    import landing_controller_b200 as lc
+    from oracle_ip import default_options, default_problem, solve_cpu
+    N = 16
+    pb = lc.apply_schedule_parameters(default_problem(), z_max=0.4)
+    pb.T = 0.5
+    cs = lc.reference_schedule(N)
+    opt = default_options(run_Qf=lc.SCHED_QF, kin_box=lc.SCHED_KIN_BOX).set_schedule(cs, lc.SCHED_QX)
+    d = np.zeros((1, 12)); d[0, 2] = 0.35; d[0, 11] = -1.0
+    r = solve_cpu(N, d, opt, pb, threads=1)
+    assert r["status"][0] == 0 and r["iters"][0] < 40 and r["viol"][0] < 1e-3
+    X, c, f = _check_schedule_solution(r["x"][0], N, cs)
+    assert f[2:, :, 2].sum(axis=1).min() > 20 and abs(X[-1, 2] - 0.2) < 0.08   # the legs carry the body towards 0.2 m
+    N = 30
+    pb, opt, cs = _schedule_problem(N, 0.6, 0.5)
+    r = solve_cpu(N, lc.single_drop(), opt, pb, threads=1)
+    assert r["status"][0] == 0 and r["iters"][0] < 60
+    X, c, f = _check_schedule_solution(r["x"][0], N, cs)
+    assert abs(X[-1, 9]) < 0.2 and abs(X[-1, 11]) < 0.3                        # the forward and vertical speed are absorbed
