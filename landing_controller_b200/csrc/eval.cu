@@ -62,11 +62,24 @@ struct ScatterSink {  // g / jac / hess values straight into the CCS value array
   }
 };
 
-struct GradSink {  // acc[var] += lam[row] * dg_row/dvar  (J^T lam, knot-local)
+// J^T lam of one knot, dealt to NGP threads by VARIABLE: part q accumulates (and later stores) the own-knot variables
+// it owns -- the six variables (c_l, f_l) of leg q and the states X_i with i % 4 == q -- so no two threads ever touch
+// the same output, and the compile-time filter leaves each thread a quarter of the Jacobian entries and 9 accumulators
+// (one thread per knot needs 255 registers + spills and runs at 8 warps per SM).  Measured on B200 (16k scenarios, N = 30,
+// SoA): NGP = 1 0.56 ms, NGP = 4 0.84 ms -- the parts repeat the rotation / wrench sub-expressions and re-read x, which
+// costs more than the registers it frees -- so one part is the default.
+#ifndef EVAL_NP_GRAD
+#define EVAL_NP_GRAD 1
+#endif
+constexpr int NGP = EVAL_NP_GRAD;
+__device__ __forceinline__ constexpr int grad_owner(int var) {  // var: 0-11 X | 12-23 c | 24-35 f ; X+, c+: nobody
+  return var < 12 ? (var & 3) : (var < 36 ? ((var - 12) % 12) / 3 : -1);
+}
+template <int PART> struct GradSink {  // acc[var] += lam[row] * dg_row/dvar for the variables of this part
   LamRow lam;
-  double acc[60];
+  double acc[36];
   __device__ __forceinline__ void g(int, double) {}
-  __device__ __forceinline__ void j(int, int row, int var, double v) { acc[var] += lam(row) * v; }
+  __device__ __forceinline__ void j(int, int row, int var, double v) { if (var < 36 && grad_owner(var) % NGP == PART) acc[var] += lam(row) * v; }
   __device__ __forceinline__ void h(int, int, int, double) {}
 };
 
@@ -168,22 +181,64 @@ __global__ void __launch_bounds__(TPB, NP > 1 ? 3 : 1) k_eval(EvalArgs a) {
   if (bad && a.status) a.status[b] = -1;
 }
 
-// grad_gamma_x = lam_f grad f + J^T lam_g ; grad_gamma_p (nlp_grad :22015). Outputs pre-zeroed.
-__global__ void __launch_bounds__(TPB) k_grad(EvalArgs a) {
+template <int PART>
+__device__ __forceinline__ void grad_x_part(const EvalArgs& a, const Knot& kn, const LamRow& lam, int k, long long b, bool last) {
+  const int N = a.pl.N;
+  GradSink<PART> s;
+  s.lam = lam;
+#pragma unroll
+  for (int i = 0; i < 36; i++) s.acc[i] = 0.0;
+  if (last)
+    knot_eval<true, false, true, false>(kn, s, lam);
+  else
+    knot_eval<false, false, true, false>(kn, s, lam);
+  // what the previous knot (or the initial-state rows) contributes to X_k, c_k
+  if (k == 0) {
+#pragma unroll
+    for (int i = 0; i < 12; i++)
+      if (grad_owner(i) % NGP == PART) s.acc[i] += a.lam_g.get(i, b);
+  } else {
+    const int pbase = 36 + 104 * (k - 1);  // (knot k-1 is never the last knot: interior row layout)
+#pragma unroll
+    for (int i = 0; i < 12; i++)
+      if (grad_owner(i) % NGP == PART) s.acc[i] += a.lam_g.get(pbase + (i < 6 ? i : (i < 9 ? i + 3 : i - 3)), b);
+#pragma unroll
+    for (int l = 0; l < 4; l++) {
+      if (l % NGP != PART) continue;  // this part's legs
+      const double fzp = a.x.get(12 * N + 24 * (k - 1) + 12 + 3 * l + 2, b);
+      const int L = pbase + Rows<false>::leg(l);
+#pragma unroll
+      for (int i = 0; i < 3; i++) s.acc[12 + 3 * l + i] += fzp * (a.lam_g.get(L + 2 + i, b) + a.lam_g.get(L + 5 + i, b));
+    }
+  }
+#pragma unroll
+  for (int vv = 0; vv < 36; vv++)
+    if (grad_owner(vv) % NGP == PART) a.grad_x.at(global_var(N, k, vv), b) = s.acc[vv];
+}
+
+// grad_gamma_x = lam_f grad f + J^T lam_g ; grad_gamma_p (nlp_grad :22015).
+// grad_x is written by OWNER threads, no atomics and no pre-zeroing: thread (scenario, knot k) owns X_k, c_k, f_k and
+// adds to its own knot's J^T lam what knot k-1 contributes through its X+ / c+ columns -- identity entries of the
+// dynamics rows and f_z,l of knot k-1 in the no-slip rows, both in closed form (no second template evaluation).  The
+// boundary thread owns X_{N-1}.  (The former version did 48-60 RED.ADD.F64 per thread on a pre-zeroed array: 29 % of the
+// HBM bandwidth.)  grad_p is pre-zeroed; only the eight scalar parameters shared by all knots are accumulated atomically.
+__global__ void __launch_bounds__(TPB, NGP > 1 ? 3 : 1) k_grad(EvalArgs a) {
   const long long b = (long long)blockIdx.x * TPB + threadIdx.x;
   const int k = blockIdx.y, N = a.pl.N;
   if (b >= a.B) return;
   const ParamOff& o = a.pl.off;
   if (k == N - 1) {
-    const int xo = 12 * (N - 1);
+    if (blockIdx.z != 0) return;
+    const int xo = 12 * (N - 1), pb = 36 + 104 * (N - 2);  // rows of the last knot (80-row layout: dynamics first)
     const double lf = a.lam_f.get(0, b);
     for (int i = 0; i < 12; i++) {
       const double d = a.x.get(xo + i, b) - a.p.get(xo + i, b);
       const double qn = a.p.get(o.QN + i, b);
       if (a.grad_x.p) {
         const int r1 = i < 6 ? 12 + i : 24 + (i - 6);
-        atomicAdd(&a.grad_x.at(xo + i, b), lf * 2.0 * qn * d + a.lam_g.get(r1, b) + a.lam_g.get(r1 + 6, b));
-        atomicAdd(&a.grad_x.at(i, b), a.lam_g.get(i, b));
+        // X+ column of the last knot's dynamics rows: pos, rpy -> rows 0-5; omega -> rows 9-11; v -> rows 6-8
+        const int dr = i < 6 ? i : (i < 9 ? i + 3 : i - 3);
+        a.grad_x.at(xo + i, b) = lf * 2.0 * qn * d + a.lam_g.get(r1, b) + a.lam_g.get(r1 + 6, b) + a.lam_g.get(pb + dr, b);
       }
       if (a.grad_p.p) {
         a.grad_p.at(xo + i, b) = -lf * 2.0 * qn * d;
@@ -197,20 +252,14 @@ __global__ void __launch_bounds__(TPB) k_grad(EvalArgs a) {
   load_knot(a, k, b, kn, last);
   LamRow lam{a.lam_g, b, 36 + 104 * k};
   if (a.grad_x.p) {
-    GradSink s;
-    s.lam = lam;
-#pragma unroll
-    for (int i = 0; i < 60; i++) s.acc[i] = 0.0;
-    if (last)
-      knot_eval<true, false, true, false>(kn, s, lam);
-    else
-      knot_eval<false, false, true, false>(kn, s, lam);
-#pragma unroll
-    for (int vv = 0; vv < 60; vv++) {
-      if (last && vv >= 48) break;
-      atomicAdd(&a.grad_x.at(global_var(N, k, vv), b), s.acc[vv]);
+    switch (blockIdx.z) {  // (block-uniform)
+      case 0: grad_x_part<0>(a, kn, lam, k, b, last); break;
+      case 1: grad_x_part<1 % NGP>(a, kn, lam, k, b, last); break;
+      case 2: grad_x_part<2 % NGP>(a, kn, lam, k, b, last); break;
+      default: grad_x_part<3 % NGP>(a, kn, lam, k, b, last); break;
     }
   }
+  if (blockIdx.z != 0) return;
   if (a.grad_p.p) {
     // parameter sensitivities of the knot rows: dt_k, mu, mass, Ib, Ib_inv
     double sf, cf, st, ct, sp, cp;
@@ -419,9 +468,10 @@ int launch_eval(const EvalArgs& a, cudaStream_t st) {
     launches++;
   }
   if (a.grad_x.p || a.grad_p.p) {
-    if (a.grad_x.p) cudaMemsetAsync(a.grad_x.p, 0, sizeof(double) * a.pl.nx * a.B, st);
-    if (a.grad_p.p) cudaMemsetAsync(a.grad_p.p, 0, sizeof(double) * a.pl.np * a.B, st);
-    k_grad<<<grid, TPB, 0, st>>>(a);
+    if (a.grad_p.p) cudaMemsetAsync(a.grad_p.p, 0, sizeof(double) * a.pl.np * a.B, st);  // (grad_x: owner writes)
+    dim3 gg = grid;
+    gg.z = a.grad_x.p ? NGP : 1;
+    k_grad<<<gg, TPB, 0, st>>>(a);
     launches++;
   }
   return launches;

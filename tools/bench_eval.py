@@ -40,12 +40,18 @@ def measure(N=30, B=16384, reps=20, layout="soa", solver=None, device=0):
     fv, gx, gp = torch.zeros(B, dtype=torch.float64, device=dev), z(d["nx"]), z(d["np"])
     peak, peak_src = hbm_peak()
     stream = torch.cuda.ExternalStream(s.stream_ptr, device=dev)
+    # algorithmic words per scenario = what the function MUST read and write: of p only dt (N-1), mu, mass, Ib, Ib_inv
+    # enter g / J / H (+ QN, Xref_N for f and the terminal Hessian diagonal) -- SURVEY 8a; the rest of p is never read
+    pk = (N - 1) + 8
+    gf = torch.zeros(*shape(d["nx"]), dtype=torch.float64, device=dev)
     cases = {
-        "nlp_g": (dict(x=x, p=p, g=g), d["nx"] + d["np"] + d["m"]),
-        "nlp_jac_g": (dict(x=x, p=p, g=g, jac=J), d["nx"] + d["np"] + d["m"] + d["nnzJ"]),
-        "nlp_hess_l": (dict(x=x, p=p, lam_f=lam_f, lam_g=lam_g, hess=H), d["nx"] + d["np"] + 1 + d["m"] + d["nnzH"]),
+        "nlp_f": (dict(x=x, p=p, f=fv), 12 + 24 + 1),
+        "nlp_grad_f": (dict(x=x, p=p, f=fv, grad_f=gf), 12 + 24 + 1 + d["nx"]),
+        "nlp_g": (dict(x=x, p=p, g=g), d["nx"] + pk + d["m"]),
+        "nlp_jac_g": (dict(x=x, p=p, g=g, jac=J), d["nx"] + pk + d["m"] + d["nnzJ"]),
+        "nlp_hess_l": (dict(x=x, p=p, lam_f=lam_f, lam_g=lam_g, hess=H), d["nx"] + pk + 12 + 1 + d["m"] + d["nnzH"]),
         "nlp_grad": (dict(x=x, p=p, lam_f=lam_f, lam_g=lam_g, f=fv, g=g, grad_x=gx, grad_p=gp),
-                     2 * (d["nx"] + d["np"] + 1 + d["m"])),
+                     d["nx"] + pk + 36 + 1 + d["m"] + 1 + d["m"] + d["nx"] + d["np"]),
     }
     out = []
     torch.cuda.synchronize()
