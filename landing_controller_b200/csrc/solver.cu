@@ -261,6 +261,7 @@ void solver_free(SolverWorkspace& ws) {
   if (ws.scratch) cudaFree(ws.scratch);
   if (ws.io) cudaFree(ws.io);
   if (ws.counter) cudaFree(ws.counter);
+  if (ws.zeros) cudaFree(ws.zeros);
   if (ws.order) cudaFree(ws.order);
   if (ws.tab.dev) cudaFree(ws.tab.dev);
   ws = SolverWorkspace{};
@@ -293,6 +294,8 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&ws.n_sm, cudaDevAttrMultiProcessorCount, dev);
     CUS(cudaMalloc(&ws.counter, sizeof(int)));
+    CUS(cudaMalloc(&ws.zeros, sizeof(double) * 16));
+    CUS(cudaMemset(ws.zeros, 0, sizeof(double) * 16));
     CUS(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_TOTAL * sizeof(double))));
     if (const char* e = getenv("LANDING_CARVEOUT"))  // experiments: shared-memory carve-out in percent
       CUS(cudaFuncSetAttribute(k_solve, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(e)));
@@ -315,6 +318,7 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
   P.run_qx = 0;
   for (int i = 0; i < 12; i++) P.run_qx |= (pb.QX[i] != 0.0);
   P.opt.reserved[0] = pl.m;  // m, for the dual scaling s_d
+  P.zeros = ws.zeros;
   P.counter = ws.counter; P.scratch = ws.scratch; P.slot = slot; P.tab = ws.tab;
   if (memspace == LANDING_HOST) {
     size_t bytes = sizeof(double) * B * (12 + nx + 2 + (io.x0 ? nx : 0) + (io.lam_g ? m : 0)) + sizeof(int) * 2 * B + 64;

@@ -29,6 +29,7 @@ struct SolverWorkspace {
   void* io = nullptr;         // staging of drops / results for host-buffer calls
   size_t io_bytes = 0;
   int* counter = nullptr;     // work-queue head
+  double* zeros = nullptr;    // 16 zeros (c+ operand of the last knot)
   int* order = nullptr;       // work-queue order (scenario ids, longest expected first)
   size_t order_cap = 0;
   SolverTables tab;

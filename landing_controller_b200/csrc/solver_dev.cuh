@@ -54,7 +54,10 @@ constexpr int SM_RED = SM_V + V_END;           // block-reduction scratch NWARP 
 constexpr int SM_TAB = SM_RED + NWARP * 8;     // lb[140] ub[140] lbo[140] ubo[140]
 constexpr int TBL_INTS = 2688;                 // index tables of the sweeps (SolverTables::sm_src)
 constexpr int SM_TBL = SM_TAB + 4 * NROWTAB;
-constexpr int SM_TOTAL = SM_TBL + TBL_INTS / 2;
+// row-kind tables (bytes): kind of knot-local row rho for every knot class | class of every knot | boundary rows
+constexpr int KT_CLASSES = 32, KT_CLS = KT_CLASSES * RK, KT_MAXK = 1024, KT_BND = KT_CLS + KT_MAXK, KT_BYTES = KT_BND + 40;
+constexpr int SM_KT = SM_TBL + TBL_INTS / 2;
+constexpr int SM_TOTAL = SM_KT + (KT_BYTES + 7) / 8;
 static_assert(SM_MS % 2 == 0 && SM_LB0 % 2 == 0 && SM_V % 2 == 0, "16-byte alignment of the regions");
 static_assert(CTAS_PER_SM * (SM_TOTAL * 8 + 1024) <= 232448, "shared memory budget (227 KB per SM)");
 
@@ -67,6 +70,7 @@ struct KParams {
   const double* x0;
   const double* dtv;  // knot spacings dt[0..K-1] (device)
   const unsigned char* csm;  // fixed-schedule formulation: contact bit mask of every knot (device), else nullptr
+  const double* zeros;       // 16 zeros in global memory (c+ of the last knot)
   double *x_star, *f_star, *lam_g, *viol;
   int *status, *iters;
   int run_qx;  // any QX != 0
@@ -205,26 +209,40 @@ __device__ __forceinline__ int dyn_state(int rho) { return rho < 6 ? rho : (rho 
 // row kinds: hard equality (initial state, dynamics: the constraints of the Riccati recursion) | inequality with a slack
 // | free (not a constraint of this formulation / knot) | dual-regularised equality (fixed-schedule rows, ip_ref.h)
 enum { ROW_EQ = 0, ROW_INEQ = 1, ROW_FREE = 2, ROW_EQS = 3 };
-__device__ __forceinline__ int row_kind(const KParams& P, int idx) {
-  const int K = P.K;
-  if (idx < 12) return ROW_EQ;
-  const bool sched = P.pb.formulation == 1;
-  if (idx < 36) return sched ? ROW_FREE : ROW_INEQ;
-  const int k = (idx - 36) / RK, rho = (idx - 36) - k * RK;
+// kind of knot-local row rho of a knot of class cls = contact bits (15 in formulation 0) + 16 (last knot)
+__device__ __forceinline__ int row_kind_of(bool sched, int cls, int rho) {
+  const bool last = cls >= 16;
+  const unsigned cs = cls & 15;
   if (rho < 12) return ROW_EQ;
-  if (!sched) return (k == K - 1 && is_noslip(rho)) ? ROW_FREE : ROW_INEQ;
-  const unsigned cs = __ldg(P.csm + k);
+  if (!sched) return (last && is_noslip(rho)) ? ROW_FREE : ROW_INEQ;
   if (rho < 16) return (cs >> (rho - 12) & 1) ? ROW_INEQ : ROW_EQS;  // f_z in [0, cs f_max]: f_z = 0 in flight
   if (rho < 64) {
     const int l = (rho - 16) / 12, j = (rho - 16) - 12 * l;
     const bool on = cs >> l & 1;
     if (j == 0) return on ? ROW_EQS : ROW_FREE;                       // cs c_z = 0
     if (j == 1) return ROW_FREE;
-    if (j < 5) return (on && k < K - 1) ? ROW_EQS : ROW_FREE;         // cs (c+ - c) = 0
+    if (j < 5) return (on && !last) ? ROW_EQS : ROW_FREE;             // cs (c+ - c) = 0
     if (j < 8) return ROW_FREE;
     return ROW_INEQ;                                                  // kinematic box, leg length
   }
   return ROW_INEQ;
+}
+// The row passes look the kind of a row up in shared memory (one division by 104 and two byte loads) instead of
+// re-deriving it: the derivation was ~100 instructions inlined at a dozen sites, and the kernel is instruction-fetch
+// bound.
+__device__ void build_kind_tables(const KParams& P, unsigned char* kt) {
+  const bool sched = P.pb.formulation == 1;
+  for (int i = TID; i < KT_CLASSES * RK; i += NT) kt[i] = (unsigned char)row_kind_of(sched, i / RK, i % RK);
+  for (int k = TID; k < P.K; k += NT) kt[KT_CLS + k] = (unsigned char)((sched ? __ldg(P.csm + k) & 15 : 15) + (k == P.K - 1 ? 16 : 0));
+  if (TID < 36) kt[KT_BND + TID] = (unsigned char)(TID < 12 ? ROW_EQ : (sched ? ROW_FREE : ROW_INEQ));
+}
+__device__ __forceinline__ const unsigned char* kind_tables(const double* tab) {  // tab = smem + SM_TAB
+  return reinterpret_cast<const unsigned char*>(tab + (SM_KT - SM_TAB));
+}
+__device__ __forceinline__ int row_kind(const unsigned char* kt, int idx) {
+  if (idx < 36) return kt[KT_BND + idx];
+  const int k = (idx - 36) / RK, rho = (idx - 36) - k * RK;
+  return kt[kt[KT_CLS + k] * RK + rho];
 }
 __device__ __forceinline__ int row_tab(int idx) { return idx < 36 ? idx : 36 + (idx - 36) % RK; }
 
@@ -233,17 +251,13 @@ template <bool LAST> struct LamY {
   __device__ __forceinline__ double operator()(int r) const { return y[rowmap<LAST>(r)]; }
 };
 
-__device__ __forceinline__ void load_knot(const KParams& P, const double* x, int k, Knot& kn) {
+__device__ __forceinline__ void load_knot(const KParams& P, const double* x, const double* zeros, int k, KnotRef& kn) {
   const int N = P.N;
-  const bool last = (k == N - 2);
-#pragma unroll
-  for (int i = 0; i < 12; i++) {
-    kn.X[i] = x[12 * k + i];
-    kn.Xn[i] = x[12 * (k + 1) + i];
-    kn.c[i] = x[12 * N + 24 * k + i];
-    kn.f[i] = x[12 * N + 24 * k + 12 + i];
-    kn.cn[i] = last ? 0.0 : x[12 * N + 24 * (k + 1) + i];
-  }
+  kn.X = x + 12 * k;
+  kn.Xn = x + 12 * (k + 1);
+  kn.c = x + 12 * N + 24 * k;
+  kn.f = kn.c + 12;
+  kn.cn = (k == N - 2) ? zeros : kn.c + 24;  // (the last knot has no c+: its no-slip rows are unused)
   kn.h = __ldg(P.dtv + k);
   if (P.csm) {
     const unsigned cs = __ldg(P.csm + k);
@@ -290,34 +304,34 @@ template <int PART> struct GSinkP {
 template <int PART>
 __device__ __noinline__ void eval_knot_j(const KParams& P, const Ws& w, const double* x, double* gout, int k0, int kstep) {
   for (int k = k0; k < P.K; k += kstep) {
-    Knot kn;
-    load_knot(P, x, k, kn);
+    KnotRef kn;
+    load_knot(P, x, P.zeros, k, kn);
     NoLam nl;
     JSinkP<PART> s{gout + 36 + RK * k, w.JL + (long long)k * NJ_PAD};
-    if (P.pb.formulation == 1) knot_eval<false, true, true, false, JSinkP<PART>, NoLam, true>(kn, s, nl);
-    else knot_eval<false, true, true, false>(kn, s, nl);
+    if (P.pb.formulation == 1) knot_eval<false, true, true, false, JSinkP<PART>, NoLam, true, KnotRef>(kn, s, nl);
+    else knot_eval<false, true, true, false, JSinkP<PART>, NoLam, false, KnotRef>(kn, s, nl);
   }
 }
 template <int PART>
 __device__ __noinline__ void eval_knot_h(const KParams& P, const Ws& w, const double* x, int k0, int kstep) {
   for (int k = k0; k < P.K; k += kstep) {
-    Knot kn;
-    load_knot(P, x, k, kn);
+    KnotRef kn;
+    load_knot(P, x, P.zeros, k, kn);
     HSinkP<PART> s{w.HL + (long long)k * NH_PAD};
     LamY<false> lam{w.Y + 36 + RK * k};
-    if (P.pb.formulation == 1) knot_eval<false, false, false, true, HSinkP<PART>, LamY<false>, true>(kn, s, lam);
-    else knot_eval<false, false, false, true>(kn, s, lam);
+    if (P.pb.formulation == 1) knot_eval<false, false, false, true, HSinkP<PART>, LamY<false>, true, KnotRef>(kn, s, lam);
+    else knot_eval<false, false, false, true, HSinkP<PART>, LamY<false>, false, KnotRef>(kn, s, lam);
   }
 }
 template <int PART>
 __device__ __noinline__ void eval_knot_g(const KParams& P, const double* x, double* gout, int k0, int kstep) {
   for (int k = k0; k < P.K; k += kstep) {
-    Knot kn;
-    load_knot(P, x, k, kn);
+    KnotRef kn;
+    load_knot(P, x, P.zeros, k, kn);
     NoLam nl;
     GSinkP<PART> s{gout + 36 + RK * k};
-    if (P.pb.formulation == 1) knot_eval<false, true, false, false, GSinkP<PART>, NoLam, true>(kn, s, nl);
-    else knot_eval<false, true, false, false>(kn, s, nl);
+    if (P.pb.formulation == 1) knot_eval<false, true, false, false, GSinkP<PART>, NoLam, true, KnotRef>(kn, s, nl);
+    else knot_eval<false, true, false, false, GSinkP<PART>, NoLam, false, KnotRef>(kn, s, nl);
   }
 }
 
@@ -514,6 +528,7 @@ __device__ __forceinline__ void row_step_sm(const bool MERIT, const Ws& w, int i
 // shared memory through a 4-buffer cp.async ring, so no thread waits on a chain of dependent L2 round trips.
 __device__ __noinline__ void row_steps(const bool MERIT, const KParams& P, const Ws& w, double* smem, const double* tab, const double* drop,
                                        double* red, double mu, double tau, StepInfo& si) {
+  const unsigned char* kt = kind_tables(tab);
   const int N = P.N, K = P.K, tid = TID, half = tid >> 7, t = tid & 127;
   const int* t_rptr = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_rptr;
   const int* t_rterms = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_rterms;
@@ -544,7 +559,7 @@ __device__ __noinline__ void row_steps(const bool MERIT, const KParams& P, const
     if (k < K && t < RK) {
       const double* rb = ring(k);
       const int rho = t, idx = 36 + RK * k + rho;
-      const int kind = row_kind(P, idx);
+      const int kind = kt[kt[KT_CLS + k] * RK + rho];
       if (kind == ROW_EQ) {
         si.theta += fabs(rb[RB_G + rho]);
       } else if (kind != ROW_FREE) {
@@ -588,6 +603,7 @@ constexpr int RU = 4;
 
 __device__ __noinline__ void merit_trial(const KParams& P, const Ws& w, const double* tab, const double* drop,
                                             double* red, double alpha, double mu, double& phi_bar, double& theta) {
+  const unsigned char* kt = kind_tables(tab);
   const int K = P.K, MR = P.MR;
   const double* __restrict__ GT = w.GT;
   const double* __restrict__ S = w.S;
@@ -605,7 +621,7 @@ __device__ __noinline__ void merit_trial(const KParams& P, const Ws& w, const do
     for (int u = 0; u < RU; u++) {
       const int idx = base + u * NT;
       if (idx >= MR) break;
-      const int kind = row_kind(P, idx);
+      const int kind = row_kind(kt, idx);
       if (kind == ROW_FREE) continue;
       if (kind == ROW_EQ || kind == ROW_EQS) {
         th += fabs(gt[u] - (idx < 12 ? drop[idx] : 0.0));
@@ -633,6 +649,7 @@ struct Errs {
 // sigma per row and the pieces of the optimality error (oracle/ip_ref.c: assemble)
 __device__ __noinline__ void row_errors(const KParams& P, const Ws& w, const double* tab, const double* drop,
                                            double* red, double mu, Errs& e) {
+  const unsigned char* kt = kind_tables(tab);
   const int K = P.K, MR = P.MR;
   const double* __restrict__ G = w.G;
   const double* __restrict__ Y = w.Y;
@@ -654,7 +671,7 @@ __device__ __noinline__ void row_errors(const KParams& P, const Ws& w, const dou
     for (int u = 0; u < RU; u++) {
       const int idx = base + u * NT;
       if (idx >= MR) break;
-      const int kind = row_kind(P, idx);
+      const int kind = row_kind(kt, idx);
       if (kind == ROW_FREE) continue;
       const double g = gv[u], y = yv[u];
       ys += fabs(y);
@@ -700,10 +717,11 @@ __device__ __noinline__ void row_errors(const KParams& P, const Ws& w, const dou
 }
 
 __device__ __noinline__ double compl_at(const KParams& P, const Ws& w, const double* tab, double* red, double mu) {
+  const unsigned char* kt = kind_tables(tab);
   const int K = P.K, MR = P.MR;
   double cmu = 0;
   for (int idx = TID; idx < MR; idx += NT) {
-    if (row_kind(P, idx) != ROW_INEQ) continue;
+    if (row_kind(kt, idx) != ROW_INEQ) continue;
     const int t = row_tab(idx);
     const double lb = tab[t], ub = tab[NROWTAB + t], s = w.S[idx];
     if (isfinite(lb)) cmu = fmax(cmu, fabs(w.ZL[idx] * (s - lb) - mu));
@@ -714,6 +732,7 @@ __device__ __noinline__ double compl_at(const KParams& P, const Ws& w, const dou
 
 // yhat = sigma (g - s) - mu/(s-lb) + mu/(ub-s)
 __device__ __noinline__ void row_yhat(const KParams& P, const Ws& w, const double* tab, double mu) {
+  const unsigned char* kt = kind_tables(tab);
   const int K = P.K, MR = P.MR;
   const double* __restrict__ G = w.G;
   const double* __restrict__ S = w.S;
@@ -731,7 +750,7 @@ __device__ __noinline__ void row_yhat(const KParams& P, const Ws& w, const doubl
     for (int u = 0; u < RU; u++) {
       const int idx = base + u * NT;
       if (idx >= MR) break;
-      const int kind = row_kind(P, idx);
+      const int kind = row_kind(kt, idx);
       if (kind == ROW_EQS) { YH[idx] = w.Y[idx] + sg[u] * gv[u]; continue; }  // yhat = y + sigma c
       if (kind != ROW_INEQ) { YH[idx] = 0.0; continue; }
       const int t = row_tab(idx);
@@ -805,11 +824,12 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
 
 // slacks pushed inside their bounds at the current g; mu-based bound multipliers (ip_ref.c: init_slacks)
 __device__ __noinline__ void init_slacks(const KParams& P, const Ws& w, const double* tab, double mu) {
+  const unsigned char* kt = kind_tables(tab);
   const int K = P.K, MR = P.MR;
   const double bp = P.opt.bound_push, bf = P.opt.bound_frac;
   for (int idx = TID; idx < MR; idx += NT) {
     w.Y[idx] = 0.0; w.ZL[idx] = 0.0; w.ZU[idx] = 0.0; w.S[idx] = 0.0;
-    if (row_kind(P, idx) != ROW_INEQ) continue;
+    if (row_kind(kt, idx) != ROW_INEQ) continue;
     const int t = row_tab(idx);
     const double l = tab[t], u = tab[NROWTAB + t];
     double sv = w.G[idx];
@@ -885,6 +905,7 @@ __device__ void solve_one(const KParams& P, Ws& w, double* smem, long long b) {
   const double kappa_sigma = 1e10, s_max = 100.0;
   const double* drop = P.drops + 12 * b;
   const double* tab = smem + SM_TAB;
+  const unsigned char* kt = kind_tables(tab);
   double* red = smem + SM_RED;
 
   // initial guess: user x0 or the reference's [Xref(:); Uref(:)] (generate_landingCtrller_IPOPT.m:199-208,336)
@@ -1094,7 +1115,7 @@ __device__ void solve_one(const KParams& P, Ws& w, double* smem, long long b) {
         for (int u = 0; u < RU; u++) {
           const int idx = base + u * NT;
           if (idx >= MR) break;
-          const int kind = row_kind(P, idx);
+          const int kind = row_kind(kt, idx);
           if (kind == ROW_FREE) continue;
           Yp[idx] = yv[u] + alpha * (yn[u] - yv[u]);
           if (kind != ROW_INEQ) continue;
@@ -1162,6 +1183,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_solve(const __grid_constant
   __syncthreads();
   const KParams& P = sP;
   build_tables(P, smem + SM_TAB);
+  build_kind_tables(P, reinterpret_cast<unsigned char*>(smem + SM_KT));
   {
     int* tbl = reinterpret_cast<int*>(smem + SM_TBL);
     for (int i = TID; i < P.tab.sm_count; i += NT) tbl[i] = __ldg(P.tab.sm_src + i);

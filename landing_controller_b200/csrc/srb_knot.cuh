@@ -90,8 +90,15 @@ SRB_HD void zcross(const double v[3], double o[3]) {  // z_hat x v
 // SCHED: the fixed-contact-schedule formulation (quadruped_SRBM_NLP.m:145-158) in the same row layout: row leg+0 is
 // cs c_z (an equality), rows leg+2..4 are cs (c+ - c) (equalities, linear), rows leg+1 and leg+5..7 are unused (zero);
 // the f_z rows 12..15 are unchanged (their bound becomes cs f_max).
-template <bool LAST, bool WG, bool WJ, bool WH, class Sink, class Lam, bool SCHED = false>
-SRB_HD void knot_eval(const Knot& kn, Sink& out, const Lam& lam) {
+// KN: Knot (values; the batched kernels gather them from strided views) or KnotRef (pointers into one scenario's x;
+// the solver kernel -- no copy of the 60 values through a local struct).
+struct KnotRef {
+  const double *X, *c, *f, *Xn, *cn;
+  double h, mu, mass, Ib[3], Ibinv[3];
+  double csv[4];
+};
+template <bool LAST, bool WG, bool WJ, bool WH, class Sink, class Lam, bool SCHED = false, class KN = Knot>
+SRB_HD void knot_eval(const KN& kn, Sink& out, const Lam& lam) {
   using RW = Rows<LAST>;
   const double h = kn.h, mu = kn.mu;
   const double* r = kn.X;
