@@ -599,7 +599,10 @@ __device__ __noinline__ void row_steps(const bool MERIT, const KParams& P, const
 // Row passes over the 104 K + 36 rows of the iterate: one row per thread and round.  The rows of RU consecutive rounds
 // are LOADED FIRST and then processed (the arrays live in the L2-resident scratch: one exposed round trip per RU rounds
 // instead of one per round; with 8 warps per scenario nothing else hides that latency).
-constexpr int RU = 4;
+#ifndef SRB_RU
+#define SRB_RU 4
+#endif
+constexpr int RU = SRB_RU;
 
 __device__ __noinline__ void merit_trial(const KParams& P, const Ws& w, const double* tab, const double* drop,
                                             double* red, double alpha, double mu, double& phi_bar, double& theta) {

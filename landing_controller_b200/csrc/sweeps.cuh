@@ -219,8 +219,6 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
     Wm[tid * LDC + tid] = 1.0;  // E: c+ (stage variable 12 + j) is component 12 + j of the next stage's state
   }
   __syncthreads();
-  for (int i = tid; i < 288; i += NT) w.PX[(long long)K * 288 + i] = Pn[(i / 24) * LDP + (i % 24)];
-  if (tid < NS) w.PV[K * 24 + tid] = V[V_PN + tid];
 
   Prof pf{P.prof, 0};
   pf.start();
@@ -231,6 +229,9 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
     __syncthreads();  // condensed data of stage k is in shared memory; P_{k+1}, p_{k+1} complete; panel buffer free
     pf.lap(PH_B_WAIT);
     if (k > 0) prefetch_ct(w, k - 1, smem + SM_LB0 + ((k - 1) & 1) * CT_STRIDE);
+    // rows X of P_{k+1} and p_{k+1} for the costates (one compact loop here instead of scattered stores from the tiles)
+    for (int i = tid; i < 288; i += NT) ST_STREAM(&w.PX[(long long)(k + 1) * 288 + i], Pn[(i / 24) * LDP + (i % 24)]);
+    if (tid >= 128 && tid < 128 + NS) w.PV[(k + 1) * 24 + tid - 128] = V[V_PN + tid - 128];
     // S1. condensed sums (+ delta_w on the (f, X, c) diagonal, dummy c+ of the last stage), G^, defects r
 #pragma unroll
     for (int rnd = 0; rnd < 2; rnd++) {
@@ -262,7 +263,7 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
         mk[q] = tile < 18 ? w_mask(oJ[q]) : 0u;
         c2[q][0] = 0.0; c2[q][1] = 0.0;
       }
-#pragma unroll
+#pragma unroll 1  // (rolled: the stage loop must stay small, the kernel is instruction-fetch bound)
       for (int s2 = 0; s2 < 6; s2++)
 #pragma unroll
         for (int q = 0; q < 3; q++)
@@ -304,7 +305,7 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
         else if (isrow && g == 0) m2 = *reinterpret_cast<const double2*>(cb + CT_Q + 8 * J + 2 * t);
         c[q][0] = m2.x; c[q][1] = m2.y;
       }
-#pragma unroll
+#pragma unroll 1
       for (int s2 = 0; s2 < 6; s2++)
 #pragma unroll
         for (int q = 0; q < 4; q++)
@@ -413,12 +414,9 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
           if (col <= row) {
             Pn[row * LDP + col] = v;
             Pn[col * LDP + row] = v;
-            if (row < 12) ST_STREAM(&w.PX[(long long)k * 288 + row * NS + col], v);
-            if (col < 12) ST_STREAM(&w.PX[(long long)k * 288 + col * NS + row], v);
           }
         } else if (g == 0) {
           V[V_PN + col] = v;
-          w.PV[k * 24 + col] = v;
         }
       }
     }
@@ -558,13 +556,26 @@ __device__ __noinline__ void forward_sweep(const KParams& P, const Ws& w, double
     __syncthreads();
     pf.lap(PH_F_RHS);
     if (warp == 0) {
-      // u = L^-T rhs (diagonal of Ls holds 1/l_ii)
+      // u = L^-T rhs (diagonal of Ls holds 1/l_ii), four unknowns per round: their right-hand sides are gathered into
+      // every lane (four independent shuffles), the 4 x 4 triangle is solved redundantly in registers (a chain of
+      // eight dependent FP64 operations instead of four shuffle round trips) and every lane above applies the four
+      // columns to its own entry.  6 rounds of ~150 cycles instead of 24 steps of ~90.
       double my = lane < NS ? rhs[lane] : 0.0;
-#pragma unroll  // (rolled, the loads of L sit on the dependent chain: +15 % per iteration)
-      for (int i = NS - 1; i >= 0; i--) {
-        const double ui = __shfl_sync(FULL, my * Ls[i * NS + i], i);
-        if (lane == i) my = ui;
-        else if (lane < i) my -= Ls[i * NS + lane] * ui;
+#pragma unroll 1
+      for (int i0 = NS - 4; i0 >= 0; i0 -= 4) {
+        const double* Lb = Ls + i0 * NS + i0;  // the 4 x 4 diagonal block (lower part used)
+        const double r0 = __shfl_sync(FULL, my, i0), r1 = __shfl_sync(FULL, my, i0 + 1),
+                     r2 = __shfl_sync(FULL, my, i0 + 2), r3 = __shfl_sync(FULL, my, i0 + 3);
+        // this lane's column entries of the four rows (lanes below the block), loaded before the chain needs them
+        const bool below = lane < i0;
+        const int lc = below ? lane : 0;
+        const double c0 = Ls[i0 * NS + lc], c1 = Ls[(i0 + 1) * NS + lc], c2 = Ls[(i0 + 2) * NS + lc], c3 = Ls[(i0 + 3) * NS + lc];
+        const double u3 = r3 * Lb[3 * NS + 3];
+        const double u2 = (r2 - Lb[3 * NS + 2] * u3) * Lb[2 * NS + 2];
+        const double u1 = (r1 - Lb[3 * NS + 1] * u3 - Lb[2 * NS + 1] * u2) * Lb[NS + 1];
+        const double u0 = (r0 - Lb[3 * NS] * u3 - Lb[2 * NS] * u2 - Lb[NS] * u1) * Lb[0];
+        if (below) my -= (c0 * u0 + c1 * u1) + (c2 * u2 + c3 * u3);
+        else if (lane < i0 + 4) my = lane == i0 ? u0 : (lane == i0 + 1 ? u1 : (lane == i0 + 2 ? u2 : u3));
       }
       if (lane < NS) u[lane] = my;
       if (lane < 12) w.dx[12 * N + 24 * k + 12 + lane] = my;
