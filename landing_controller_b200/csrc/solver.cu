@@ -41,7 +41,7 @@ namespace {
 // ---------------------------------------------------------------- host: tables
 struct HostTables {
   std::vector<int> all;
-  size_t o_jl, o_hl, o_rptr, o_rterms, o_cptr, o_cterms, o_sm;
+  size_t o_jl, o_hl, o_rptr, o_rterms, o_cptr, o_cterms, o_sm, o_tinit;
   std::vector<int> sm;  // shared-memory tables
   int o_g, n_g, o_qptr, o_qterms, o_uabh, o_uptr, o_uterms, n_u, s_rptr, s_rterms, s_cptr, s_cterms;
 };
@@ -126,6 +126,26 @@ HostTables build_tables_host() {
     uptr.push_back((int)uterms.size());
   }
   T.n_u = (int)uabh.size();
+  {
+    // inverse of the target list for the accumulator tiles of the factorisation (sweeps.cuh: backward_stages, S3)
+    std::map<int, int> pos;
+    for (int i = 0; i < (int)uabh.size(); i++) pos[uabh[i] & 4095] = i;
+    std::vector<int> tinit(NTILE * 32);
+    for (int tile = 0; tile < NTILE; tile++)
+      for (int lane = 0; lane < 32; lane++) {
+        const int I = tile_I(tile), J = tile_J(tile), g = lane >> 2, t = lane & 3;
+        unsigned word = 0;
+        for (int e = 0; e < 2; e++) {
+          const int row = 8 * I + g, col = 8 * J + 2 * t + e;
+          unsigned idx = 0xffffu;
+          if (I == 6) { if (g == 0) idx = (unsigned)(CT_Q + col); }
+          else if (col <= row && pos.count(row * NW + col)) idx = (unsigned)pos[row * NW + col];
+          word |= idx << (16 * e);
+        }
+        tinit[tile * 32 + lane] = (int)word;
+      }
+    T.o_tinit = push(tinit);
+  }
   T.o_uabh = pushs(uabh);
   T.o_uptr = pushs(uptr);
   T.o_uterms = pushs(uterms);
@@ -263,6 +283,7 @@ void solver_free(SolverWorkspace& ws) {
   if (ws.counter) cudaFree(ws.counter);
   if (ws.zeros) cudaFree(ws.zeros);
   if (ws.order) cudaFree(ws.order);
+  if (ws.kt) cudaFree(ws.kt);
   if (ws.tab.dev) cudaFree(ws.tab.dev);
   ws = SolverWorkspace{};
 }
@@ -286,6 +307,7 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
     ws.tab.r_ptr = d + T.o_rptr; ws.tab.r_terms = d + T.o_rterms;
     ws.tab.c_ptr = d + T.o_cptr; ws.tab.c_terms = d + T.o_cterms;
     ws.tab.sm_src = d + T.o_sm; ws.tab.sm_count = (int)T.sm.size();
+    ws.tab.tinit = d + T.o_tinit;
     if (ws.tab.sm_count > TBL_INTS) { *err = "landing_solve_batch: shared-memory tables exceed their region"; return LANDING_ERR_ARG; }
     ws.tab.o_g = T.o_g; ws.tab.n_g = T.n_g; ws.tab.o_qptr = T.o_qptr; ws.tab.o_qterms = T.o_qterms;
     ws.tab.o_uabh = T.o_uabh; ws.tab.o_uptr = T.o_uptr; ws.tab.o_uterms = T.o_uterms; ws.tab.n_u = T.n_u;
@@ -294,6 +316,7 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&ws.n_sm, cudaDevAttrMultiProcessorCount, dev);
     CUS(cudaMalloc(&ws.counter, sizeof(int)));
+    CUS(cudaMalloc(&ws.kt, KT_BYTES));
     CUS(cudaMalloc(&ws.zeros, sizeof(double) * 16));
     CUS(cudaMemset(ws.zeros, 0, sizeof(double) * 16));
     CUS(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(SM_TOTAL * sizeof(double))));
@@ -319,7 +342,7 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
   for (int i = 0; i < 12; i++) P.run_qx |= (pb.QX[i] != 0.0);
   P.opt.reserved[0] = pl.m;  // m, for the dual scaling s_d
   P.zeros = ws.zeros;
-  P.counter = ws.counter; P.scratch = ws.scratch; P.slot = slot; P.tab = ws.tab;
+  P.counter = ws.counter; P.scratch = ws.scratch; P.slot = slot; P.tab = ws.tab; P.kt = ws.kt;
   if (memspace == LANDING_HOST) {
     size_t bytes = sizeof(double) * B * (12 + nx + 2 + (io.x0 ? nx : 0) + (io.lam_g ? m : 0)) + sizeof(int) * 2 * B + 64;
     if (bytes > ws.io_bytes) {
@@ -376,8 +399,9 @@ int solver_run(SolverWorkspace& ws, const DevicePlan& pl, long long B, int memsp
   long long gcap = nslots;
   if (const char* e = getenv("LANDING_GRID")) gcap = std::max(1LL, std::min<long long>(nslots, atoll(e)));  // experiments
   const int grid = (int)std::min<long long>(gcap, B);
+  k_kinds<<<1, 256, 0, st>>>(P);
   k_solve<<<grid, NT, SM_TOTAL * sizeof(double), st>>>(P);
-  *launches += 1;
+  *launches += 2;
   CUS(cudaGetLastError());
   if (want_prof) {
     unsigned long long h[PH_COUNT];

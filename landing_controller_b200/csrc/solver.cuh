@@ -13,6 +13,9 @@ struct SolverTables {
   const int *jl_last, *hl_last;            // emission index of the last-knot template -> interior index
   const int *r_ptr, *r_terms;              // per inequality row rho: sum J_e dw[idx]
   const int *c_ptr, *c_terms;              // per local variable (60): sum J_e y_rho  (grad of the Lagrangian)
+  // accumulator-tile initialisation of the stage factorisation: for tile (27) x lane (32), the positions of the lane's
+  // two entries in the condensed stage data (low / high 16 bits; 0xffff = structurally zero)
+  const int *tinit;
   // tables the sweeps keep in SHARED memory (copied once per CTA): offsets into sm_src[0..sm_count)
   const int *sm_src; int sm_count;
   int o_g, n_g;          // dynamics entries: e | (state*36 + var) << 10   -> G
@@ -31,6 +34,7 @@ struct SolverWorkspace {
   int* counter = nullptr;     // work-queue head
   double* zeros = nullptr;    // 16 zeros (c+ operand of the last knot)
   int* order = nullptr;       // work-queue order (scenario ids, longest expected first)
+  unsigned char* kt = nullptr;  // row-kind tables (k_kinds)
   size_t order_cap = 0;
   SolverTables tab;
   int n_sm = 0;

@@ -20,10 +20,18 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 #define TID ((int)threadIdx.x)
-constexpr int NT = 256;          // threads per CTA (= per scenario)
+// Threads per CTA (= per scenario) and CTAs per SM are build-time choices (make EXTRA="-DSRB_NT=.. -DSRB_CTAS=.."):
+// the solve of ONE scenario is a chain of short dependent phases (24 pivots per stage, K stages per sweep), so what fills
+// an SM is the number of INDEPENDENT scenarios resident on it, not the number of threads of one scenario.  Shared memory
+// per CTA (below) and the register file bound the choice: 256 x 2, 128 x 4 or 64 x 5 (threads x CTAs per SM).
+#ifndef SRB_NT
+#define SRB_NT 256
+#endif
+constexpr int NT = SRB_NT;       // threads per CTA (= per scenario)
 constexpr int NWARP = NT / 32;
+static_assert(NT == 64 || NT == 128 || NT == 256, "threads per scenario");
 #ifndef SRB_CTAS
-#define SRB_CTAS 2
+#define SRB_CTAS (SRB_NT == 256 ? 2 : (SRB_NT == 128 ? 4 : 5))
 #endif
 constexpr int CTAS_PER_SM = SRB_CTAS;
 constexpr int NS = 24;           // stage state / control size
@@ -37,29 +45,37 @@ constexpr int NJ_PAD = 388, NH_PAD = 192;  // strides of the per-knot entry list
 // condensed stage data: 278 target sums | 48 stage-gradient entries | 137 G values | 12 dynamics defects
 constexpr int CT_Q = 280, CT_G = 328, CT_R = 468, CT_STRIDE = 480;
 
-// ---- shared memory carve-up (doubles) per CTA
-constexpr int SM_M = 0;                        // 48 x 52 condensed stage matrix Mc (lower triangle, elimination order)
-constexpr int SM_P = SM_M + NW * LDC;          // 24 x 28   P_{k+1} (full, symmetric)
+// ---- shared memory carve-up (doubles) per CTA.  The condensed stage matrix itself never sits in shared memory: the
+// accumulator tiles of the factorisation are initialised straight from the condensed sums through a host-made inverse
+// table (SolverTables::tinit), and the panel buffer shares its region with T (dead once the tiles are formed).
+constexpr int SM_P = 0;                        // 24 x 28   P_{k+1} (full, symmetric)
 constexpr int SM_W = SM_P + NS * LDP;          // 24 x 52   W = [G^ ; E]: next stage state = W (stage variables)
 constexpr int SM_T = SM_W + NS * LDC;          // 24 x 52   T = P W
-constexpr int SM_MS = SM_T + NS * LDC;         // 49 x 28   panel buffer: L | Yt | yv of the stage being factored
-constexpr int SM_G = SM_W;                     // (forward sweep: second factor buffer)
+constexpr int SM_MS = SM_T;                    // 50 x 28   panel buffer: L | Yt | yv of the stage being factored (aliases T)
+constexpr int SM_SWEEP_END = SM_MS + 50 * LDMS;  // (49 rows + a zero row)
+constexpr int SM_SWEEP = SM_SWEEP_END - SM_P;  // doubles of the sweep regions (ring buffers of the row passes alias them)
 // stage list buffers (double-buffered, filled by cp.async): J | H | sigma | yhat | dynamics defects
 constexpr int LB_J = 0, LB_H = 388, LB_SIG = 580, LB_YH = 684, LB_GD = 788, LB_SIZE = 800;
-constexpr int SM_LB0 = SM_MS + 49 * LDMS;
+constexpr int SM_LB0 = SM_SWEEP_END;
 constexpr int LB_REGION = 2 * CT_STRIDE;       // two condensed-stage buffers (backward) / one list buffer (pre-pass)
 constexpr int SM_V = SM_LB0 + LB_REGION;       // vectors
 constexpr int V_Q = 0, V_Z = 48, V_R = 96, V_T = 108, V_YV = 132, V_PN = 156, V_XI = 180, V_U = 204, V_END = 228;  // V_Z: 24 zeros
-constexpr int SM_RED = SM_V + V_END;           // block-reduction scratch NWARP x 8
-constexpr int SM_TAB = SM_RED + NWARP * 8;     // lb[140] ub[140] lbo[140] ubo[140]
+constexpr int SM_RED = SM_V + V_END;           // block-reduction scratch 8 x 8
+constexpr int SM_TAB = SM_RED + 8 * 8;         // lb[140] ub[140] lbo[140] ubo[140]
 constexpr int TBL_INTS = 2688;                 // index tables of the sweeps (SolverTables::sm_src)
+// the index tables live in shared memory (one copy per CTA) when the CTA is large enough to afford it, else they are read
+// from global memory through the L1 (one copy per SM in effect)
+#ifndef SRB_TBL_SMEM
+#define SRB_TBL_SMEM (SRB_NT >= 128)
+#endif
+constexpr bool TBL_SMEM = SRB_TBL_SMEM;
 constexpr int SM_TBL = SM_TAB + 4 * NROWTAB;
-// row-kind tables (bytes): kind of knot-local row rho for every knot class | class of every knot | boundary rows
+constexpr int SM_TOTAL = SM_TBL + (TBL_SMEM ? TBL_INTS / 2 : 0);
+// row-kind tables (bytes, GLOBAL memory, built once per launch by k_kinds): kind of knot-local row rho for every knot
+// class | class of every knot | boundary rows
 constexpr int KT_CLASSES = 32, KT_CLS = KT_CLASSES * RK, KT_MAXK = 1024, KT_BND = KT_CLS + KT_MAXK, KT_BYTES = KT_BND + 40;
-constexpr int SM_KT = SM_TBL + TBL_INTS / 2;
-constexpr int SM_TOTAL = SM_KT + (KT_BYTES + 7) / 8;
-static_assert(SM_MS % 2 == 0 && SM_LB0 % 2 == 0 && SM_V % 2 == 0, "16-byte alignment of the regions");
-static_assert(CTAS_PER_SM * (SM_TOTAL * 8 + 1024) <= 232448, "shared memory budget (227 KB per SM)");
+static_assert(SM_W % 2 == 0 && SM_T % 2 == 0 && SM_LB0 % 2 == 0 && SM_V % 2 == 0, "16-byte alignment of the regions");
+static_assert(CTAS_PER_SM * (SM_TOTAL * 8 + 2048 + 1024) <= 232448, "shared memory budget (227 KB per SM)");
 
 struct KParams {
   int N, K, nx, MR;
@@ -80,6 +96,7 @@ struct KParams {
   SolverTables tab;
   unsigned long long* prof;  // optional per-phase cycle counters (LANDING_PROF=1), else nullptr
   const int* order;          // queue position -> scenario id (nullptr: input order)
+  unsigned char* kt;         // row-kind tables (KT_BYTES, global memory; filled by k_kinds before k_solve)
 };
 
 // phase ids of the optional cycle profile
@@ -156,31 +173,32 @@ __device__ __forceinline__ double block_reduce1(double* red, double v) {
   __syncthreads();
   return a;
 }
-// Reduces sizeof...(OPS) <= 8 quantities over the CTA: the values are transposed through the (idle) stage-matrix region
-// of shared memory and WARP q reduces quantity q, so the code is one short loop instead of NQ unrolled shuffle
+// Reduces sizeof...(OPS) <= 8 quantities over the CTA: the values are transposed through the (idle) sweep regions of
+// shared memory and warp q (mod NWARP) reduces quantity q, so the code is one short loop instead of NQ unrolled shuffle
 // trees (1.2k instructions for eight quantities; the kernel is instruction-fetch bound).
 // Every thread returns with the identical results in v[].  `red` = smem + SM_RED.
 template <int... OPS>
 __device__ __forceinline__ void block_reduce(double* red, double (&v)[sizeof...(OPS)]) {
   constexpr int NQ = sizeof...(OPS);
-  static_assert(NQ <= NWARP && NQ * NT <= NW * LDC, "one warp per quantity; the transpose buffer aliases the stage matrix");
-  double* buf = red - SM_RED + SM_M;
+  static_assert(NQ <= 8 && NQ * NT <= SM_SWEEP, "the transpose buffer aliases the sweep regions");
+  double* buf = red - SM_RED + SM_P;
   const int tid = TID, lane = tid & 31, warp = tid >> 5;
 #pragma unroll
   for (int q = 0; q < NQ; q++) buf[q * NT + tid] = v[q];
   __syncthreads();
-  if (warp < NQ) {
-    constexpr int ops[NQ] = {OPS...};
+  constexpr int ops[NQ] = {OPS...};
+#pragma unroll 1
+  for (int q = warp; q < NQ; q += NWARP) {
     int op = ops[0];
 #pragma unroll
-    for (int q = 1; q < NQ; q++) op = (warp == q) ? ops[q] : op;
-    const double* b = buf + warp * NT + lane;
+    for (int j = 1; j < NQ; j++) op = (q == j) ? ops[j] : op;
+    const double* b = buf + q * NT + lane;
     double a = b[0];
 #pragma unroll
     for (int j = 1; j < NT / 32; j++) a = rcomb(op, a, b[32 * j]);
 #pragma unroll 1
     for (int o = 16; o; o >>= 1) a = rcomb(op, a, __shfl_xor_sync(FULL, a, o));
-    if (lane == 0) red[warp] = a;
+    if (lane == 0) red[q] = a;
   }
   __syncthreads();
 #pragma unroll
@@ -227,17 +245,15 @@ __device__ __forceinline__ int row_kind_of(bool sched, int cls, int rho) {
   }
   return ROW_INEQ;
 }
-// The row passes look the kind of a row up in shared memory (one division by 104 and two byte loads) instead of
+// The row passes look the kind of a row up in a byte table (one division by 104 and two byte loads, L1 hits) instead of
 // re-deriving it: the derivation was ~100 instructions inlined at a dozen sites, and the kernel is instruction-fetch
-// bound.
-__device__ void build_kind_tables(const KParams& P, unsigned char* kt) {
+// bound.  The table depends only on the problem, so one copy in global memory serves all CTAs.
+__global__ void k_kinds(const KParams P) {
+  unsigned char* kt = P.kt;
   const bool sched = P.pb.formulation == 1;
-  for (int i = TID; i < KT_CLASSES * RK; i += NT) kt[i] = (unsigned char)row_kind_of(sched, i / RK, i % RK);
-  for (int k = TID; k < P.K; k += NT) kt[KT_CLS + k] = (unsigned char)((sched ? __ldg(P.csm + k) & 15 : 15) + (k == P.K - 1 ? 16 : 0));
+  for (int i = TID; i < KT_CLASSES * RK; i += blockDim.x) kt[i] = (unsigned char)row_kind_of(sched, i / RK, i % RK);
+  for (int k = TID; k < P.K; k += blockDim.x) kt[KT_CLS + k] = (unsigned char)((sched ? __ldg(P.csm + k) & 15 : 15) + (k == P.K - 1 ? 16 : 0));
   if (TID < 36) kt[KT_BND + TID] = (unsigned char)(TID < 12 ? ROW_EQ : (sched ? ROW_FREE : ROW_INEQ));
-}
-__device__ __forceinline__ const unsigned char* kind_tables(const double* tab) {  // tab = smem + SM_TAB
-  return reinterpret_cast<const unsigned char*>(tab + (SM_KT - SM_TAB));
 }
 __device__ __forceinline__ int row_kind(const unsigned char* kt, int idx) {
   if (idx < 36) return kt[KT_BND + idx];
@@ -273,65 +289,54 @@ __device__ __forceinline__ void load_knot(const KParams& P, const double* x, con
 // The LAST knot is evaluated with the interior template too (c+ := 0): its no-slip rows and their entries are
 // never used -- those rows are ROW_FREE (sigma = y = 0 for the whole solve, skipped by every row pass) -- and a
 // second instantiation would run serially in the same warp (divergence) and double the code the warp streams.
-//
-// One knot is evaluated by EVP threads of EVP different warps (lane = knot): each runs the knot template behind a
-// compile-time filter (srb_knot.cuh: g_owner / j_owner / h_owner) and emits only its own legs' rows and entries, so a
-// thread executes about a third of the template instead of all of it.  Measured (B200, N = 30): 4 parts shorten an
-// iteration by 1 % (426 vs 430 us alone, 490 k vs 488 k iterations/s) for 76 kB more code; default 1.
-#ifndef SRB_EVAL_PARTS
-#define SRB_EVAL_PARTS 1
-#endif
-constexpr int EVP = SRB_EVAL_PARTS;
-static_assert(EVP == 1 || EVP == 2 || EVP == 4, "parts per knot");
-template <int PART> struct JSinkP {  // g rows + Jacobian entry list
+// (Splitting one knot over several threads behind a compile-time filter, as the batched evaluation kernels do, was
+// measured here at +1 % for 76 kB more code and is not kept.)
+struct JSinkP {  // g rows + Jacobian entry list
   double *gp, *jl;
-  __device__ __forceinline__ void g(int r, double v) { if (g_owner<false>(r) % EVP == PART) gp[r] = v; }
-  __device__ __forceinline__ void j(int e, int row, int var, double v) { if (j_owner<false>(row, var) % EVP == PART) jl[e] = v; }
+  __device__ __forceinline__ void g(int r, double v) { gp[r] = v; }
+  __device__ __forceinline__ void j(int e, int, int, double v) { jl[e] = v; }
   __device__ __forceinline__ void h(int, int, int, double) {}
 };
-template <int PART> struct HSinkP {  // Hessian entry list
+struct HSinkP {  // Hessian entry list
   double* hl;
   __device__ __forceinline__ void g(int, double) {}
   __device__ __forceinline__ void j(int, int, int, double) {}
-  __device__ __forceinline__ void h(int e, int va, int vb, double v) { if (h_owner(e, va, vb) % EVP == PART) hl[e] = v; }
+  __device__ __forceinline__ void h(int e, int, int, double v) { hl[e] = v; }
 };
-template <int PART> struct GSinkP {
+struct GSinkP {
   double* gp;
-  __device__ __forceinline__ void g(int r, double v) { if (g_owner<false>(r) % EVP == PART) gp[r] = v; }
+  __device__ __forceinline__ void g(int r, double v) { gp[r] = v; }
   __device__ __forceinline__ void j(int, int, int, double) {}
   __device__ __forceinline__ void h(int, int, int, double) {}
 };
-template <int PART>
 __device__ __noinline__ void eval_knot_j(const KParams& P, const Ws& w, const double* x, double* gout, int k0, int kstep) {
   for (int k = k0; k < P.K; k += kstep) {
     KnotRef kn;
     load_knot(P, x, P.zeros, k, kn);
     NoLam nl;
-    JSinkP<PART> s{gout + 36 + RK * k, w.JL + (long long)k * NJ_PAD};
-    if (P.pb.formulation == 1) knot_eval<false, true, true, false, JSinkP<PART>, NoLam, true, KnotRef>(kn, s, nl);
-    else knot_eval<false, true, true, false, JSinkP<PART>, NoLam, false, KnotRef>(kn, s, nl);
+    JSinkP s{gout + 36 + RK * k, w.JL + (long long)k * NJ_PAD};
+    if (P.pb.formulation == 1) knot_eval<false, true, true, false, JSinkP, NoLam, true, KnotRef>(kn, s, nl);
+    else knot_eval<false, true, true, false, JSinkP, NoLam, false, KnotRef>(kn, s, nl);
   }
 }
-template <int PART>
 __device__ __noinline__ void eval_knot_h(const KParams& P, const Ws& w, const double* x, int k0, int kstep) {
   for (int k = k0; k < P.K; k += kstep) {
     KnotRef kn;
     load_knot(P, x, P.zeros, k, kn);
-    HSinkP<PART> s{w.HL + (long long)k * NH_PAD};
+    HSinkP s{w.HL + (long long)k * NH_PAD};
     LamY<false> lam{w.Y + 36 + RK * k};
-    if (P.pb.formulation == 1) knot_eval<false, false, false, true, HSinkP<PART>, LamY<false>, true, KnotRef>(kn, s, lam);
-    else knot_eval<false, false, false, true, HSinkP<PART>, LamY<false>, false, KnotRef>(kn, s, lam);
+    if (P.pb.formulation == 1) knot_eval<false, false, false, true, HSinkP, LamY<false>, true, KnotRef>(kn, s, lam);
+    else knot_eval<false, false, false, true, HSinkP, LamY<false>, false, KnotRef>(kn, s, lam);
   }
 }
-template <int PART>
 __device__ __noinline__ void eval_knot_g(const KParams& P, const double* x, double* gout, int k0, int kstep) {
   for (int k = k0; k < P.K; k += kstep) {
     KnotRef kn;
     load_knot(P, x, P.zeros, k, kn);
     NoLam nl;
-    GSinkP<PART> s{gout + 36 + RK * k};
-    if (P.pb.formulation == 1) knot_eval<false, true, false, false, GSinkP<PART>, NoLam, true, KnotRef>(kn, s, nl);
-    else knot_eval<false, true, false, false, GSinkP<PART>, NoLam, false, KnotRef>(kn, s, nl);
+    GSinkP s{gout + 36 + RK * k};
+    if (P.pb.formulation == 1) knot_eval<false, true, false, false, GSinkP, NoLam, true, KnotRef>(kn, s, nl);
+    else knot_eval<false, true, false, false, GSinkP, NoLam, false, KnotRef>(kn, s, nl);
   }
 }
 
@@ -369,39 +374,20 @@ __device__ __noinline__ double run_cost_part(const KParams& P, const double* dro
 // g(x) (and, when LISTS, the J/H entry lists with multipliers Y) for all knots; returns f(x)
 template <bool LISTS>
 __device__ double eval_all(const KParams& P, const Ws& w, const double* drop, const double* x, double* gout, double* red) {
-  const int N = P.N, tid = TID, warp = tid >> 5, lane = tid & 31;
+  const int N = P.N, tid = TID;
   if (LISTS) {
-    // warps 0..EVP-1: Jacobian lists (part = warp), warps 4..4+EVP-1: Hessian lists; lane = knot
-    if (warp < 4) {
-      switch (warp) {  // (warp-uniform)
-        case 0: eval_knot_j<0>(P, w, x, gout, lane, 32); break;
-        case 1: if (EVP > 1) eval_knot_j<1 % EVP>(P, w, x, gout, lane, 32); break;
-        case 2: if (EVP > 2) eval_knot_j<2 % EVP>(P, w, x, gout, lane, 32); break;
-        default: if (EVP > 2) eval_knot_j<3 % EVP>(P, w, x, gout, lane, 32); break;
-      }
-    } else {
-      switch (warp - 4) {
-        case 0: eval_knot_h<0>(P, w, x, lane, 32); break;
-        case 1: if (EVP > 1) eval_knot_h<1 % EVP>(P, w, x, lane, 32); break;
-        case 2: if (EVP > 2) eval_knot_h<2 % EVP>(P, w, x, lane, 32); break;
-        default: if (EVP > 2) eval_knot_h<3 % EVP>(P, w, x, lane, 32); break;
-      }
-    }
+    // Jacobian lists on the warps of the first half of the CTA, Hessian lists on the second half; thread = knot
+    constexpr int HALF = NT / 2;
+    if (tid < HALF) eval_knot_j(P, w, x, gout, tid, HALF);
+    else eval_knot_h(P, w, x, tid - HALF, HALF);
   } else {
-    // all eight warps: part = warp % EVP, knots lane + 32 (warp / EVP), step 32 (8 / EVP)
-    const int k0 = lane + 32 * (warp / EVP), ks = 32 * (NWARP / EVP);
-    switch (warp % EVP) {
-      case 0: eval_knot_g<0>(P, x, gout, k0, ks); break;
-      case 1: eval_knot_g<1 % EVP>(P, x, gout, k0, ks); break;
-      case 2: eval_knot_g<2 % EVP>(P, x, gout, k0, ks); break;
-      default: eval_knot_g<3 % EVP>(P, x, gout, k0, ks); break;
-    }
+    eval_knot_g(P, x, gout, tid, NT);
   }
   // boundary rows 0..35 and objective (generate_landingCtrller_IPOPT.m:83-97)
   double fl = 0.0;
   const int xo = 12 * (N - 1);
-  if (tid >= 224 && tid < 236) {
-    const int i = tid - 224;
+  if (tid >= NT - 32 && tid < NT - 20) {
+    const int i = tid - (NT - 32);
     gout[i] = x[i];
     const double q = x[xo + i];
     const int r1 = i < 6 ? 12 + i : 24 + (i - 6);
@@ -449,6 +435,16 @@ __device__ __forceinline__ void row_step(const Ws& w, int idx, double lb, double
   w.DZU[idx] = dzu;
 }
 
+// index tables of the sweeps: shared memory (one copy per CTA) or global memory through the L1 (TBL_SMEM)
+__device__ __forceinline__ const int* sweep_tables(const KParams& P, const double* smem) {
+  if constexpr (TBL_SMEM) return reinterpret_cast<const int*>(smem + SM_TBL);
+  else return P.tab.sm_src;
+}
+__device__ __forceinline__ int tld(const int* p) {
+  if constexpr (TBL_SMEM) return *p;
+  else return __ldg(p);
+}
+
 #include "sweeps.cuh"
 
 // stage variable (X 0-11, c 12-23, f 24-35, c+ 36-47) of knot k -> index into x / dx
@@ -461,32 +457,28 @@ __device__ __forceinline__ int stage_var(int N, int k, int sv) {
 // row buffer of one knot for row_steps (doubles): J list | s | g | sigma | zL | zU | dx of the 48 stage variables
 constexpr int RB_J = 0, RB_S = NJ_PAD, RB_G = RB_S + RK, RB_SIG = RB_G + RK, RB_ZL = RB_SIG + RK, RB_ZU = RB_ZL + RK,
               RB_DX = RB_ZU + RK, RB_SIZE = RB_DX + NW + 4;
-static_assert(RB_SIZE % 2 == 0 && 2 * RB_SIZE <= NW * LDC && RB_SIZE <= LB_REGION && RB_SIZE <= NS * LDP + 2 * NS * LDC,
-              "row buffers alias the sweep regions");
+static_assert(RB_SIZE % 2 == 0 && RB_SIZE <= LB_REGION && 3 * RB_SIZE <= SM_SWEEP, "row buffers alias the sweep regions");
+
+// knots per round of row_steps / threads per knot
+constexpr int RG = NT >= 256 ? 2 : 1, TG = NT / RG, RS_DIST = 4 / RG - 1;  // RS_DIST: rounds prefetched ahead (ring of 4)
 
 __device__ __forceinline__ void prefetch_rows(const Ws& w, int N, int K, int k, double* rb) {
-  // called by 128 threads (t = TID & 127) for knot k
-  const int t = TID & 127, r0 = 36 + RK * k;
+  // called by the TG threads of one group (t = TID % TG) for knot k
+  const int t = TID % TG, r0 = 36 + RK * k;
   const double* Jk = w.JL + (long long)k * NJ_PAD;
-  for (int i = t; i < NJ_PAD / 2; i += 128) cp_async16(rb + RB_J + 2 * i, Jk + 2 * i);
-  if (t < RK / 2) {
-    cp_async16(rb + RB_S + 2 * t, w.S + r0 + 2 * t);
-    cp_async16(rb + RB_G + 2 * t, w.G + r0 + 2 * t);
-    cp_async16(rb + RB_SIG + 2 * t, w.SIG + r0 + 2 * t);
-  } else if (t < RK) {
-    const int i = t - RK / 2;
-    cp_async16(rb + RB_ZL + 2 * i, w.ZL + r0 + 2 * i);
-    cp_async16(rb + RB_ZU + 2 * i, w.ZU + r0 + 2 * i);
-  } else if (t < RK + 6) {
-    const int i = t - RK;
-    cp_async16(rb + RB_DX + 2 * i, w.dx + 12 * k + 2 * i);                    // dX_k
-  } else if (t < RK + 18) {
-    const int i = t - RK - 6;
-    cp_async16(rb + RB_DX + 12 + 2 * i, w.dx + 12 * N + 24 * k + 2 * i);      // dc_k, df_k
-  } else if (t < RK + 24) {
-    const int i = t - RK - 18;
-    if (k + 1 < K) cp_async16(rb + RB_DX + 36 + 2 * i, w.dx + 12 * N + 24 * (k + 1) + 2 * i);  // dc_{k+1}
-    else { rb[RB_DX + 36 + 2 * i] = 0.0; rb[RB_DX + 37 + 2 * i] = 0.0; }
+  constexpr int H = RK / 2, C_J = NJ_PAD / 2, C_S = C_J + H, C_G = C_S + H, C_SIG = C_G + H, C_ZL = C_SIG + H, C_ZU = C_ZL + H,
+                C_X = C_ZU + 6, C_CF = C_X + 12, C_END = C_CF + 6;
+  for (int i = t; i < C_END; i += TG) {
+    if (i < C_J) cp_async16(rb + RB_J + 2 * i, Jk + 2 * i);
+    else if (i < C_S) cp_async16(rb + RB_S + 2 * (i - C_J), w.S + r0 + 2 * (i - C_J));
+    else if (i < C_G) cp_async16(rb + RB_G + 2 * (i - C_S), w.G + r0 + 2 * (i - C_S));
+    else if (i < C_SIG) cp_async16(rb + RB_SIG + 2 * (i - C_G), w.SIG + r0 + 2 * (i - C_G));
+    else if (i < C_ZL) cp_async16(rb + RB_ZL + 2 * (i - C_SIG), w.ZL + r0 + 2 * (i - C_SIG));
+    else if (i < C_ZU) cp_async16(rb + RB_ZU + 2 * (i - C_ZL), w.ZU + r0 + 2 * (i - C_ZL));
+    else if (i < C_X) cp_async16(rb + RB_DX + 2 * (i - C_ZU), w.dx + 12 * k + 2 * (i - C_ZU));                      // dX_k
+    else if (i < C_CF) cp_async16(rb + RB_DX + 12 + 2 * (i - C_X), w.dx + 12 * N + 24 * k + 2 * (i - C_X));          // dc_k, df_k
+    else if (k + 1 < K) cp_async16(rb + RB_DX + 36 + 2 * (i - C_CF), w.dx + 12 * N + 24 * (k + 1) + 2 * (i - C_CF)); // dc_{k+1}
+    else { rb[RB_DX + 36 + 2 * (i - C_CF)] = 0.0; rb[RB_DX + 37 + 2 * (i - C_CF)] = 0.0; }
   }
 }
 
@@ -524,22 +516,26 @@ __device__ __forceinline__ void row_step_sm(const bool MERIT, const Ws& w, int i
 }
 
 // ds = J_row . dx + (g - s), new multipliers, dz, fraction-to-the-boundary limits, merit pieces.
-// Two knots per round (threads 0-127 / 128-255, one row per thread); the knots' J lists, row data and steps arrive in
+// RG knots per round (TG threads each, one or two rows per thread); the knots' J lists, row data and steps arrive in
 // shared memory through a 4-buffer cp.async ring, so no thread waits on a chain of dependent L2 round trips.
 __device__ __noinline__ void row_steps(const bool MERIT, const KParams& P, const Ws& w, double* smem, const double* tab, const double* drop,
                                        double* red, double mu, double tau, StepInfo& si) {
-  const unsigned char* kt = kind_tables(tab);
-  const int N = P.N, K = P.K, tid = TID, half = tid >> 7, t = tid & 127;
-  const int* t_rptr = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_rptr;
-  const int* t_rterms = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_rterms;
+  const unsigned char* kt = P.kt;
+  const int N = P.N, K = P.K, tid = TID, grp = tid / TG, t = tid % TG;
+  const int* t_rptr = sweep_tables(P, smem) + P.tab.o_rptr;
+  const int* t_rterms = sweep_tables(P, smem) + P.tab.o_rterms;
   si.a_pr = 1.0; si.a_du = 1.0; si.dphi_bar = 0.0; si.phi_bar = 0.0; si.theta = 0.0;
   auto ring = [&](int k) {
     const int j = k & 3;
-    return smem + (j == 0 ? SM_LB0 : (j == 1 ? SM_M : (j == 2 ? SM_M + RB_SIZE : SM_P)));
+    return smem + (j == 0 ? SM_LB0 : SM_P + (j - 1) * RB_SIZE);
   };
-  const int rounds = (K + 1) / 2;
-  if (half < K) prefetch_rows(w, N, K, half, ring(half));
-  cp_async_commit();
+  const int rounds = (K + RG - 1) / RG;
+#pragma unroll
+  for (int r = 0; r < RS_DIST; r++) {
+    const int k = RG * r + grp;
+    if (k < K) prefetch_rows(w, N, K, k, ring(k));
+    cp_async_commit();
+  }
   // boundary rows meanwhile (initial-state rows, terminal inequality rows)
   if (tid < 12) si.theta += fabs(w.G[tid] - drop[tid]);
   else if (tid < 36 && P.pb.formulation != 1) {  // (the fixed-schedule formulation has no terminal rows)
@@ -549,40 +545,43 @@ __device__ __noinline__ void row_steps(const bool MERIT, const KParams& P, const
   Prof pf{P.prof, 0, 20};  // (thread 20: an inequality row)
   pf.start();
   for (int r = 0; r < rounds; r++) {
-    const int k = 2 * r + half, kn = k + 2;
+    const int k = RG * r + grp, kn = k + RG * RS_DIST;
     if (kn < K) prefetch_rows(w, N, K, kn, ring(kn));
     cp_async_commit();
     pf.lap(PH_X0);
-    cp_async_wait_group<1>();
+    cp_async_wait_group<RS_DIST>();
     __syncthreads();
     pf.lap(PH_X1);
-    if (k < K && t < RK) {
+    if (k < K) {
       const double* rb = ring(k);
-      const int rho = t, idx = 36 + RK * k + rho;
-      const int kind = kt[kt[KT_CLS + k] * RK + rho];
-      if (kind == ROW_EQ) {
-        si.theta += fabs(rb[RB_G + rho]);
-      } else if (kind != ROW_FREE) {
-        double jdx = 0.0, jd1 = 0.0;
-        const int p0 = t_rptr[rho], p1 = t_rptr[rho + 1];
-        for (int p = p0; p < p1; p += 4) {  // (lists padded to fours with null terms; dc+ is zero at the last knot)
-          const int u0 = t_rterms[p], u1 = t_rterms[p + 1], u2 = t_rterms[p + 2], u3 = t_rterms[p + 3];
-          jdx += rb[RB_J + (u0 & 1023)] * rb[RB_DX + (u0 >> 10)];
-          jd1 += rb[RB_J + (u1 & 1023)] * rb[RB_DX + (u1 >> 10)];
-          jdx += rb[RB_J + (u2 & 1023)] * rb[RB_DX + (u2 >> 10)];
-          jd1 += rb[RB_J + (u3 & 1023)] * rb[RB_DX + (u3 >> 10)];
+      const unsigned char* kinds = kt + kt[KT_CLS + k] * RK;
+      for (int rho = t; rho < RK; rho += TG) {
+        const int idx = 36 + RK * k + rho;
+        const int kind = kinds[rho];
+        if (kind == ROW_EQ) {
+          si.theta += fabs(rb[RB_G + rho]);
+        } else if (kind != ROW_FREE) {
+          double jdx = 0.0, jd1 = 0.0;
+          const int p0 = tld(t_rptr + rho), p1 = tld(t_rptr + rho + 1);
+          for (int p = p0; p < p1; p += 4) {  // (lists padded to fours with null terms; dc+ is zero at the last knot)
+            const int u0 = tld(t_rterms + p), u1 = tld(t_rterms + p + 1), u2 = tld(t_rterms + p + 2), u3 = tld(t_rterms + p + 3);
+            jdx += rb[RB_J + (u0 & 1023)] * rb[RB_DX + (u0 >> 10)];
+            jd1 += rb[RB_J + (u1 & 1023)] * rb[RB_DX + (u1 >> 10)];
+            jdx += rb[RB_J + (u2 & 1023)] * rb[RB_DX + (u2 >> 10)];
+            jd1 += rb[RB_J + (u3 & 1023)] * rb[RB_DX + (u3 >> 10)];
+          }
+          jdx += jd1;
+          pf.lap(PH_X2);
+          if (kind == ROW_EQS) {  // y+ = y + sigma (J dx + c); no slack, no step-length limit
+            const double c = rb[RB_G + rho];
+            si.theta += fabs(c);
+            w.YN[idx] = w.Y[idx] + rb[RB_SIG + rho] * (jdx + c);
+            w.DS[idx] = 0.0; w.DZL[idx] = 0.0; w.DZU[idx] = 0.0;
+          } else {
+            row_step_sm(MERIT, w, idx, rb, rho, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
+          }
+          pf.lap(PH_X3);
         }
-        jdx += jd1;
-        pf.lap(PH_X2);
-        if (kind == ROW_EQS) {  // y+ = y + sigma (J dx + c); no slack, no step-length limit
-          const double c = rb[RB_G + rho];
-          si.theta += fabs(c);
-          w.YN[idx] = w.Y[idx] + rb[RB_SIG + rho] * (jdx + c);
-          w.DS[idx] = 0.0; w.DZL[idx] = 0.0; w.DZU[idx] = 0.0;
-        } else {
-          row_step_sm(MERIT, w, idx, rb, rho, tab[36 + rho], tab[NROWTAB + 36 + rho], jdx, mu, tau, si);
-        }
-        pf.lap(PH_X3);
       }
     }
     __syncthreads();
@@ -606,7 +605,7 @@ constexpr int RU = SRB_RU;
 
 __device__ __noinline__ void merit_trial(const KParams& P, const Ws& w, const double* tab, const double* drop,
                                             double* red, double alpha, double mu, double& phi_bar, double& theta) {
-  const unsigned char* kt = kind_tables(tab);
+  const unsigned char* kt = P.kt;
   const int K = P.K, MR = P.MR;
   const double* __restrict__ GT = w.GT;
   const double* __restrict__ S = w.S;
@@ -652,7 +651,7 @@ struct Errs {
 // sigma per row and the pieces of the optimality error (oracle/ip_ref.c: assemble)
 __device__ __noinline__ void row_errors(const KParams& P, const Ws& w, const double* tab, const double* drop,
                                            double* red, double mu, Errs& e) {
-  const unsigned char* kt = kind_tables(tab);
+  const unsigned char* kt = P.kt;
   const int K = P.K, MR = P.MR;
   const double* __restrict__ G = w.G;
   const double* __restrict__ Y = w.Y;
@@ -720,7 +719,7 @@ __device__ __noinline__ void row_errors(const KParams& P, const Ws& w, const dou
 }
 
 __device__ __noinline__ double compl_at(const KParams& P, const Ws& w, const double* tab, double* red, double mu) {
-  const unsigned char* kt = kind_tables(tab);
+  const unsigned char* kt = P.kt;
   const int K = P.K, MR = P.MR;
   double cmu = 0;
   for (int idx = TID; idx < MR; idx += NT) {
@@ -735,7 +734,7 @@ __device__ __noinline__ double compl_at(const KParams& P, const Ws& w, const dou
 
 // yhat = sigma (g - s) - mu/(s-lb) + mu/(ub-s)
 __device__ __noinline__ void row_yhat(const KParams& P, const Ws& w, const double* tab, double mu) {
-  const unsigned char* kt = kind_tables(tab);
+  const unsigned char* kt = P.kt;
   const int K = P.K, MR = P.MR;
   const double* __restrict__ G = w.G;
   const double* __restrict__ S = w.S;
@@ -769,8 +768,8 @@ __device__ __noinline__ void row_yhat(const KParams& P, const Ws& w, const doubl
 // max |grad f + J' y| (gradient of the Lagrangian w.r.t. x): one (knot, variable) item per thread
 __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const double* drop, const double* smem, double* red) {
   const int N = P.N, K = P.K, tid = TID;
-  const int* t_cptr = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_cptr;
-  const int* t_cterms = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_cterms;
+  const int* t_cptr = sweep_tables(P, smem) + P.tab.o_cptr;
+  const int* t_cterms = sweep_tables(P, smem) + P.tab.o_cterms;
   double dmax = 0.0;
   for (int item = tid; item < K * 36; item += NT) {
     const int k = item / 36, v = item - k * 36;
@@ -778,9 +777,9 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
     const double* yk = w.Y + 36 + RK * k;
     double a = 0.0, a1 = 0.0;
     {
-      const int p0 = t_cptr[v], p1 = t_cptr[v + 1];
+      const int p0 = tld(t_cptr + v), p1 = tld(t_cptr + v + 1);
       for (int p = p0; p < p1; p += 4) {  // (lists padded to fours with null terms)
-        const int u0 = t_cterms[p], u1 = t_cterms[p + 1], u2 = t_cterms[p + 2], u3 = t_cterms[p + 3];
+        const int u0 = tld(t_cterms + p), u1 = tld(t_cterms + p + 1), u2 = tld(t_cterms + p + 2), u3 = tld(t_cterms + p + 3);
         a += Jk[u0 & 1023] * yk[u0 >> 10];
         a1 += Jk[u1 & 1023] * yk[u1 >> 10];
         a += Jk[u2 & 1023] * yk[u2 >> 10];
@@ -793,9 +792,9 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
       if (k > 0) {  // what knot k-1 contributes to (X_k, c_k) through its X+ / c+ columns
         const double* Jp = Jk - NJ_PAD;
         const double* yp = yk - RK;
-        const int p0 = t_cptr[36 + v], p1 = t_cptr[36 + v + 1];
+        const int p0 = tld(t_cptr + 36 + v), p1 = tld(t_cptr + 36 + v + 1);
         for (int p = p0; p < p1; p += 4) {
-          const int u0 = t_cterms[p], u1 = t_cterms[p + 1], u2 = t_cterms[p + 2], u3 = t_cterms[p + 3];
+          const int u0 = tld(t_cterms + p), u1 = tld(t_cterms + p + 1), u2 = tld(t_cterms + p + 2), u3 = tld(t_cterms + p + 3);
           a += Jp[u0 & 1023] * yp[u0 >> 10];
           a1 += Jp[u1 & 1023] * yp[u1 >> 10];
           a += Jp[u2 & 1023] * yp[u2 >> 10];
@@ -812,9 +811,9 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
     const double* Jk = w.JL + (long long)(K - 1) * NJ_PAD;
     const double* yk = w.Y + 36 + RK * (K - 1);
     double a = 0.0;
-    const int p0 = t_cptr[36 + tid], p1 = t_cptr[36 + tid + 1];
+    const int p0 = tld(t_cptr + 36 + tid), p1 = tld(t_cptr + 36 + tid + 1);
     for (int p = p0; p < p1; p++) {
-      const int term = t_cterms[p];  // (null terms add 0 * y_0)
+      const int term = tld(t_cterms + p);  // (null terms add 0 * y_0)
       a += Jk[term & 1023] * yk[term >> 10];
     }
     const int r1 = tid < 6 ? 12 + tid : 24 + (tid - 6);
@@ -827,7 +826,7 @@ __device__ __noinline__ double dual_inf_x(const KParams& P, const Ws& w, const d
 
 // slacks pushed inside their bounds at the current g; mu-based bound multipliers (ip_ref.c: init_slacks)
 __device__ __noinline__ void init_slacks(const KParams& P, const Ws& w, const double* tab, double mu) {
-  const unsigned char* kt = kind_tables(tab);
+  const unsigned char* kt = P.kt;
   const int K = P.K, MR = P.MR;
   const double bp = P.opt.bound_push, bf = P.opt.bound_frac;
   for (int idx = TID; idx < MR; idx += NT) {
@@ -908,7 +907,7 @@ __device__ void solve_one(const KParams& P, Ws& w, double* smem, long long b) {
   const double kappa_sigma = 1e10, s_max = 100.0;
   const double* drop = P.drops + 12 * b;
   const double* tab = smem + SM_TAB;
-  const unsigned char* kt = kind_tables(tab);
+  const unsigned char* kt = P.kt;
   double* red = smem + SM_RED;
 
   // initial guess: user x0 or the reference's [Xref(:); Uref(:)] (generate_landingCtrller_IPOPT.m:199-208,336)
@@ -1186,8 +1185,7 @@ __global__ void __launch_bounds__(NT, CTAS_PER_SM) k_solve(const __grid_constant
   __syncthreads();
   const KParams& P = sP;
   build_tables(P, smem + SM_TAB);
-  build_kind_tables(P, reinterpret_cast<unsigned char*>(smem + SM_KT));
-  {
+  if constexpr (TBL_SMEM) {
     int* tbl = reinterpret_cast<int*>(smem + SM_TBL);
     for (int i = TID; i < P.tab.sm_count; i += NT) tbl[i] = __ldg(P.tab.sm_src + i);
   }

@@ -13,21 +13,34 @@
 // ---- FP64 tensor-core tiles.  The dense work of a stage (T = P W, M += W'T, the trailing updates of the blocked
 // factorisation) runs as mma.sync.m8n8k4.f64 (DMMA in SASS; measured 37.1 TFLOP/s on B200 = the DFMA peak,
 // tools/ubench_dmma.cu) at an eighth of the issue slots and a fraction of the shared-memory operand traffic of a DFMA
-// loop: the 49 x 48 stage matrix (48 variables + the gradient row) lives in the REGISTERS of the eight warps as 8 x 8
+// loop: the 49 x 48 stage matrix (48 variables + the gradient row) lives in the REGISTERS of the CTA's warps as 8 x 8
 // accumulator tiles for the whole stage; only the current 8-column panel passes through shared memory.
 // Fragment layout (lane = 4 g + t): A[g][t] (8 x 4, row), B[t][g] (4 x 8, col), C[g][2t], C[g][2t+1].
 __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
   asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
-// the 27 tiles (I, J), J <= I, of the lower triangle of the 56 x 48 padded stage matrix (tile row 6 = gradient row),
-// column by column; warp w owns tiles w, w + 8, w + 16, w + 24: every trailing update is spread over all warps
+// The 27 tiles (I, J), J <= I, of the lower triangle of the 56 x 48 padded stage matrix (tile row 6 = gradient row) are
+// numbered column by column; warp w owns tiles w, w + NWARP, w + 2 NWARP, ...  The stage code is instantiated once per
+// warp (template parameter WARP), so every tile coordinate, every structural-zero mask and every shared-memory offset
+// is a COMPILE-TIME constant: a tile product costs its two operand loads and the DMMA, nothing else (the data-driven
+// version of this loop spent ~20 instructions per DMMA on masks, selects and address arithmetic, and the sweep is
+// bound by instruction issue, profiles/r2_ksolve_summary.txt).
 constexpr int NTILE = 27;
-__constant__ unsigned char c_tile[32] = {
-    0x00, 0x01, 0x02, 0x03, 0x04, 0x05, 0x06, 0x11, 0x12, 0x13, 0x14, 0x15, 0x16, 0x22, 0x23, 0x24,
-    0x25, 0x26, 0x33, 0x34, 0x35, 0x36, 0x44, 0x45, 0x46, 0x55, 0x56, 0xff, 0xff, 0xff, 0xff, 0xff};  // J << 4 | I
+__host__ __device__ constexpr int tile_J(int tile) {
+  int j = 0, start = 0;
+  while (tile >= start + (7 - j)) { start += 7 - j; j++; }
+  return j;
+}
+__host__ __device__ constexpr int tile_I(int tile) {
+  int j = 0, start = 0;
+  while (tile >= start + (7 - j)) { start += 7 - j; j++; }
+  return j + (tile - start);
+}
+static_assert(tile_I(0) == 0 && tile_J(0) == 0 && tile_I(6) == 6 && tile_J(7) == 1 && tile_I(7) == 1 && tile_I(26) == 6 &&
+              tile_J(26) == 5 && tile_I(25) == 5, "tile numbering");
 // k-steps (groups of four rows of W = [G^ ; E]) with structural non-zeros in column tile J of W: the c+ columns
 // (12..23) are zero in G^ (rows 0..11) and carry the identity E (rows 12..23)
-__device__ __forceinline__ unsigned w_mask(int J) { return (unsigned)((0x07070730'0f07ull >> (8 * J)) & 0xffu); }
+__host__ __device__ constexpr unsigned w_mask(int J) { return (unsigned)((0x070707300f07ull >> (8 * J)) & 0xffu); }
 constexpr int PNB = 8;  // panel width = tile width
 // the Riccati factors are written once per stage and read once by the forward sweep: streaming stores (evict-first) keep
 // the L2 for the row arrays and the iterate, which every pass of an iteration touches
@@ -46,14 +59,18 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 
 // stage lists of knot k -> list buffer (asynchronously, 16-byte chunks)
 __device__ __forceinline__ void prefetch_lists(const Ws& w, int k, double* lb) {
-  const int tid = TID, rb = 36 + RK * k;
+  const int rb = 36 + RK * k;
   const double* Jk = w.JL + (long long)k * NJ_PAD;
   const double* Hk = w.HL + (long long)k * NH_PAD;
-  if (tid < NJ_PAD / 2) cp_async16(lb + LB_J + 2 * tid, Jk + 2 * tid);
-  else if (tid < NJ_PAD / 2 + RK / 2) { const int i = tid - NJ_PAD / 2; cp_async16(lb + LB_SIG + 2 * i, w.SIG + rb + 2 * i); }
-  if (tid < NH_PAD / 2) cp_async16(lb + LB_H + 2 * tid, Hk + 2 * tid);
-  else if (tid < NH_PAD / 2 + RK / 2) { const int i = tid - NH_PAD / 2; cp_async16(lb + LB_YH + 2 * i, w.YH + rb + 2 * i); }
-  else if (tid < NH_PAD / 2 + RK / 2 + 6) { const int i = tid - NH_PAD / 2 - RK / 2; cp_async16(lb + LB_GD + 2 * i, w.G + rb + 2 * i); }
+  // chunk ranges: J list | sigma | H list | yhat | dynamics defects
+  constexpr int C_J = NJ_PAD / 2, C_S = C_J + RK / 2, C_H = C_S + NH_PAD / 2, C_Y = C_H + RK / 2, C_END = C_Y + 6;
+  for (int i = TID; i < C_END; i += NT) {
+    if (i < C_J) cp_async16(lb + LB_J + 2 * i, Jk + 2 * i);
+    else if (i < C_S) cp_async16(lb + LB_SIG + 2 * (i - C_J), w.SIG + rb + 2 * (i - C_J));
+    else if (i < C_H) cp_async16(lb + LB_H + 2 * (i - C_S), Hk + 2 * (i - C_S));
+    else if (i < C_Y) cp_async16(lb + LB_YH + 2 * (i - C_H), w.YH + rb + 2 * (i - C_H));
+    else cp_async16(lb + LB_GD + 2 * (i - C_Y), w.G + rb + 2 * (i - C_Y));
+  }
   cp_async_commit();
 }
 
@@ -82,7 +99,7 @@ template <int PENDING> __device__ __forceinline__ void cp_async_wait_group() {
 
 __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double* smem, const double* drop) {
   const int K = P.K, tid = TID;
-  const int* tbl = reinterpret_cast<const int*>(smem + SM_TBL);
+  const int* tbl = sweep_tables(P, smem);
   const SolverTables& tb = P.tab;
   const int* t_g = tbl + tb.o_g;
   const int* t_qptr = tbl + tb.o_qptr;
@@ -93,12 +110,13 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
   const bool run = has_run_cost(P);
   const double rq0 = 2.0 * P.pb.Qf[0], rq1 = 2.0 * P.pb.Qf[1], rq2 = 2.0 * P.pb.Qf[2];
   auto run2q = [&](int j) { return j % 3 == 0 ? rq0 : (j % 3 == 1 ? rq1 : rq2); };  // 2 Qf of force component j (times dt_k)
-  // 4-deep ring of list buffers over regions that are idle before the sweeps: list region | stage matrix (2) | P,G,T
+  // 4-deep ring of list buffers over regions that are idle before the sweeps: list region | sweep regions (3)
   auto ring = [&](int k) {
     const int j = k & 3;
-    return smem + (j == 0 ? SM_LB0 : (j == 1 ? SM_M : (j == 2 ? SM_M + LB_SIZE : SM_P)));
+    return smem + (j == 0 ? SM_LB0 : SM_P + (j - 1) * LB_SIZE);
   };
-  static_assert(2 * LB_SIZE <= NW * LDC && LB_SIZE <= LB_REGION && LB_SIZE <= NS * LDP + 2 * NS * LDC, "ring buffers fit");
+  static_assert(LB_SIZE <= LB_REGION && 3 * LB_SIZE <= SM_SWEEP, "ring buffers fit");
+  const int n_items = tb.n_u + NW + tb.n_g + 12, n_rounds = (n_items + NT - 1) / NT;
   for (int k = 0; k < 3; k++) {
     if (k < K) prefetch_lists(w, k, ring(k)); else cp_async_commit();
   }
@@ -112,16 +130,16 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
     const double* SIGs = lb + LB_SIG;
     const double* YHs = lb + LB_YH;
     double* ct = w.CT + (long long)k * CT_STRIDE;
-#pragma unroll
-    for (int rnd = 0; rnd < 2; rnd++) {
-      // second round in reverse thread order: the threads that had the long targets get the trivial items
-      const int it = rnd == 0 ? tid : 2 * NT - 1 - tid;
+    for (int rnd = 0; rnd < n_rounds; rnd++) {
+      // every other round in reverse thread order (the targets are sorted longest first): the threads that had the
+      // long targets get the short ones next
+      const int it = (rnd & 1) == 0 ? rnd * NT + tid : (rnd + 1) * NT - 1 - tid;
       if (it < tb.n_u) {
-        const int abh = t_uabh[it], h = abh >> 12;
+        const int abh = tld(t_uabh + it), h = abh >> 12;
         double a0 = h ? Hs[h - 1] : 0.0, a1 = 0.0;
-        const int p0 = t_uptr[it], p1 = t_uptr[it + 1];
+        const int p0 = tld(t_uptr + it), p1 = tld(t_uptr + it + 1);
         for (int p = p0; p < p1; p += 2) {
-          const int u0 = t_uterms[p], u1 = t_uterms[p + 1];
+          const int u0 = tld(t_uterms + p), u1 = tld(t_uterms + p + 1);
           a0 += SIGs[u0 >> 20] * Js[(u0 >> 10) & 1023] * Js[u0 & 1023];
           a1 += SIGs[u1 >> 20] * Js[(u1 >> 10) & 1023] * Js[u1 & 1023];
         }
@@ -134,9 +152,9 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
       } else if (it < tb.n_u + NW) {
         const int m = it - tb.n_u;
         double a0 = 0.0, a1 = 0.0;
-        const int p0 = t_qptr[m], p1 = t_qptr[m + 1];
+        const int p0 = tld(t_qptr + m), p1 = tld(t_qptr + m + 1);
         for (int p = p0; p < p1; p += 2) {
-          const int u0 = t_qterms[p], u1 = t_qterms[p + 1];
+          const int u0 = tld(t_qterms + p), u1 = tld(t_qterms + p + 1);
           a0 += YHs[u0 >> 10] * Js[u0 & 1023];
           a1 += YHs[u1 >> 10] * Js[u1 & 1023];
         }
@@ -146,7 +164,7 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
         ST_STREAM(&ct[CT_Q + m], a0 + a1);
       } else if (it < tb.n_u + NW + tb.n_g) {
         const int n = it - tb.n_u - NW;
-        ST_STREAM(&ct[CT_G + n], -Js[t_g[n] & 1023]);
+        ST_STREAM(&ct[CT_G + n], -Js[tld(t_g + n) & 1023]);
       } else if (it < tb.n_u + NW + tb.n_g + 12) {
         const int i = it - tb.n_u - NW - tb.n_g;
         ct[CT_R + dyn_state(i)] = -lb[LB_GD + i];
@@ -159,66 +177,62 @@ __device__ __noinline__ void condense_all(const KParams& P, const Ws& w, double*
 
 // condensed data of stage k -> shared memory (asynchronously, 16-byte chunks)
 __device__ __forceinline__ void prefetch_ct(const Ws& w, int k, double* cb) {
-  const int tid = TID;
-  if (tid < CT_STRIDE / 2) cp_async16(cb + 2 * tid, w.CT + (long long)k * CT_STRIDE + 2 * tid);
+  for (int i = TID; i < CT_STRIDE / 2; i += NT) cp_async16(cb + 2 * i, w.CT + (long long)k * CT_STRIDE + 2 * i);
   cp_async_commit();
 }
 
 // ---------------------------------------------------------------- backward sweep
 // Factors every stage and propagates P, p.  false -> not PD (wrong inertia).
 //
-// One stage, all 256 threads (DMMA = mma.sync.m8n8k4.f64, tiles of the 49 x 48 stage matrix in registers):
-//   S1  condensed sums -> Mc (the 278 structural targets; everything else of Mc stays zero for the whole sweep),
-//       structural entries of G^ -> W, defects r
+// One stage, all threads of the CTA (DMMA = mma.sync.m8n8k4.f64, tiles of the 49 x 48 stage matrix in registers):
+//   S1  structural entries of G^ -> W, defects r  (the condensed sums stay where the prefetch put them)
 //   S2  T = P_{k+1} W                                   (DMMA, 54 tile products)  ->  shared memory
-//   S3  M = Mc + W'T, gradient row q + W't              (DMMA, 62 + 19)           ->  accumulator tiles in registers
+//   S3  M = Mc + W'T, gradient row q + W't              (DMMA, 62 + 19)           ->  accumulator tiles in registers,
+//       initialised from the condensed sums through the inverse table (SolverTables::tinit)
 //   S4  three block steps of 8 pivots: the panel (one row per thread of warps 0-1; the 8 x 8 diagonal block is factored
 //       redundantly in the registers of every panel thread, right-looking, fused column by column with the triangular
 //       solve of the thread's row) -> shared memory; trailing update of the register tiles (DMMA, k = 8)
 //   S5  Schur complement = P_k, p_k from the tiles; L | Yt | yv from the panel buffer to the scratch (forward sweep)
-__device__ __forceinline__ void store_tile_ms(double* Ms, int I, int J, int g, int t, double c0, double c1) {
-  if (I < 6 || g == 0) *reinterpret_cast<double2*>(Ms + (8 * I + g) * LDMS + 8 * J + 2 * t) = make_double2(c0, c1);
-}
+// The stage loop is ONE code body shared by all warps (the kernel is bound by instruction fetch: with a copy of the
+// loop per warp -- compile-time tile coordinates -- the SM instruction cache hit rate fell to 52 % and the GPC-level
+// cache saturated, profiles/r2_ksolve_templated_summary.txt).  Tile coordinates are per-warp RUNTIME values (I, J per
+// accumulator tile q), everything else is compile time: the k-step loops are unrolled so that every operand address
+// is a per-tile base plus an immediate, and structural-zero k-steps are skipped by warp-uniform predicates.
+constexpr int TPW = (NTILE + NWARP - 1) / NWARP;  // accumulator tiles per warp
+constexpr int TQ2 = (18 + NWARP - 1) / NWARP;     // tiles of T = P W (3 x 6) per warp
+constexpr int MS_ZROW = NW + 1;                   // an all-zero row of the panel buffer (A operand of unused lanes)
+static_assert((MS_ZROW + 1) * LDMS <= SM_SWEEP_END - SM_MS, "panel buffer with its zero row");
+constexpr int W_TCOL = NW;                        // column of W that carries t = P [r; 0] + p (columns 49..51 stay zero)
 
-__device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, double* smem, double dwreg) {
-  const int N = P.N, K = P.K, tid = TID, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  double* Mc = smem + SM_M;
+__device__ __forceinline__ unsigned w_mask_rt(int J) { return (unsigned)((0x070707300f07ull >> (8 * J)) & 0xffu); }
+
+// the stage loop (returns false on a non-positive pivot; the result is block-uniform)
+__device__ __noinline__ bool backward_stages(const KParams& P, const Ws& w, double* smem, double dwreg, volatile int* s_bad) {
+  const int K = P.K, tid = TID, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   double* Pn = smem + SM_P;
   double* Wm = smem + SM_W;
   double* Ts = smem + SM_T;
   double* Ms = smem + SM_MS;
   double* V = smem + SM_V;
-  const int* tbl = reinterpret_cast<const int*>(smem + SM_TBL);
+  const int* tbl = sweep_tables(P, smem);
   const SolverTables& tb = P.tab;
-  __shared__ int s_ok, s_bad;
-  if (TID == 0) s_bad = 0;  // (visible after the barriers below)
   const int* t_g = tbl + tb.o_g;
-  const int* t_uabh = tbl + tb.o_uabh;
-  // this warp's accumulator tiles
-  int tI[4], tJ[4];
+  // this warp's accumulator tiles: coordinates, where the lane's two entries sit in the condensed sums (0xffff:
+  // structurally zero), k-step masks
+  int tI[TPW], tJ[TPW], tin[TPW];
+  unsigned mk3[TPW];
 #pragma unroll
-  for (int q = 0; q < 4; q++) {
-    const int e = c_tile[warp + 8 * q];
-    tI[q] = e == 0xff ? -1 : (e & 15);
-    tJ[q] = e == 0xff ? 0 : (e >> 4);
+  for (int q = 0; q < TPW; q++) {
+    const int tile = warp + NWARP * q;
+    const bool valid = tile < NTILE;
+    int j = 0, start = 0;
+    while (valid && tile >= start + (7 - j)) { start += 7 - j; j++; }
+    tJ[q] = valid ? j : 0;
+    tI[q] = valid ? j + (tile - start) : -1;
+    tin[q] = valid ? __ldg(tb.tinit + tile * 32 + lane) : -1;
+    mk3[q] = valid ? w_mask_rt(tI[q] == 6 ? tJ[q] : tI[q]) : 0u;
   }
-  prefetch_ct(w, K - 1, smem + SM_LB0 + ((K - 1) & 1) * CT_STRIDE);
-  // Mc: zero outside the condensing targets; W: zero outside the structural entries of G^, identity E; terminal P_K, p_K
-  for (int i = tid; i < NW * LDC; i += NT) Mc[i] = 0.0;
-  for (int i = tid; i < NS * LDP; i += NT) Pn[i] = 0.0;
-  for (int i = tid; i < NS * LDC; i += NT) Wm[i] = 0.0;
-  if (tid < NS) { V[V_PN + tid] = 0.0; V[V_Z + tid] = 0.0; }
-  __syncthreads();
-  if (tid < 12) {
-    const int r1 = tid < 6 ? 12 + tid : 24 + (tid - 6), r2 = r1 + 6;
-    const double q = w.x[12 * (N - 1) + tid];
-    const double ref = tid < 6 ? P.pb.q_term_ref[tid] : P.pb.qd_term_ref[tid - 6];
-    Pn[tid * LDP + tid] = 2.0 * P.pb.QN[tid] + w.SIG[r1] + w.SIG[r2] + dwreg;
-    V[V_PN + tid] = 2.0 * P.pb.QN[tid] * (q - ref) + w.YH[r1] + w.YH[r2];
-  } else if (tid < 24) {
-    Wm[tid * LDC + tid] = 1.0;  // E: c+ (stage variable 12 + j) is component 12 + j of the next stage's state
-  }
-  __syncthreads();
+  double c[TPW][2];
 
   Prof pf{P.prof, 0};
   pf.start();
@@ -231,96 +245,76 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
     if (k > 0) prefetch_ct(w, k - 1, smem + SM_LB0 + ((k - 1) & 1) * CT_STRIDE);
     // rows X of P_{k+1} and p_{k+1} for the costates (one compact loop here instead of scattered stores from the tiles)
     for (int i = tid; i < 288; i += NT) ST_STREAM(&w.PX[(long long)(k + 1) * 288 + i], Pn[(i / 24) * LDP + (i % 24)]);
-    if (tid >= 128 && tid < 128 + NS) w.PV[(k + 1) * 24 + tid - 128] = V[V_PN + tid - 128];
-    // S1. condensed sums (+ delta_w on the (f, X, c) diagonal, dummy c+ of the last stage), G^, defects r
-#pragma unroll
-    for (int rnd = 0; rnd < 2; rnd++) {
-      const int i = tid + NT * rnd;
-      if (i < tb.n_u) {
-        const int ab = t_uabh[i] & 4095, a = ab / NW, b2 = ab - a * NW;
-        double acc = cb[i];
-        if (a == b2) acc += (a >= 12 && a < 24) ? (k == K - 1 ? 1.0 : 0.0) : dwreg;
-        Mc[a * LDC + b2] = acc;
-      }
+    if (tid >= NT - 32 && tid < NT - 32 + NS) w.PV[(k + 1) * 24 + tid - (NT - 32)] = V[V_PN + tid - (NT - 32)];
+    // S1. G^ (structural entries; the rest of W never changes), defects r
+    for (int i = tid; i < tb.n_g; i += NT) {
+      const int e = tld(t_g + i) >> 10, row = e / 36, v = e - 36 * row;  // v: G column (X, c, f) -> elimination order
+      Wm[row * LDC + (v < 24 ? v + 24 : v - 24)] = cb[CT_G + i];
     }
-    if (tid < tb.n_g) {
-      const int e = t_g[tid] >> 10, row = e / 36, v = e - 36 * row;  // v: G column (X, c, f) -> elimination order
-      Wm[row * LDC + (v < 24 ? v + 24 : v - 24)] = cb[CT_G + tid];
-    } else if (tid >= 224 && tid < 236) {
-      V[V_R + tid - 224] = cb[CT_R + tid - 224];
-    }
+    if (tid >= NT - 32 && tid < NT - 20) V[V_R + tid - (NT - 32)] = cb[CT_R + tid - (NT - 32)];
     __syncthreads();
     pf.lap(PH_B_P1);
-    // S2. T = P W (24 x 48); t = P [r; 0] + p.  Warp w: tiles w, w + 8, w + 16 (< 18), their products interleaved
-    {
-      int oI[3], oJ[3];
-      unsigned mk[3];
-      double c2[3][2];
+    // S2. T = P W (24 x 48), tiles warp, warp + NWARP, ... of the 3 x 6 grid; t = P [r; 0] + p into column 48 of W
 #pragma unroll
-      for (int q = 0; q < 3; q++) {
-        const int tile = warp + NWARP * q, I = tile / 6;
-        oI[q] = I; oJ[q] = tile - 6 * I;
-        mk[q] = tile < 18 ? w_mask(oJ[q]) : 0u;
-        c2[q][0] = 0.0; c2[q][1] = 0.0;
+    for (int q = 0; q < TQ2; q++) {
+      const int tile = warp + NWARP * q;
+      if (tile < 18) {  // (warp-uniform)
+        const int I = tile / 6, J = tile - 6 * I;
+        const unsigned mk = w_mask_rt(J);
+        const double* pa = Pn + (8 * I + g) * LDP + t;
+        const double* pb = Wm + t * LDC + 8 * J + g;
+        double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+        for (int s2 = 0; s2 < 6; s2++)
+          if (mk >> s2 & 1) dmma(c0, c1, pa[4 * s2], pb[4 * s2 * LDC]);
+        *reinterpret_cast<double2*>(Ts + (8 * I + g) * LDC + 8 * J + 2 * t) = make_double2(c0, c1);
       }
-#pragma unroll 1  // (rolled: the stage loop must stay small, the kernel is instruction-fetch bound)
-      for (int s2 = 0; s2 < 6; s2++)
-#pragma unroll
-        for (int q = 0; q < 3; q++)
-          if (mk[q] >> s2 & 1)
-            dmma(c2[q][0], c2[q][1], Pn[(8 * oI[q] + g) * LDP + 4 * s2 + t], Wm[(4 * s2 + t) * LDC + 8 * oJ[q] + g]);
-#pragma unroll
-      for (int q = 0; q < 3; q++)
-        if (mk[q]) *reinterpret_cast<double2*>(Ts + (8 * oI[q] + g) * LDC + 8 * oJ[q] + 2 * t) = make_double2(c2[q][0], c2[q][1]);
     }
-    if (warp == 7 && lane < NS) {
+    if (warp == NWARP - 1 && lane < NS) {
       double a0 = V[V_PN + lane], a1 = 0.0;
 #pragma unroll
       for (int l = 0; l < 12; l += 2) {
         a0 += Pn[lane * LDP + l] * V[V_R + l];
         a1 += Pn[lane * LDP + l + 1] * V[V_R + l + 1];
       }
-      V[V_T + lane] = a0 + a1;
+      Wm[lane * LDC + W_TCOL] = a0 + a1;
     }
     __syncthreads();
     pf.lap(PH_B_P2);
-    // S3. accumulator tiles: M = Mc + W'T (rows 0..47), q + W't (row 48 = lane group 0 of tile row 6); the products of
-    // the warp's (up to) four tiles are interleaved k-step by k-step
-    double c[4][2];
-    {
-      const double *pa[4], *pb[4];
-      int sa[4];
-      unsigned mk[4];
+    // S3. accumulator tiles: M = Mc + W'T (rows 0..47), q + W't (row 48 = lane group 0 of tile row 6: the A operand
+    // is column 48 + g of W, i.e. t for g = 0 and zeros for g = 1..3; lane groups 4..7 read past the row and produce
+    // numbers in accumulator rows 52..55 that nothing ever uses)
 #pragma unroll
-      for (int q = 0; q < 4; q++) {
-        const int I = tI[q], J = tJ[q];
-        const bool valid = I >= 0, isrow = I == 6;
-        mk[q] = valid ? w_mask(isrow ? J : I) : 0u;
-        // A operand: column 8I+g of W (rows 4s+t) | gradient row: t (lane group 0), zero for the other groups
-        pa[q] = isrow ? (V + (g == 0 ? V_T : V_Z) + t) : (Wm + t * LDC + 8 * (valid ? I : 0) + g);
-        sa[q] = isrow ? 4 : 4 * LDC;
-        pb[q] = (isrow ? Wm : Ts) + t * LDC + 8 * J + g;
-        double2 m2 = make_double2(0.0, 0.0);
-        if (valid && !isrow) m2 = *reinterpret_cast<const double2*>(Mc + (8 * I + g) * LDC + 8 * J + 2 * t);
-        else if (isrow && g == 0) m2 = *reinterpret_cast<const double2*>(cb + CT_Q + 8 * J + 2 * t);
-        c[q][0] = m2.x; c[q][1] = m2.y;
+    for (int q = 0; q < TPW; q++) {
+      const int I = tI[q], J = tJ[q];
+      const unsigned lo = (unsigned)tin[q] & 0xffffu, hi = (unsigned)tin[q] >> 16;
+      double m0 = lo == 0xffffu ? 0.0 : cb[lo], m1 = hi == 0xffffu ? 0.0 : cb[hi];
+      if (I == J) {  // diagonal: delta_w on (f, X, c), the dummy c+ of the last stage
+        const int row = 8 * I + g, col = 8 * J + 2 * t;
+        const double d = (row >= 12 && row < 24) ? (k == K - 1 ? 1.0 : 0.0) : dwreg;
+        if (row == col) m0 += d;
+        if (row == col + 1) m1 += d;
       }
-#pragma unroll 1
+      c[q][0] = m0; c[q][1] = m1;
+      const double* pa = Wm + t * LDC + 8 * (I < 0 ? 0 : I) + g;
+      const double* pb = (I == 6 ? Wm : Ts) + t * LDC + 8 * J + g;
+      const unsigned mk = mk3[q];
+#pragma unroll
       for (int s2 = 0; s2 < 6; s2++)
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-          if (mk[q] >> s2 & 1) dmma(c[q][0], c[q][1], pa[q][s2 * sa[q]], pb[q][s2 * 4 * LDC]);
-#pragma unroll
-      for (int q = 0; q < 4; q++)
-        if (tI[q] >= 0 && tJ[q] == 0) store_tile_ms(Ms, tI[q], 0, g, t, c[q][0], c[q][1]);
+        if (mk >> s2 & 1) dmma(c[q][0], c[q][1], pa[4 * s2 * LDC], pb[4 * s2 * LDC]);
     }
+    __syncthreads();  // T is dead: its region becomes the panel buffer
+#pragma unroll
+    for (int q = 0; q < TPW; q++)
+      if (tI[q] >= 0 && tJ[q] == 0 && (tI[q] < 6 || g == 0))
+        *reinterpret_cast<double2*>(Ms + (8 * tI[q] + g) * LDMS + 2 * t) = make_double2(c[q][0], c[q][1]);
     __syncthreads();
     pf.lap(PH_B_P3);
     // S4. eliminate the controls: three block steps of 8 pivots
 #pragma unroll 1
     for (int b = 0; b < NS / PNB; b++) {
       const int p0 = PNB * b, i0 = p0 + PNB;
-      if (tid < 64) {
+      if (NT == 64 || tid < 64) {
         double L[PNB][PNB], x[PNB];
 #pragma unroll
         for (int i = 0; i < PNB; i++)
@@ -352,8 +346,8 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
 #pragma unroll
           for (int j = 0; j < PNB; j++) arow[j] = x[j];
         }
-        if (!pd && tid == 0) s_bad = 1;
-        __syncthreads();  // (all 256 threads meet here or at the barrier of the else branch)
+        if (!pd && tid == 0) *s_bad = 1;
+        __syncthreads();  // (all threads meet here or at the barrier of the else branch)
         if (tid == 63) {  // the block's own factor: nobody reads the diagonal block any more
 #pragma unroll
           for (int i = 0; i < PNB; i++)
@@ -363,46 +357,38 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
       } else {
         __syncthreads();
       }
-      if (s_bad) {  // block-uniform
+      if (*s_bad) {  // block-uniform
         cp_async_wait_all();  // no prefetch may still be in flight when the sweep is retried
         __syncthreads();
         return false;
       }
       pf.lap(PH_C_DIAG);
-      // trailing update of the register tiles: C -= X_I X_J' over the 8 panel columns (loads of all tiles first)
-      {
-        double a0[4], a1[4], b0[4], b1[4];
-        bool act[4];
+      // trailing update of the register tiles: C -= X_I X_J' over the 8 panel columns (the negated panel entries of the
+      // row block are the A operand; lanes of the gradient tile row that hold no row read the zero row)
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int I = tI[q], J = tJ[q];
-          act[q] = I > b && J > b;  // (warp-uniform)
-          const bool arow_ok = act[q] && (I < 6 || g == 0);
-          const double* xa = Ms + (arow_ok ? 8 * I + g : 0) * LDMS + p0 + t;
-          const double* xb = Ms + (8 * (act[q] ? J : 0) + g) * LDMS + p0 + t;
-          a0[q] = arow_ok ? -xa[0] : 0.0; a1[q] = arow_ok ? -xa[4] : 0.0;
-          b0[q] = xb[0]; b1[q] = xb[4];
+      for (int q = 0; q < TPW; q++) {
+        const int I = tI[q], J = tJ[q];
+        if (I > b && J > b) {  // (warp-uniform)
+          const double* xa = Ms + ((I < 6 || g == 0) ? 8 * I + g : MS_ZROW) * LDMS + p0 + t;
+          const double* xb = Ms + (8 * J + g) * LDMS + p0 + t;
+          dmma(c[q][0], c[q][1], -xa[0], xb[0]);
+          dmma(c[q][0], c[q][1], -xa[4], xb[4]);
         }
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-          if (act[q]) dmma(c[q][0], c[q][1], a0[q], b0[q]);
-#pragma unroll
-        for (int q = 0; q < 4; q++)
-          if (act[q]) dmma(c[q][0], c[q][1], a1[q], b1[q]);
       }
       if (b + 1 < NS / PNB) {
         // the tiles of column b + 1 go to the panel buffer's columns i0 .. i0 + 7: disjoint from the columns
         // p0 .. p0 + 7 that the updates above read and that thread 63 writes, so no barrier in between
 #pragma unroll
-        for (int q = 0; q < 4; q++)
-          if (tI[q] > b && tJ[q] == b + 1) store_tile_ms(Ms, tI[q], b + 1, g, t, c[q][0], c[q][1]);
+        for (int q = 0; q < TPW; q++)
+          if (tJ[q] == b + 1 && tI[q] > b && (tI[q] < 6 || g == 0))
+            *reinterpret_cast<double2*>(Ms + (8 * tI[q] + g) * LDMS + 8 * tJ[q] + 2 * t) = make_double2(c[q][0], c[q][1]);
       }
       __syncthreads();
       pf.lap(PH_C_TRAIL);
     }
     // S5. P_k, p_k from the Schur-complement tiles; L | Yt | yv, r to the scratch for the forward sweep
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < TPW; q++) {
       const int I = tI[q], J = tJ[q];
       if (I < 3 || J < 3) continue;
 #pragma unroll
@@ -421,42 +407,65 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
       }
     }
     {
-      const int i = tid >> 3, c3 = 3 * (tid & 7);
       double* FY = w.FY + (long long)k * 1152;
       // rows 0-23: L (strict lower, 1/l_ii on the diagonal); rows 24-47: Yt
-#pragma unroll
-      for (int d = 0; d < 3; d++) ST_STREAM(&FY[i * NS + c3 + d], Ms[i * LDMS + c3 + d]);
-      if (i < 16) {
-#pragma unroll
-        for (int d = 0; d < 3; d++) ST_STREAM(&FY[(32 + i) * NS + c3 + d], Ms[(32 + i) * LDMS + c3 + d]);
-      }
-      if (tid >= 224 && tid < 224 + NS) w.yvf[k * 24 + tid - 224] = Ms[NW * LDMS + tid - 224];
-      else if (tid >= 192 && tid < 204) w.rf[k * 12 + tid - 192] = V[V_R + tid - 192];
+      for (int e = tid; e < NW * NS; e += NT) ST_STREAM(&FY[e], Ms[(e / NS) * LDMS + (e % NS)]);
+      if (tid >= NT - 32 && tid < NT - 32 + NS) w.yvf[k * 24 + tid - (NT - 32)] = Ms[NW * LDMS + tid - (NT - 32)];
+      else if (tid < 12) w.rf[k * 12 + tid] = V[V_R + tid];
     }
     pf.lap(PH_B_P6);
   }
+  return true;
+}
+
+__device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, double* smem, double dwreg) {
+  const int N = P.N, K = P.K, tid = TID, lane = tid & 31, warp = tid >> 5;
+  double* Pn = smem + SM_P;
+  double* Wm = smem + SM_W;
+  double* V = smem + SM_V;
+  __shared__ int s_ok, s_bad;
+  if (TID == 0) s_bad = 0;  // (visible after the barriers below)
+  prefetch_ct(w, K - 1, smem + SM_LB0 + ((K - 1) & 1) * CT_STRIDE);
+  // W: zero outside the structural entries of G^, identity E; terminal P_K, p_K
+  for (int i = tid; i < NS * LDP; i += NT) Pn[i] = 0.0;
+  for (int i = tid; i < NS * LDC; i += NT) Wm[i] = 0.0;
+  if (tid < NS) { V[V_PN + tid] = 0.0; V[V_Z + tid] = 0.0; }
+  if (tid < LDMS) smem[SM_MS + MS_ZROW * LDMS + tid] = 0.0;  // (beyond T, which shares the region: stays zero for the sweep)
+  __syncthreads();
+  if (tid < 12) {
+    const int r1 = tid < 6 ? 12 + tid : 24 + (tid - 6), r2 = r1 + 6;
+    const double q = w.x[12 * (N - 1) + tid];
+    const double ref = tid < 6 ? P.pb.q_term_ref[tid] : P.pb.qd_term_ref[tid - 6];
+    Pn[tid * LDP + tid] = 2.0 * P.pb.QN[tid] + w.SIG[r1] + w.SIG[r2] + dwreg;
+    V[V_PN + tid] = 2.0 * P.pb.QN[tid] * (q - ref) + w.YH[r1] + w.YH[r2];
+  } else if (tid < 24) {
+    Wm[tid * LDC + tid] = 1.0;  // E: c+ (stage variable 12 + j) is component 12 + j of the next stage's state
+  }
+  __syncthreads();
+  const bool ok = backward_stages(P, w, smem, dwreg, &s_bad);
+  if (!ok) return false;
   // free initial foot positions: Cholesky of P_0's (c,c) block (12 x 12) by warp 0, 1/l_ii on the diagonal
   __syncthreads();
   if (tid == 0) s_ok = 1;
-  double* M = Mc;
+  double* M = smem + SM_W;  // (W is rebuilt by the next sweep)
   for (int idx = tid; idx < 144; idx += NT) M[(idx / 12) * LDC + (idx % 12)] = Pn[(12 + idx / 12) * LDP + 12 + (idx % 12)];
   __syncthreads();
   if (tid < 32) {
-    bool ok = true;
-    for (int j = 0; j < 12 && ok; j++) {
+    bool ok2 = true;
+    for (int j = 0; j < 12 && ok2; j++) {
       double v = 0.0;
       if (lane >= j && lane < 12) {
         v = M[lane * LDC + j];
         for (int l = 0; l < j; l++) v -= M[lane * LDC + l] * M[j * LDC + l];
       }
       const double d = __shfl_sync(FULL, v, j);
-      if (!(d > 1e-14)) { ok = false; break; }
+      if (!(d > 1e-14)) { ok2 = false; break; }
       const double rs = rsqrt(d);
       if (lane == j) M[j * LDC + j] = rs;
       else if (lane > j && lane < 12) M[lane * LDC + j] = v * rs;
       __syncwarp();
     }
-    if (!ok && lane == 0) s_ok = 0;
+    if (!ok2 && lane == 0) s_ok = 0;
   }
   __syncthreads();
   if (!s_ok) return false;
@@ -466,31 +475,34 @@ __device__ __noinline__ bool backward_sweep(const KParams& P, const Ws& w, doubl
 }
 
 // ---------------------------------------------------------------- forward sweep
-// forward-stage buffer (doubles): FY 48x24 (L | Yt) | J list 388 | yv 24 | r 12 ; G (12x37) is rebuilt per stage
-constexpr int FB_FY = 0, FB_J = 1152, FB_YV = FB_J + NJ_PAD, FB_R = FB_YV + NS, FB_SIZE = FB_R + 12;
-static_assert(FB_SIZE <= NW * LDC && FB_SIZE <= 2 * NS * LDC, "forward buffers alias the backward regions");
+// forward-stage buffers (doubles): FY 48x24 (L | Yt) in the sweep regions | J list 388, yv 24, r 12 in the list region;
+// G (12x37) is rebuilt per stage in the P region
+constexpr int SB_J = 0, SB_YV = NJ_PAD, SB_R = SB_YV + NS, SB_SIZE = SB_R + 12;
+static_assert(2 * NW * NS <= SM_SWEEP - NS * LDP && 2 * SB_SIZE <= LB_REGION && 12 * LDG <= NS * LDP,
+              "forward buffers alias the backward regions");
 
-__device__ __forceinline__ void prefetch_factors(const Ws& w, int k, double* fb) {
-  const int tid = TID;
+__device__ __forceinline__ void prefetch_factors(const Ws& w, int k, double* fy, double* sb) {
   const double* FY = w.FY + (long long)k * 1152;
   const double* Jk = w.JL + (long long)k * NJ_PAD;
-  for (int i = tid; i < 576; i += NT) cp_async16(fb + FB_FY + 2 * i, FY + 2 * i);
-  if (tid < NJ_PAD / 2) cp_async16(fb + FB_J + 2 * tid, Jk + 2 * tid);
-  else if (tid < NJ_PAD / 2 + 12) { const int i = tid - NJ_PAD / 2; cp_async16(fb + FB_YV + 2 * i, w.yvf + k * 24 + 2 * i); }
-  else if (tid < NJ_PAD / 2 + 18) { const int i = tid - NJ_PAD / 2 - 12; cp_async16(fb + FB_R + 2 * i, w.rf + k * 12 + 2 * i); }
+  constexpr int C_F = 576, C_J = C_F + NJ_PAD / 2, C_Y = C_J + 12, C_END = C_Y + 6;
+  for (int i = TID; i < C_END; i += NT) {
+    if (i < C_F) cp_async16(fy + 2 * i, FY + 2 * i);
+    else if (i < C_J) cp_async16(sb + SB_J + 2 * (i - C_F), Jk + 2 * (i - C_F));
+    else if (i < C_Y) cp_async16(sb + SB_YV + 2 * (i - C_J), w.yvf + k * 24 + 2 * (i - C_J));
+    else cp_async16(sb + SB_R + 2 * (i - C_Y), w.rf + k * 12 + 2 * (i - C_Y));
+  }
   cp_async_commit();
 }
 
 // dx for all stages; equality multipliers of the initial-state rows into YN (dynamics costates: costates())
 __device__ __noinline__ void forward_sweep(const KParams& P, const Ws& w, double* smem, const double* drop) {
   const int N = P.N, K = P.K, tid = TID, lane = tid & 31, warp = tid >> 5;
-  double* fbuf[2] = {smem + SM_M, smem + SM_G};
   double* Pn = smem + SM_P;  // holds P_0 on entry; afterwards the dense G of the current stage
   double* V = smem + SM_V;
   double* xi = V + V_XI;
   double* u = V + V_U;
   double* rhs = V + V_Q;     // 24
-  const int* t_g = reinterpret_cast<const int*>(smem + SM_TBL) + P.tab.o_g;
+  const int* t_g = sweep_tables(P, smem) + P.tab.o_g;
   // initial state step and free initial feet
   if (tid < 12) xi[tid] = -(w.G[tid] - drop[tid]);
   __syncthreads();
@@ -521,35 +533,37 @@ __device__ __noinline__ void forward_sweep(const KParams& P, const Ws& w, double
     w.DS[tid] = 0.0;
   }
   __syncthreads();  // P_0 consumed: every backward region may now be overwritten
-  prefetch_factors(w, 0, fbuf[0]);
+  prefetch_factors(w, 0, smem + SM_W, smem + SM_LB0);
   double* Gs = Pn;
   for (int i = tid; i < 12 * LDG; i += NT) Gs[i] = 0.0;
   Prof pf{P.prof, 0};
   pf.start();
   for (int k = 0; k < K; k++) {
     const bool last = (k == K - 1);
-    const double* fb = fbuf[k & 1];
-    const double* Ls = fb + FB_FY;             // 24 x 24
-    const double* Ys = fb + FB_FY + NS * NS;   // Yt[i][c]
+    const double* Ls = smem + SM_W + (k & 1) * (NW * NS);  // 24 x 24
+    const double* Ys = Ls + NS * NS;                       // Yt[i][c]
+    const double* sb = smem + SM_LB0 + (k & 1) * SB_SIZE;
     cp_async_wait_all();
     __syncthreads();  // factors of stage k in shared memory, xi complete, previous G no longer read
     pf.lap(PH_F_WAIT);
     if (k == 0) { pf.lap(PH_CAL); pf.lap(PH_CAL); pf.lap(PH_CAL); pf.lap(PH_CAL); }  // (cost of the instrumentation itself)
-    if (!last) prefetch_factors(w, k + 1, fbuf[(k + 1) & 1]);
+    if (!last) prefetch_factors(w, k + 1, smem + SM_W + ((k + 1) & 1) * (NW * NS), smem + SM_LB0 + ((k + 1) & 1) * SB_SIZE);
     // rhs = -(Y xi + yv): thread (c, part) sums 6 terms, the 4 parts sit in neighbouring lanes | G | dx
-    if (tid < 96) {
-      const int c = tid >> 2, p = tid & 3;
+    for (int i = tid; i < 96; i += NT) {  // (whole warps: 96 and NT are multiples of 32)
+      const int c = i >> 2, p = i & 3;
       double v = 0.0;
 #pragma unroll
       for (int ii = 0; ii < 6; ii++) v += Ys[(4 * ii + p) * NS + c] * xi[4 * ii + p];
       v += __shfl_xor_sync(FULL, v, 1);
       v += __shfl_xor_sync(FULL, v, 2);
-      if (p == 0) rhs[c] = -(v + fb[FB_YV + c]);
-    } else if (tid < 96 + P.tab.n_g) {
-      const int e = t_g[tid - 96], t = e >> 10;
-      Gs[(t / 36) * LDG + (t % 36)] = -fb[FB_J + (e & 1023)];
-    } else if (tid >= 240 && tid < 252) {  // step of this knot's state / foot variables
-      const int i = tid - 240;
+      if (p == 0) rhs[c] = -(v + sb[SB_YV + c]);
+    }
+    for (int i = tid; i < P.tab.n_g; i += NT) {
+      const int e = tld(t_g + i), t = e >> 10;
+      Gs[(t / 36) * LDG + (t % 36)] = -sb[SB_J + (e & 1023)];
+    }
+    if (tid >= NT - 32 && tid < NT - 20) {  // step of this knot's state / foot variables
+      const int i = tid - (NT - 32);
       w.dx[12 * k + i] = xi[i];
       w.dx[12 * N + 24 * k + i] = xi[12 + i];
     }
@@ -592,7 +606,7 @@ __device__ __noinline__ void forward_sweep(const KParams& P, const Ws& w, double
           v += Gs[i * LDG + j] * (j < NS ? xi[j] : u[j - NS]);
         }
         v += __shfl_xor_sync(0x00ffffffu, v, 1);
-        xn = v + fb[FB_R + i];
+        xn = v + sb[SB_R + i];
       }
       __syncwarp();
       if (lane < NS && (lane & 1) == 0) xi[lane >> 1] = xn;
