@@ -205,6 +205,23 @@ void landing_tvlqr_default(landing_tvlqr *par);
 int landing_tvlqr_batch(landing_ctx *ctx, long long B, int memspace, const landing_tvlqr *par,
                         const double *x_star, double *P_out, double *K_out);
 
+/* Kino-dynamic ("full-body") landing NLP, the reference's KNITRO variant (SURVEY 8 f-2;
+ * generate_solver/generate_landingCtrller_KNITRO.m:34-193): +12 joint angles per knot, foot positions tied to the forward
+ * kinematics of the legs (get_forward_kin_foot.m:4-25), joint-torque limits tau = J_f' (-R' f) (get_foot_jacobians_mc.m:12-24),
+ * joint limits, XYZ rotation convention (rpyToRotMat_xyz.m:2).  Batched constraint values and sparse Jacobian (CCS value
+ * array, pattern from landing_kino_sparsity) -- the functions an NLP solver iterates on; the interior-point kernel itself
+ * solves the SRB formulations only.  x[B x n_x] = [X(:); jpos(:); U(:)] per scenario (Opti variable order :45-51),
+ * g[B x m], jac[B x nnz]; dims = {N, n_x = 12N + 36(N-1), m = 48 + 141(N-2) + 117, nnz}.  The row map and the bounds
+ * lbg / ubg are restated in oracle/kino_ref.py (pinned to the stored solution generate_solver/prevSoln.mat). */
+typedef struct landing_kino_problem {
+  double mu, mass, Ib[3], Ib_inv[3];
+  const double *dt; /* HOST pointer to N-1 knot spacings */
+} landing_kino_problem;
+int landing_kino_dims(int n_knots, long long dims[4]);
+const long long *landing_kino_sparsity(int n_knots); /* CCS {nrow, ncol, colind[ncol+1], row[nnz]}, host, library-owned */
+int landing_kino_eval_batch(landing_ctx *ctx, long long B, int memspace, int layout, const landing_kino_problem *pb,
+                            const double *x, double *g, double *jac);
+
 /* Measured FP64 FMA throughput of the context's device in TFLOP/s (a DFMA micro-kernel timed with CUDA
  * events): the roofline denominator of the interior-point kernel, which is FP64-pipe bound by design. */
 int landing_fp64_peak(landing_ctx *ctx, double *tflops);

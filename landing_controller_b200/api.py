@@ -61,6 +61,12 @@ class Tvlqr(ctypes.Structure):
                 ("Ib", ctypes.c_double * 9), ("mass", ctypes.c_double)]
 
 
+class KinoProblem(ctypes.Structure):
+    """landing_kino_problem: shared numeric data of the kino-dynamic NLP (generate_landingCtrller_KNITRO.m:224-262)."""
+    _fields_ = [("mu", ctypes.c_double), ("mass", ctypes.c_double), ("Ib", ctypes.c_double * 3),
+                ("Ib_inv", ctypes.c_double * 3), ("dt", _dp)]
+
+
 class SolveIO(ctypes.Structure):
     _fields_ = [("drops", _dp), ("x0", _dp), ("x_star", _dp), ("f_star", _dp), ("lam_g", _dp),
                 ("viol", _dp), ("status", _ip), ("iters", _ip)]
@@ -86,6 +92,12 @@ def load_library(path=LIB_PATH):
     lib.landing_solve_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int,
                                         ctypes.POINTER(Problem), ctypes.POINTER(Options),
                                         ctypes.POINTER(SolveIO)]
+    if hasattr(lib, "landing_kino_eval_batch"):
+        lib.landing_kino_dims.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]
+        lib.landing_kino_sparsity.restype = ctypes.POINTER(ctypes.c_longlong)
+        lib.landing_kino_sparsity.argtypes = [ctypes.c_int]
+        lib.landing_kino_eval_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                                ctypes.POINTER(KinoProblem), _dp, _dp, _dp]
     lib.landing_launch_count.restype = ctypes.c_longlong
     lib.landing_launch_count.argtypes = [ctypes.c_void_p]
     if hasattr(lib, "landing_fp64_peak"):
@@ -319,6 +331,52 @@ class LandingSolver:
         self._check(self.lib.landing_tvlqr_batch(self.ctx, B, HOST, ctypes.byref(par), _ptr(x), _ptr(P), _ptr(K)),
                     "landing_tvlqr_batch")
         return (P, K) if want_K else P
+
+    # ---- kino-dynamic ("full-body") NLP of the reference's KNITRO variant
+    def kino_dims(self):
+        d = (ctypes.c_longlong * 4)()
+        self._check(self.lib.landing_kino_dims(self.N, d), "landing_kino_dims")
+        return {"N": int(d[0]), "nx": int(d[1]), "m": int(d[2]), "nnzJ": int(d[3])}
+
+    def kino_sparsity(self):
+        """CCS pattern of dg/dx: (colind [nx + 1], row [nnz])."""
+        d = self.kino_dims()
+        sp = self.lib.landing_kino_sparsity(self.N)
+        a = np.ctypeslib.as_array(sp, shape=(2 + d["nx"] + 1 + d["nnzJ"],))
+        return a[2:2 + d["nx"] + 1].copy(), a[2 + d["nx"] + 1:].copy()
+
+    def kino_problem(self, dt, mu=0.75, mass=None, Ib=None, Ib_inv=None):
+        """Parameter values of generate_landingCtrller_KNITRO.m:224-262 (mass / inertia as in landing_problem)."""
+        pb = KinoProblem()
+        pb.mu = mu
+        pb.mass = self.problem.mass if mass is None else mass
+        for i in range(3):
+            pb.Ib[i] = self.problem.Ib[i] if Ib is None else Ib[i]
+            pb.Ib_inv[i] = self.problem.Ib_inv[i] if Ib_inv is None else Ib_inv[i]
+        self._kino_dt = np.ascontiguousarray(dt, dtype=np.float64)
+        if self._kino_dt.shape != (self.N - 1,):
+            raise ValueError("dt must have N-1 = %d entries" % (self.N - 1))
+        pb.dt = self._kino_dt.ctypes.data_as(_dp)
+        return pb
+
+    def kino_eval_host(self, x, pb, want_g=True, want_jac=True, layout=AOS):
+        """g [B, m] and the CCS value array of dg/dx [B, nnz] of the kino-dynamic NLP for a batch of
+        x = [X(:); jpos(:); U(:)] (host arrays; layout SOA: [n, B])."""
+        d = self.kino_dims()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        B = x.shape[0] if layout == AOS else x.shape[1]
+        shp = (lambda n: (B, n)) if layout == AOS else (lambda n: (n, B))
+        g = np.zeros(shp(d["m"])) if want_g else None
+        jac = np.zeros(shp(d["nnzJ"])) if want_jac else None
+        self._check(self.lib.landing_kino_eval_batch(self.ctx, B, HOST, layout, ctypes.byref(pb), _ptr(x), _ptr(g), _ptr(jac)),
+                    "landing_kino_eval_batch")
+        return g, jac
+
+    def kino_eval_device(self, x, pb, g=None, jac=None, layout=SOA):
+        """Same with CUDA torch tensors already in HBM (enqueued on the library stream)."""
+        B = x.shape[0] if layout == AOS else x.shape[1]
+        self._check(self.lib.landing_kino_eval_batch(self.ctx, B, DEVICE, layout, ctypes.byref(pb), _ptr(x), _ptr(g), _ptr(jac)),
+                    "landing_kino_eval_batch")
 
     def synchronize(self):
         self._check(self.lib.landing_synchronize(self.ctx), "landing_synchronize")

@@ -3,7 +3,9 @@
 // every entry point that produces numbers needs a CUDA device and fails loudly without one.
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -56,6 +58,9 @@ struct landing_ctx {
   // contact schedule of the current call (formulation 1): bit mask per knot
   unsigned char* h_cs = nullptr;
   unsigned char* d_cs = nullptr;
+  // kino-dynamic NLP (landing_kino_eval_batch): host plan and its device tables, made on first use
+  std::shared_ptr<const KinoPlan> kino;
+  int* d_kino = nullptr;
 };
 
 // dt[0..N-2] of this call on the device (stream-ordered): the caller's vector or the uniform T/(N-1)
@@ -179,6 +184,7 @@ void landing_destroy(landing_ctx* c) {
   if (c->h_dt) cudaFreeHost(c->h_dt);
   if (c->d_cs) cudaFree(c->d_cs);
   if (c->h_cs) cudaFreeHost(c->h_cs);
+  if (c->d_kino) cudaFree(c->d_kino);
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -198,6 +204,77 @@ int landing_synchronize(landing_ctx* c) {
   if (!c) return fail(LANDING_ERR_ARG, "landing_synchronize: null ctx");
   DeviceGuard guard_(c->device);
   CU(cudaStreamSynchronize(c->stream));
+  return LANDING_OK;
+}
+
+// ---------------------------------------------------------------- kino-dynamic NLP
+static std::shared_ptr<const KinoPlan> get_kino_plan(int N) {
+  static std::mutex mu;
+  static std::map<int, std::shared_ptr<const KinoPlan>> cache;
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(N);
+  if (it != cache.end()) return it->second;
+  auto pl = std::make_shared<const KinoPlan>(make_kino_plan(N));
+  cache[N] = pl;
+  return pl;
+}
+
+int landing_kino_dims(int N, long long d[4]) {
+  if (N < 3 || !d) return fail(LANDING_ERR_ARG, "landing_kino_dims: need N >= 3");
+  auto pl = get_kino_plan(N);
+  d[0] = N; d[1] = pl->nx; d[2] = pl->m; d[3] = pl->nnz;
+  return LANDING_OK;
+}
+
+const long long* landing_kino_sparsity(int N) { return N < 3 ? nullptr : get_kino_plan(N)->sparsity.data(); }
+
+int landing_kino_eval_batch(landing_ctx* c, long long B, int memspace, int layout, const landing_kino_problem* pb,
+                            const double* x, double* g, double* jac) {
+  if (!c || !pb || !pb->dt || !x || B < 0) return fail(LANDING_ERR_ARG, "landing_kino_eval_batch: bad arguments");
+  if (B == 0 || (!g && !jac)) return LANDING_OK;
+  DeviceGuard guard_(c->device);
+  if (!c->kino) {
+    auto pl = get_kino_plan(c->N);
+    const size_t n = pl->gpos.size() + pl->bpos.size();
+    CU(cudaMalloc(&c->d_kino, sizeof(int) * n));
+    CU(cudaMemcpy(c->d_kino, pl->gpos.data(), sizeof(int) * pl->gpos.size(), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(c->d_kino + pl->gpos.size(), pl->bpos.data(), sizeof(int) * pl->bpos.size(), cudaMemcpyHostToDevice));
+    c->kino = pl;
+  }
+  const KinoPlan& pl = *c->kino;
+  // knot spacings through the same staging as the solver's
+  landing_problem tmp{};
+  tmp.dt = pb->dt;
+  int rc = stage_dt(c, &tmp);
+  if (rc) return rc;
+  const double* dx = x;
+  double *dg = g, *dj = jac;
+  if (memspace == LANDING_HOST) {
+    const size_t bx = sizeof(double) * pl.nx * B, bg = g ? sizeof(double) * pl.m * B : 0, bj = jac ? sizeof(double) * pl.nnz * B : 0;
+    rc = ensure_stage(c, bx + bg + bj + 256);
+    if (rc) return rc;
+    char* s = (char*)c->stage;
+    CU(cudaMemcpyAsync(s, x, bx, cudaMemcpyHostToDevice, c->stream));
+    dx = (const double*)s;
+    dg = g ? (double*)(s + bx) : nullptr;
+    dj = jac ? (double*)(s + bx + bg) : nullptr;
+  }
+  KinoArgs a{};
+  a.N = c->N; a.B = B;
+  a.x = make_cview(dx, pl.nx, B, layout);
+  a.g = make_view(dg, pl.m, B, layout);
+  a.jac = make_view(dj, pl.nnz, B, layout);
+  a.pr.mu = pb->mu; a.pr.mass = pb->mass;
+  for (int i = 0; i < 3; i++) { a.pr.Ib[i] = pb->Ib[i]; a.pr.Ib_inv[i] = pb->Ib_inv[i]; }
+  a.dtv = c->d_dt;
+  a.gpos = c->d_kino; a.bpos = c->d_kino + pl.gpos.size();
+  c->launches += launch_kino(a, dg != nullptr, dj != nullptr, c->stream);
+  CU(cudaGetLastError());
+  if (memspace == LANDING_HOST) {
+    if (g) CU(cudaMemcpyAsync(g, dg, sizeof(double) * pl.m * B, cudaMemcpyDeviceToHost, c->stream));
+    if (jac) CU(cudaMemcpyAsync(jac, dj, sizeof(double) * pl.nnz * B, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+  }
   return LANDING_OK;
 }
 

@@ -2,7 +2,10 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <vector>
+
 #include "../../include/landing_b200.h"
+#include "kino_knot.cuh"
 #include "plan.cuh"
 
 namespace srb {
@@ -54,6 +57,26 @@ struct TvlqrArgs {
   landing_tvlqr par;
 };
 int launch_tvlqr(const TvlqrArgs& a, long long B, cudaStream_t st);
+
+// kino-dynamic NLP (kino.cu): host plan (sizes, CCS pattern, scatter tables) and the batched evaluation
+struct KinoPlan {
+  int N = 0;
+  long long nx = 0, m = 0, nnz = 0;
+  std::vector<long long> sparsity;  // CasADi CCS {nrow, ncol, colind[ncol+1], row[nnz]}
+  std::vector<int> gpos;            // [knot][local input 72][local row 141] -> CCS position or -1
+  std::vector<int> bpos;            // the 48 boundary rows' (identity) entries
+};
+KinoPlan make_kino_plan(int N);
+struct KinoArgs {
+  int N;
+  long long B;
+  CView x;
+  View g, jac;
+  kino::Params pr;
+  const double* dtv;  // knot spacings (device)
+  const int *gpos, *bpos;
+};
+int launch_kino(const KinoArgs& a, bool want_g, bool want_jac, cudaStream_t st);
 
 // returns number of kernel launches issued
 int launch_eval(const EvalArgs& a, cudaStream_t st);

@@ -1,0 +1,162 @@
+// kino.cu -- batched evaluation of the kino-dynamic ("full-body") landing NLP of the reference's KNITRO variant
+// (generate_solver/generate_landingCtrller_KNITRO.m:34-193): constraint values g and the sparse Jacobian
+// dg/dx in CCS order for a whole batch of trajectories.  One thread = one (scenario, knot); with the SoA layout every
+// load and store of a warp is one coalesced 256-byte transaction.  The Jacobian columns are exact forward-mode
+// derivatives of the same knot function (kino_knot.cuh, Dual1): one pass per knot-local input, spread over blockIdx.z.
+//
+// x = [X(:) (12 N); jpos(:) (12 (N-1)); U(:) (24 (N-1))], g rows: 48 boundary rows, then 141 per knot (117 for the
+// last) -- the row map is in oracle/kino_ref.py, which is pinned to the solution of this NLP that the reference stores.
+#include <algorithm>
+#include <map>
+#include <random>
+#include <vector>
+
+#include "kernels.cuh"
+#include "kino_knot.cuh"
+
+namespace srb {
+namespace {
+
+using kino::Dual1;
+using kino::NIN;
+using kino::ROWS_INT;
+using kino::ROWS_LAST;
+
+__host__ __device__ inline long long kino_col(int N, int k, int v) {  // knot-local input v of knot k -> column of x
+  if (v < 12) return 12LL * k + v;
+  if (v < 24) return 12LL * N + 12LL * k + (v - 12);
+  if (v < 48) return 12LL * N + 12LL * (N - 1) + 24LL * k + (v - 24);
+  if (v < 60) return 12LL * (k + 1) + (v - 48);
+  return 12LL * N + 12LL * (N - 1) + 24LL * (k + 1) + (v - 60);
+}
+
+struct GSink {
+  View g;
+  long long b, base;
+  __device__ __forceinline__ void operator()(int rho, double v) { g.at(base + rho, b) = v; }
+};
+struct JSink {
+  View jac;
+  long long b;
+  const int* gp;  // CCS position of (row rho, this column) or -1
+  __device__ __forceinline__ void operator()(int rho, Dual1 v) {
+    const int p = __ldg(gp + rho);
+    if (p >= 0) jac.at(p, b) = v.d;
+  }
+};
+
+__global__ void __launch_bounds__(128) k_kino_g(KinoArgs a) {
+  const long long b = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (b >= a.B) return;
+  const int N = a.N, k = blockIdx.y;
+  const bool last = k == N - 2;
+  double in[NIN];
+#pragma unroll 4
+  for (int v = 0; v < NIN; v++) in[v] = (last && v >= 60) ? 0.0 : a.x.get(kino_col(N, k, v), b);
+  GSink s{a.g, b, 48 + (long long)ROWS_INT * k};
+  kino::knot_rows<double>(in, __ldg(a.dtv + k), a.pr, last, s);
+  if (k == 0) {  // boundary rows: q_0, qd_0, c_0 | q_{N-1} twice | qd_{N-1} twice   (:93-101)
+    for (int i = 0; i < 12; i++) a.g.at(i, b) = in[i];
+    for (int i = 0; i < 12; i++) a.g.at(12 + i, b) = in[24 + i];
+    for (int i = 0; i < 6; i++) {
+      const double q = a.x.get(12LL * (N - 1) + i, b), qd = a.x.get(12LL * (N - 1) + 6 + i, b);
+      a.g.at(24 + i, b) = q; a.g.at(30 + i, b) = q;
+      a.g.at(36 + i, b) = qd; a.g.at(42 + i, b) = qd;
+    }
+  }
+}
+
+// blockIdx.z = slice of the knot-local inputs (NIN / gridDim.z each)
+__global__ void __launch_bounds__(128) k_kino_jac(KinoArgs a) {
+  const long long b = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (b >= a.B) return;
+  const int N = a.N, k = blockIdx.y;
+  const bool last = k == N - 2;
+  double x[NIN];
+#pragma unroll 4
+  for (int v = 0; v < NIN; v++) x[v] = (last && v >= 60) ? 0.0 : a.x.get(kino_col(N, k, v), b);
+  const int per = NIN / gridDim.z, v0 = per * blockIdx.z;
+  const double h = __ldg(a.dtv + k);
+  for (int v = v0; v < v0 + per; v++) {
+    if (last && v >= 60) break;
+    Dual1 in[NIN];
+#pragma unroll 4
+    for (int i = 0; i < NIN; i++) in[i] = Dual1(x[i], i == v ? 1.0 : 0.0);
+    JSink s{a.jac, b, a.gpos + ((long long)k * NIN + v) * ROWS_INT};
+    kino::knot_rows<Dual1>(in, h, a.pr, last, s);
+  }
+  if (k == 0 && blockIdx.z == 0)
+    for (int i = 0; i < 48; i++) a.jac.at(__ldg(a.bpos + i), b) = 1.0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host: pattern and CCS tables
+KinoPlan make_kino_plan(int N) {
+  KinoPlan pl;
+  pl.N = N;
+  pl.nx = 12LL * N + 36LL * (N - 1);
+  pl.m = 48 + (long long)ROWS_INT * (N - 2) + ROWS_LAST;
+  const int K = N - 1;
+  // knot-local pattern by probing the knot function with tangents at random points (both knot classes)
+  std::mt19937_64 rng(12345);
+  std::uniform_real_distribution<double> U(-1.0, 1.0);
+  kino::Params pr{0.75, 8.252, {0.0576, 0.234, 0.28}, {17.4, 4.27, 3.58}};
+  std::vector<char> pat[2];
+  for (int cls = 0; cls < 2; cls++) {
+    const bool last = cls == 1;
+    pat[cls].assign((size_t)NIN * ROWS_INT, 0);
+    for (int rep = 0; rep < 3; rep++) {
+      double xv[NIN];
+      for (int i = 0; i < NIN; i++) xv[i] = U(rng);
+      for (int v = 0; v < NIN; v++) {
+        if (last && v >= 60) continue;
+        Dual1 in[NIN];
+        for (int i = 0; i < NIN; i++) in[i] = Dual1(xv[i], i == v ? 1.0 : 0.0);
+        auto sink = [&](int rho, Dual1 d) { if (d.d != 0.0) pat[cls][(size_t)v * ROWS_INT + rho] = 1; };
+        kino::knot_rows<Dual1>(in, 0.03, pr, last, sink);
+      }
+    }
+  }
+  // global entries (col, row) -> CCS order
+  struct E { long long col, row; int k, v, rho; };
+  std::vector<E> ent;
+  auto bnd = [&](int row, long long col) { ent.push_back({col, row, -1, row, 0}); };
+  for (int i = 0; i < 12; i++) bnd(i, i);
+  for (int i = 0; i < 12; i++) bnd(12 + i, 12LL * N + 12LL * (N - 1) + i);
+  for (int i = 0; i < 6; i++) {
+    bnd(24 + i, 12LL * (N - 1) + i); bnd(30 + i, 12LL * (N - 1) + i);
+    bnd(36 + i, 12LL * (N - 1) + 6 + i); bnd(42 + i, 12LL * (N - 1) + 6 + i);
+  }
+  for (int k = 0; k < K; k++) {
+    const int cls = k == K - 1;
+    for (int v = 0; v < NIN; v++)
+      for (int rho = 0; rho < ROWS_INT; rho++)
+        if (pat[cls][(size_t)v * ROWS_INT + rho]) ent.push_back({kino_col(N, k, v), 48 + (long long)ROWS_INT * k + rho, k, v, rho});
+  }
+  std::sort(ent.begin(), ent.end(), [](const E& a, const E& b) { return a.col != b.col ? a.col < b.col : a.row < b.row; });
+  pl.nnz = (long long)ent.size();
+  pl.sparsity.assign(2 + pl.nx + 1 + pl.nnz, 0);
+  pl.sparsity[0] = pl.m; pl.sparsity[1] = pl.nx;
+  pl.gpos.assign((size_t)K * NIN * ROWS_INT, -1);
+  pl.bpos.assign(48, 0);
+  for (long long p = 0; p < pl.nnz; p++) {
+    const E& e = ent[p];
+    pl.sparsity[2 + e.col + 1] += 1;
+    pl.sparsity[2 + pl.nx + 1 + p] = e.row;
+    if (e.k < 0) pl.bpos[e.v] = (int)p;
+    else pl.gpos[((size_t)e.k * NIN + e.v) * ROWS_INT + e.rho] = (int)p;
+  }
+  for (long long c = 0; c < pl.nx; c++) pl.sparsity[2 + c + 1] += pl.sparsity[2 + c];
+  return pl;
+}
+
+int launch_kino(const KinoArgs& a, bool want_g, bool want_jac, cudaStream_t st) {
+  int n = 0;
+  const unsigned gx = (unsigned)((a.B + 127) / 128);
+  if (want_g) { k_kino_g<<<dim3(gx, a.N - 1, 1), 128, 0, st>>>(a); n++; }
+  if (want_jac) { k_kino_jac<<<dim3(gx, a.N - 1, 8), 128, 0, st>>>(a); n++; }
+  return n;
+}
+
+}  // namespace srb

@@ -254,20 +254,29 @@ __device__ __noinline__ bool backward_stages(const KParams& P, const Ws& w, doub
     if (tid >= NT - 32 && tid < NT - 20) V[V_R + tid - (NT - 32)] = cb[CT_R + tid - (NT - 32)];
     __syncthreads();
     pf.lap(PH_B_P1);
-    // S2. T = P W (24 x 48), tiles warp, warp + NWARP, ... of the 3 x 6 grid; t = P [r; 0] + p into column 48 of W
+    // S2. T = P W (24 x 48), tiles warp, warp + NWARP, ... of the 3 x 6 grid (their DMMA chains interleaved k-step by
+    // k-step: a dependent DMMA takes 26 cycles, an independent one issues every 17); t = P [r; 0] + p into column 48 of W
+    {
+      const double *pa2[TQ2], *pb2[TQ2];
+      unsigned mk2[TQ2];
+      double c2[TQ2][2];
 #pragma unroll
-    for (int q = 0; q < TQ2; q++) {
-      const int tile = warp + NWARP * q;
-      if (tile < 18) {  // (warp-uniform)
-        const int I = tile / 6, J = tile - 6 * I;
-        const unsigned mk = w_mask_rt(J);
-        const double* pa = Pn + (8 * I + g) * LDP + t;
-        const double* pb = Wm + t * LDC + 8 * J + g;
-        double c0 = 0.0, c1 = 0.0;
+      for (int q = 0; q < TQ2; q++) {
+        const int tile = warp + NWARP * q, I = tile / 6, J = tile - 6 * I;
+        mk2[q] = tile < 18 ? w_mask_rt(J) : 0u;  // (warp-uniform)
+        pa2[q] = Pn + (8 * (tile < 18 ? I : 0) + g) * LDP + t;
+        pb2[q] = Wm + t * LDC + 8 * (tile < 18 ? J : 0) + g;
+        c2[q][0] = 0.0; c2[q][1] = 0.0;
+      }
 #pragma unroll
-        for (int s2 = 0; s2 < 6; s2++)
-          if (mk >> s2 & 1) dmma(c0, c1, pa[4 * s2], pb[4 * s2 * LDC]);
-        *reinterpret_cast<double2*>(Ts + (8 * I + g) * LDC + 8 * J + 2 * t) = make_double2(c0, c1);
+      for (int s2 = 0; s2 < 6; s2++)
+#pragma unroll
+        for (int q = 0; q < TQ2; q++)
+          if (mk2[q] >> s2 & 1) dmma(c2[q][0], c2[q][1], pa2[q][4 * s2], pb2[q][4 * s2 * LDC]);
+#pragma unroll
+      for (int q = 0; q < TQ2; q++) {
+        const int tile = warp + NWARP * q, I = tile / 6, J = tile - 6 * I;
+        if (tile < 18) *reinterpret_cast<double2*>(Ts + (8 * I + g) * LDC + 8 * J + 2 * t) = make_double2(c2[q][0], c2[q][1]);
       }
     }
     if (warp == NWARP - 1 && lane < NS) {
@@ -284,24 +293,28 @@ __device__ __noinline__ bool backward_stages(const KParams& P, const Ws& w, doub
     // S3. accumulator tiles: M = Mc + W'T (rows 0..47), q + W't (row 48 = lane group 0 of tile row 6: the A operand
     // is column 48 + g of W, i.e. t for g = 0 and zeros for g = 1..3; lane groups 4..7 read past the row and produce
     // numbers in accumulator rows 52..55 that nothing ever uses)
+    {
+      const double *pa3[TPW], *pb3[TPW];
 #pragma unroll
-    for (int q = 0; q < TPW; q++) {
-      const int I = tI[q], J = tJ[q];
-      const unsigned lo = (unsigned)tin[q] & 0xffffu, hi = (unsigned)tin[q] >> 16;
-      double m0 = lo == 0xffffu ? 0.0 : cb[lo], m1 = hi == 0xffffu ? 0.0 : cb[hi];
-      if (I == J) {  // diagonal: delta_w on (f, X, c), the dummy c+ of the last stage
-        const int row = 8 * I + g, col = 8 * J + 2 * t;
-        const double d = (row >= 12 && row < 24) ? (k == K - 1 ? 1.0 : 0.0) : dwreg;
-        if (row == col) m0 += d;
-        if (row == col + 1) m1 += d;
+      for (int q = 0; q < TPW; q++) {
+        const int I = tI[q], J = tJ[q];
+        const unsigned lo = (unsigned)tin[q] & 0xffffu, hi = (unsigned)tin[q] >> 16;
+        double m0 = lo == 0xffffu ? 0.0 : cb[lo], m1 = hi == 0xffffu ? 0.0 : cb[hi];
+        if (I == J) {  // diagonal: delta_w on (f, X, c), the dummy c+ of the last stage
+          const int row = 8 * I + g, col = 8 * J + 2 * t;
+          const double d = (row >= 12 && row < 24) ? (k == K - 1 ? 1.0 : 0.0) : dwreg;
+          if (row == col) m0 += d;
+          if (row == col + 1) m1 += d;
+        }
+        c[q][0] = m0; c[q][1] = m1;
+        pa3[q] = Wm + t * LDC + 8 * (I < 0 ? 0 : I) + g;
+        pb3[q] = (I == 6 ? Wm : Ts) + t * LDC + 8 * J + g;
       }
-      c[q][0] = m0; c[q][1] = m1;
-      const double* pa = Wm + t * LDC + 8 * (I < 0 ? 0 : I) + g;
-      const double* pb = (I == 6 ? Wm : Ts) + t * LDC + 8 * J + g;
-      const unsigned mk = mk3[q];
 #pragma unroll
       for (int s2 = 0; s2 < 6; s2++)
-        if (mk >> s2 & 1) dmma(c[q][0], c[q][1], pa[4 * s2 * LDC], pb[4 * s2 * LDC]);
+#pragma unroll
+        for (int q = 0; q < TPW; q++)
+          if (mk3[q] >> s2 & 1) dmma(c[q][0], c[q][1], pa3[q][4 * s2 * LDC], pb3[q][4 * s2 * LDC]);
     }
     __syncthreads();  // T is dead: its region becomes the panel buffer
 #pragma unroll

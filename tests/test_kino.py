@@ -1,0 +1,114 @@
+"""Kino-dynamic ("full-body") landing NLP, the reference's KNITRO variant.
+
+CPU: the numpy restatement oracle/kino_ref.py against the solutions of this NLP that the reference stores
+(generate_solver/prevSoln.mat, main_scripts/prevSoln.mat -> tests/golden/kino_n21.npz by make_kino_golden.py):
+every one of the 2844 restated rows is feasible at the stored points, and the stored multipliers make the stored point
+stationary for the restated Jacobian -- which pins row order, signs, the XYZ rotation convention, the leg kinematics
+and the torque rows.  GPU: the batched CUDA evaluation (g and the CCS Jacobian) against that oracle."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import kino_ref as kr  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden", "kino_n21.npz")
+
+
+def stored(tag):
+    d = np.load(GOLD)
+    x, lam = d[tag + "_x"], d[tag + "_lam_g"]
+    pb = kr.default_problem(21)
+    X, _, U = kr.split(x, 21)
+    vb = kr.rpy_to_rot_xyz(X[0, 3:6]).T @ X[0, 9:12]  # generate_landingCtrller_KNITRO.m:255-257
+    pb["kin_box"] = np.array([kr.kin_box_limits(vb[0], "x"), kr.kin_box_limits(vb[1], "y")])
+    return pb, x, lam, (X[0, :6].copy(), X[0, 6:].copy(), U[0, :12].copy())
+
+
+def test_sizes_match_the_stored_artefacts():
+    d = kr.dims(21)
+    assert d["nx"] == 972 and d["m"] == 2844  # data_param.mat output_mean, prevSoln.mat lam_g_star
+    assert np.load(GOLD)["ms_lam_g"].shape == (2844,)
+
+
+def test_closed_form_leg_kinematics_equal_the_spatial_chain():
+    rng = np.random.default_rng(1)
+    for _ in range(20):
+        q = np.concatenate([rng.normal(size=3), rng.uniform(-1, 1, 3), rng.uniform(-1.5, 2.5, 12)])
+        lit = kr.forward_kin_foot_literal(q)  # get_forward_kin_foot.m on the 18-body model
+        R = kr.rpy_to_rot_xyz(q[3:6])
+        for l in range(4):
+            assert np.allclose(q[:3] + R @ kr.leg_fk_body(l, q[6 + 3 * l:9 + 3 * l]), lit[l], atol=1e-14)
+    # home pose of the model (get_robot_model.m:147): feet under the hips, symmetric
+    feet = kr.forward_kin_foot_literal(np.concatenate([np.zeros(6), np.tile([0, -1.45, 2.65], 4)]))
+    assert np.allclose(feet[0] * [1, -1, 1], feet[1]) and np.allclose(feet[2] * [1, -1, 1], feet[3])
+
+
+@pytest.mark.parametrize("tag,tol", [("ms", 1e-6), ("gs", 5e-5)])
+def test_stored_knitro_solutions_are_feasible_for_the_restated_rows(tag, tol):
+    pb, x, _, (q0, qd0, c0) = stored(tag)
+    g = kr.eval_g(pb, x)
+    lb, ub = kr.bounds(pb, q0, qd0, c0)
+    assert g.shape == (2844,) and np.all(lb <= ub)
+    viol = np.maximum(np.maximum(lb - g, g - ub), 0.0)
+    assert viol.max() <= tol, (viol.max(), int(viol.argmax()))
+    # the equality rows (dynamics) hold to the solver's tolerance, the foot positions follow the leg kinematics to 1 cm
+    for k in range(20):
+        assert np.abs(g[48 + 141 * k:48 + 141 * k + 12]).max() <= tol
+
+
+def test_stored_knitro_point_is_stationary_for_the_restated_jacobian():
+    pb, x, lam, _ = stored("ms")
+    J = kr.jac_fd(pb, x)
+    r = J.T @ lam
+    QN = np.array([0, 0, 100, 10, 10, 0, 10, 10, 10, 10, 10, 10.0])         # :260
+    ref = np.array([0, 0, 0.25, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])              # :236-237
+    r[240:252] += 2 * QN * (x[240:252] - ref)                              # grad f lives on X_{N-1} only (:86-88)
+    scale = np.abs(J.T * lam).max()
+    assert scale > 1e-2 and np.abs(r).max() <= 1e-4 * scale, (np.abs(r).max(), scale)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [21, 30])
+def test_gpu_kino_functions_match_the_oracle(N):
+    import landing_controller_b200 as lc
+    s = lc.LandingSolver(N=N, device=0)
+    d = s.kino_dims()
+    assert d["nx"] == kr.dims(N)["nx"] and d["m"] == kr.dims(N)["m"]
+    pbo = kr.default_problem(N)
+    pb = s.kino_problem(pbo["dt"], mu=pbo["mu"], mass=pbo["mass"], Ib=pbo["Ib"], Ib_inv=pbo["Ib_inv"])
+    rng = np.random.default_rng(N)
+    B = 5
+    if N == 21:  # the stored solution and perturbations of it
+        _, xs, _, _ = stored("ms")
+        x = xs[None, :] + 0.05 * rng.normal(size=(B, d["nx"]))
+        x[0] = xs
+    else:
+        x = rng.uniform(-0.6, 0.6, size=(B, d["nx"]))
+    g, jac = s.kino_eval_host(x, pb)
+    colind, row = s.kino_sparsity()
+    assert colind[-1] == d["nnzJ"] == jac.shape[1] and np.all(np.diff(colind) >= 0)
+    for b in range(B):
+        go = kr.eval_g(pbo, x[b])
+        assert np.max(np.abs(g[b] - go) / np.maximum(1.0, np.abs(go))) <= 1e-12
+    # Jacobian: dense from CCS against central differences of the oracle (one scenario; FD error ~1e-7)
+    b = 0
+    Jd = np.zeros((d["m"], d["nx"]))
+    for c in range(d["nx"]):
+        Jd[row[colind[c]:colind[c + 1]], c] = jac[b, colind[c]:colind[c + 1]]
+    cols = np.sort(rng.choice(d["nx"], size=240, replace=False))
+    Jo = kr.jac_fd(pbo, x[b], cols=cols, literal=False)
+    assert np.max(np.abs(Jd[:, cols] - Jo[:, cols])) <= 2e-6 * max(1.0, np.abs(Jo).max())
+    assert np.count_nonzero(np.abs(Jo[:, cols]) > 1e-9) <= np.count_nonzero(Jd[:, cols]) + 0  # nothing outside the pattern
+    # SoA layout gives the same numbers
+    g2, j2 = s.kino_eval_host(np.ascontiguousarray(x.T), pb, layout=lc.SOA)
+    assert np.array_equal(g2.T, g) and np.array_equal(j2.T, jac)
+    if N == 21:  # the stored multipliers make the stored point stationary for the GPU Jacobian too
+        _, xs, lam, _ = stored("ms")
+        r = Jd.T @ lam
+        QN = np.array([0, 0, 100, 10, 10, 0, 10, 10, 10, 10, 10, 10.0])
+        r[240:252] += 2 * QN * (xs[240:252] - np.array([0, 0, 0.25, 0, 0, 0, 0, 0, 0, 0, 0, 0.0]))
+        assert np.abs(r).max() <= 1e-4 * np.abs(Jd.T * lam).max()
