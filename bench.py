@@ -476,7 +476,7 @@ def main():
             # the evaluation kernels (HBM-bound rows a-3..a-6 of SURVEY 8): 16k scenarios, SoA, a few milliseconds
             try:
                 sys.path.insert(0, os.path.join(ROOT, "tools"))
-                from bench_eval import cpu_reference, measure
+                from bench_eval import cpu_reference, dropin_latency, measure
                 keys = ("function", "N", "B", "layout", "ms", "achieved", "peak", "unit", "frac", "evals_per_s")
                 line["roofline"]["eval_kernels"] = [
                     {k: r[k] for k in keys} for r in measure(N, 16384, 10, "soa", solver=solver, device=local_rank)]
@@ -489,6 +489,8 @@ def main():
                 for r in rows:
                     r["cpu_baseline"] = ref.get(r["function"]) if ref else None
                 line["roofline"]["eval_kernels_n21"] = rows
+                # one scenario per call through the CasADi symbols of the drop-in (what the unmodified reference would do)
+                line["roofline"]["dropin_call_latency"] = dropin_latency()
             except Exception as e:  # reported, never hidden
                 line["roofline"]["eval_kernels"] = {"error": repr(e)}
         if world == 1:

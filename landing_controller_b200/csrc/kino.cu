@@ -2,7 +2,8 @@
 // (generate_solver/generate_landingCtrller_KNITRO.m:34-193): constraint values g and the sparse Jacobian
 // dg/dx in CCS order for a whole batch of trajectories.  One thread = one (scenario, knot); with the SoA layout every
 // load and store of a warp is one coalesced 256-byte transaction.  The Jacobian columns are exact forward-mode
-// derivatives of the same knot function (kino_knot.cuh, Dual1): one pass per knot-local input, spread over blockIdx.z.
+// derivatives of the same knot function (kino_knot.cuh, Dual1): one pass per knot-local input, spread over blockIdx.z;
+// a pass evaluates only the row groups its input can reach (kino::reach).
 //
 // x = [X(:) (12 N); jpos(:) (12 (N-1)); U(:) (24 (N-1))], g rows: 48 boundary rows, then 141 per knot (117 for the
 // last) -- the row map is in oracle/kino_ref.py, which is pinned to the solution of this NLP that the reference stores.
@@ -66,7 +67,7 @@ __global__ void __launch_bounds__(128) k_kino_g(KinoArgs a) {
   }
 }
 
-// blockIdx.z = slice of the knot-local inputs (NIN / gridDim.z each)
+// blockIdx.z = slice of the knot-local inputs
 __global__ void __launch_bounds__(128) k_kino_jac(KinoArgs a) {
   const long long b = (long long)blockIdx.x * 128 + threadIdx.x;
   if (b >= a.B) return;
@@ -75,15 +76,14 @@ __global__ void __launch_bounds__(128) k_kino_jac(KinoArgs a) {
   double x[NIN];
 #pragma unroll 4
   for (int v = 0; v < NIN; v++) x[v] = (last && v >= 60) ? 0.0 : a.x.get(kino_col(N, k, v), b);
-  const int per = NIN / gridDim.z, v0 = per * blockIdx.z;
   const double h = __ldg(a.dtv + k);
-  for (int v = v0; v < v0 + per; v++) {
+  for (int v = blockIdx.z; v < NIN; v += gridDim.z) {  // (interleaved: the passes differ in cost by what they reach)
     if (last && v >= 60) break;
     Dual1 in[NIN];
 #pragma unroll 4
     for (int i = 0; i < NIN; i++) in[i] = Dual1(x[i], i == v ? 1.0 : 0.0);
     JSink s{a.jac, b, a.gpos + ((long long)k * NIN + v) * ROWS_INT};
-    kino::knot_rows<Dual1>(in, h, a.pr, last, s);
+    kino::knot_rows<Dual1>(in, h, a.pr, last, s, kino::reach(v));
   }
   if (k == 0 && blockIdx.z == 0)
     for (int i = 0; i < 48; i++) a.jac.at(__ldg(a.bpos + i), b) = 1.0;

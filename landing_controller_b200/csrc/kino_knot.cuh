@@ -51,9 +51,21 @@ KHD double hip_x(int l) { return l < 2 ? 0.19 : -0.19; }      // hipSrbmLocation
 KHD double hip_y(int l) { return (l & 1) ? 0.1 : -0.1; }
 KHD double side_y(int l) { return (l & 1) ? 1.0 : -1.0; }     // side_sign(2, leg) = sideSign of get_foot_jacobians_mc.m:3
 
-// rows of one knot into out(rho, value).  in[72] as above, h = dt_k.
+// Row groups (what an input can reach): the Jacobian passes evaluate only the groups that depend on their input.
+enum : unsigned { G_DYN = 1u, G_LEG0 = 2u, G_FRIC = 32u, G_Z = 64u, G_JPOS = 128u, G_ALL = 255u };
+KHD unsigned reach(int v) {  // knot-local input -> row groups
+  if (v < 6) return G_DYN | (15u * G_LEG0) | G_Z;          // r, rpy: dynamics, every leg's hip / torque / FK rows, z_k
+  if (v < 12) return G_DYN;                                // omega, v
+  if (v < 24) return (G_LEG0 << ((v - 12) / 3)) | G_JPOS;  // joint angles of one leg
+  if (v < 36) return G_DYN | (G_LEG0 << ((v - 24) / 3));   // foot position of one leg
+  if (v < 48) return G_DYN | (G_LEG0 << ((v - 36) / 3)) | G_FRIC;  // GRF of one leg
+  if (v < 60) return G_DYN;                                // next state (identity entries of the dynamics rows)
+  return G_LEG0 << ((v - 60) / 3);                         // next foot position: no-slip rows of one leg
+}
+
+// rows of one knot into out(rho, value).  in[72] as above, h = dt_k; only the row groups in mask are evaluated.
 template <class S, class Sink>
-KHD void knot_rows(const S* in, double h, const Params& pr, bool last, Sink& out) {
+KHD void knot_rows(const S* in, double h, const Params& pr, bool last, Sink& out, unsigned mask = G_ALL) {
   const S* X = in;
   const S* jp = in + 12;
   const S* c = in + 24;
@@ -68,6 +80,7 @@ KHD void knot_rows(const S* in, double h, const Params& pr, bool last, Sink& out
   const S R[9] = {cp * cy, -(cp * sy), sp,
                   cr * sy + sr * sp * cy, cr * cy - sr * sp * sy, -(sr * cp),
                   sr * sy - cr * sp * cy, sr * cy + cr * sp * sy, cr * cp};
+  if (mask & G_DYN) {
   // dynamics (:119-131)
   S fs[3] = {S(0.0), S(0.0), S(0.0)}, tq[3] = {S(0.0), S(0.0), S(0.0)};
   #pragma unroll
@@ -102,12 +115,16 @@ KHD void knot_rows(const S* in, double h, const Params& pr, bool last, Sink& out
     out(10, Xn[4] - X[4] - e1 * S(h));
     out(11, Xn[5] - X[5] - e2 * S(h));
   }
+  }
+  if (mask & G_FRIC) {
   #pragma unroll
   for (int l = 0; l < 4; l++) out(12 + l, f[3 * l + 2]);
+  }
   const int per_leg = last ? 9 : 15;
   S foot[12];
   #pragma unroll
   for (int l = 0; l < 4; l++) {
+    if (!(mask & (G_LEG0 << l))) continue;
     int rho = 16 + per_leg * l;
     const S fz = f[3 * l + 2];
     out(rho++, c[3 * l + 2]);
@@ -159,6 +176,7 @@ KHD void knot_rows(const S* in, double h, const Params& pr, bool last, Sink& out
   }
   int rho = 16 + 4 * per_leg;
   const double km = 0.71 * pr.mu;
+  if (mask & G_FRIC) {
   #pragma unroll
   for (int l = 0; l < 4; l++) out(rho + l, f[3 * l] - S(km) * f[3 * l + 2]);
   #pragma unroll
@@ -167,19 +185,24 @@ KHD void knot_rows(const S* in, double h, const Params& pr, bool last, Sink& out
   for (int l = 0; l < 4; l++) out(rho + 8 + l, f[3 * l + 1] - S(km) * f[3 * l + 2]);
   #pragma unroll
   for (int l = 0; l < 4; l++) out(rho + 12 + l, -(S(km) * f[3 * l + 2]) - f[3 * l + 1]);
+  }
   rho += 16;
-  out(rho++, X[2]);
+  if (mask & G_Z) out(rho, X[2]);
+  rho++;
   #pragma unroll
   for (int i = 0; i < 12; i++) {
+    if (!(mask & (G_LEG0 << (i / 3)))) continue;
     const S d = c[i] - foot[i];
     out(rho + i, d);
     out(rho + 12 + i, d);
   }
   rho += 24;
+  if (mask & G_JPOS) {
   #pragma unroll
   for (int i = 0; i < 12; i++) {
     out(rho + i, jp[i]);
     out(rho + 12 + i, jp[i]);
+  }
   }
 }
 

@@ -115,6 +115,40 @@ def cpu_reference(B=8192, reps=3, threads=None):
     return out
 
 
+def dropin_latency(calls=300):
+    """Per-call latency of the CasADi-ABI drop-in (one scenario per call: H2D + launch + D2H on the calling thread) next
+    to the reference's own compiled function (oracle/_ref, one thread): what running the UNMODIFIED reference -- IPOPT
+    calling nlp_g / nlp_jac_g / nlp_hess_l once per iteration -- costs per evaluation in either library.  Both are timed
+    by the same loop (oracle/ref_timing.c: dlopen + B sequential calls of F(arg, res, iw, w, mem))."""
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_lib import REF_SO, Oracle, build_oracle
+    import landing_controller_b200 as lc
+    lib = ctypes.CDLL(build_oracle())
+    o = Oracle(21)
+    pb = o.default_problem()
+    d = lc.grid_sweep(1024)[:: 1024 // 8]
+    rng = np.random.default_rng(0)
+    X = np.zeros((calls, o.nx)); P = np.zeros((calls, o.np_))
+    for b in range(calls):
+        P[b], X[b] = o.build_p_x0(pb, d[b % len(d), :6], d[b % len(d), 6:])
+    X += 0.01 * rng.standard_normal(X.shape)
+    lam_f, lam_g = np.ones(calls), rng.standard_normal((calls, o.m))
+    dp = ctypes.POINTER(ctypes.c_double)
+    rows = []
+    libs = [("dropin (GPU, this library)", lc.DROPIN_PATH)] + ([("reference C (gcc -O3, 1 thread)", REF_SO)] if os.path.exists(REF_SO) else [])
+    for name, ins in (("nlp_g", [X, P]), ("nlp_jac_g", [X, P]), ("nlp_hess_l", [X, P, lam_f, lam_g])):
+        row = {"function": name, "N": 21, "unit": "us per call"}
+        for tag, path in libs:
+            arr = (dp * 4)(*[a.ctypes.data_as(dp) for a in ins] + [None] * (4 - len(ins)))
+            sec, chk = ctypes.c_double(), ctypes.c_double()
+            for _ in range(2):  # (first pass: context creation, page-in)
+                rc = lib.ref_time_function(path.encode(), name.encode(), calls, arr, 1, 1, ctypes.byref(sec), ctypes.byref(chk))
+            row[tag] = None if rc != 0 else 1e6 * sec.value / calls
+        rows.append(row)
+    return rows
+
+
 if __name__ == "__main__":
     N = int(sys.argv[1]) if len(sys.argv) > 1 else 30
     B = int(sys.argv[2]) if len(sys.argv) > 2 else 16384
