@@ -29,7 +29,7 @@ constexpr unsigned FULL = 0xffffffffu;
 #endif
 constexpr int NT = SRB_NT;       // threads per CTA (= per scenario)
 constexpr int NWARP = NT / 32;
-static_assert(NT == 64 || NT == 128 || NT == 256, "threads per scenario");
+static_assert(NT % 32 == 0 && NT >= 64 && NT <= 384, "threads per scenario");
 #ifndef SRB_CTAS
 #define SRB_CTAS (SRB_NT == 256 ? 2 : (SRB_NT == 128 ? 4 : 5))
 #endif
@@ -60,8 +60,8 @@ constexpr int SM_LB0 = SM_SWEEP_END;
 constexpr int LB_REGION = 2 * CT_STRIDE;       // two condensed-stage buffers (backward) / one list buffer (pre-pass)
 constexpr int SM_V = SM_LB0 + LB_REGION;       // vectors
 constexpr int V_Q = 0, V_Z = 48, V_R = 96, V_T = 108, V_YV = 132, V_PN = 156, V_XI = 180, V_U = 204, V_END = 228;  // V_Z: 24 zeros
-constexpr int SM_RED = SM_V + V_END;           // block-reduction scratch 8 x 8
-constexpr int SM_TAB = SM_RED + 8 * 8;         // lb[140] ub[140] lbo[140] ubo[140]
+constexpr int SM_RED = SM_V + V_END;           // block-reduction scratch (up to 12 warps) x 8
+constexpr int SM_TAB = SM_RED + 16 * 8;        // lb[140] ub[140] lbo[140] ubo[140]
 constexpr int TBL_INTS = 2688;                 // index tables of the sweeps (SolverTables::sm_src)
 // the index tables live in shared memory (one copy per CTA) when the CTA is large enough to afford it, else they are read
 // from global memory through the L1 (one copy per SM in effect)
