@@ -35,7 +35,7 @@ struct SolverWorkspace {
   double* zeros = nullptr;    // 16 zeros (c+ operand of the last knot)
   int* order = nullptr;       // work-queue order (scenario ids, longest expected first)
   unsigned char* kt = nullptr;  // row-kind tables (k_kinds)
-  size_t order_cap = 0;
+  size_t order_cap = 0;       // bytes (order, and for large sweeps the sort keys / ids / temporary storage behind it)
   SolverTables tab;
   int n_sm = 0;
   bool ready = false;         // first-call set-up (tables, queue head, kernel attributes) completed
