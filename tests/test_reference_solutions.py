@@ -154,3 +154,60 @@ def test_gpu_solver_reproduces_stored_ipopt_solutions():
     print("GPU: same local solution as IPOPT on %d of %d stored runs; same cost as the CPU restatement on %d of %d"
           % (same, len(drops), agree.sum(), both.sum()))
     assert same >= 24 and agree.mean() >= 0.7
+
+
+FIX_ALL = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ccc_n41_all.npz")
+
+
+def _compare_with_all_stored(r):
+    """counts of (converged, same local solution as IPOPT, lower cost, higher cost) over the 294 stored runs"""
+    import ccc_problem as ccc
+    d = np.load(FIX_ALL)
+    same = lower = higher = 0
+    dfz, dterm = [], []
+    for b in range(len(d["drops"])):
+        if r["status"][b] != 0:
+            continue
+        Xs, cs, fs = ccc.split(r["x"][b])
+        rel = (r["f"][b] - d["cost"][b]) / d["cost"][b]
+        if abs(rel) <= 2e-3 and ccc.touchdown(fs) == d["td"][b].astype(int).tolist():
+            same += 1
+            dfz.append(np.max(np.abs(fs[2::3] - d["fz"][b])))
+            dterm.append(max(np.max(np.abs(Xs[2:5, -1] - d["term"][b][2:5])), np.max(np.abs(Xs[6:, -1] - d["term"][b][6:]))))
+        elif rel < 0:
+            lower += 1
+        else:
+            higher += 1
+    return int((r["status"] == 0).sum()), same, lower, higher, float(np.median(dfz)), float(np.max(dterm))
+
+
+def test_cpu_solver_on_all_294_stored_ipopt_solutions():
+    """The same soft known-answer test on EVERY valid stored IPOPT run of the reference (294; fixture
+    tests/golden/ccc_n41_all.npz).  Measured: 286 converge, 190 land on IPOPT's solution (cost within 0.2 %, identical
+    touchdown knots, terminal state within 1e-3), 65 find a lower cost than IPOPT did, 31 a higher one."""
+    import ccc_problem as ccc
+    from oracle_ip import default_options, default_problem, solve_cpu
+    d = np.load(FIX_ALL)
+    assert len(d["drops"]) == 294
+    opt = default_options(run_Qf=list(ccc.QF), kin_box=list(ccc.KIN_BOX))
+    r = solve_cpu(ccc.N, np.ascontiguousarray(d["drops"]), opt=opt, pb=ccc.fill_problem(default_problem()))
+    conv, same, lower, higher, dfz, dterm = _compare_with_all_stored(r)
+    print("CPU: converged %d of 294, same local solution as IPOPT %d, lower cost %d, higher cost %d; median max|df_z| %.2f N, "
+          "max terminal-state difference %.1e" % (conv, same, lower, higher, dfz, dterm))
+    assert conv >= 280 and same >= 180 and higher <= 40 and dfz <= 1.0 and dterm <= 1e-3
+
+
+@pytest.mark.gpu
+def test_gpu_solver_on_all_294_stored_ipopt_solutions():
+    """... and through the C ABI on the GPU: the same counts within a few runs (the non-convex problem amplifies rounding
+    differences between the two implementations on a handful of runs)."""
+    import ccc_problem as ccc
+    d = np.load(FIX_ALL)
+    s = lc.LandingSolver(N=ccc.N)
+    ccc.fill_problem(s.problem)
+    g = s.solve(np.ascontiguousarray(d["drops"]))
+    s.close()
+    conv, same, lower, higher, dfz, dterm = _compare_with_all_stored(g)
+    print("GPU: converged %d of 294, same local solution as IPOPT %d, lower cost %d, higher cost %d; median max|df_z| %.2f N, "
+          "max terminal-state difference %.1e" % (conv, same, lower, higher, dfz, dterm))
+    assert conv >= 280 and same >= 180 and higher <= 40 and dfz <= 1.0 and dterm <= 1e-3
