@@ -155,7 +155,8 @@ typedef struct landing_options {
  * mu_strategy = adaptive / mu_oracle = probing (monotone Fiacco-McCormick update instead), max_soc (no second-order
  * correction), min/max_refinement_steps (no iterative refinement of the Riccati solve), nlp_scaling_method =
  * gradient-based (never triggers at the reference's initial guesses: max |J(x0)| <= 50), acceptable_tol /
- * acceptable_iter (only the strict tolerances terminate), and IPOPT's restoration phase (replaced by re-centring with
+ * acceptable_iter (only the strict tolerances terminate; with acceptable_tol = tol the acceptable test was measured
+ * never to fire on the sweeps), and IPOPT's restoration phase (replaced by re-centring with
  * the watchdog above).  DESIGN.md section 3 lists the measured consequences. */
 void landing_options_default(landing_options *opt);
 

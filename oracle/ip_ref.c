@@ -48,6 +48,8 @@ void ip_options_default(ip_options *o) {
   o->cs = NULL;
   for (int i = 0; i < 12; i++) o->QX[i] = 0.0;
   o->delta_c = 1e-7;
+  o->acceptable_tol = 1e-4;
+  o->acceptable_iter = 0; /* (off by default: see DESIGN.md 3) */
 }
 
 typedef struct {
@@ -709,7 +711,7 @@ static int ip_solve_ws(ipws *w, const double *p, const double *x0, const ip_opti
   init_slacks(w, opt, mu);
   w->nfilt = 0;
   double theta0 = -1, dw_last = 0;
-  int status = 1, it = 0, restarts = 0, tiny = 0;
+  int status = 1, it = 0, restarts = 0, tiny = 0, n_acc = 0;
   for (it = 0; it <= opt->max_iter; it++) {
     double err[3], cmu, ysum, zsum;
     int nzb;
@@ -730,6 +732,11 @@ static int ip_solve_ws(ipws *w, const double *p, const double *x0, const ip_opti
         err[2] <= opt->compl_inf_tol) {
       status = 0;
       break;
+    }
+    if (opt->acceptable_iter > 0) { /* IPOPT: "solved to acceptable level" */
+      if (E0 <= opt->acceptable_tol && err[0] <= 1e10 && viol <= 1e-2 && err[2] <= 1e-2) n_acc++;
+      else n_acc = 0;
+      if (n_acc >= opt->acceptable_iter) { status = 5; break; }
     }
     if (it == opt->max_iter) { status = 1; break; }
     /* monotone barrier update (Fiacco-McCormick) */

@@ -51,10 +51,16 @@ typedef struct ip_options {
   const int *cs;
   double QX[12];
   double delta_c; /* 1e-7 */
+  /* IPOPT's "acceptable" termination, which the reference sets (generate_landingCtrller_IPOPT.m:233,235: acceptable_tol
+   * 1e-4, acceptable_iter 5): stop after acceptable_iter consecutive iterates whose scaled optimality error is within
+   * acceptable_tol and whose unscaled errors are within IPOPT's default acceptable levels (constraint violation 1e-2,
+   * dual infeasibility 1e10, complementarity 1e-2).  Status 5.  acceptable_iter = 0 switches it off. */
+  double acceptable_tol;
+  int acceptable_iter;
 } ip_options;
 
 typedef struct ip_result {
-  int status; /* 0 converged, 1 max_iter, 2 line-search failure, 3 NaN, 4 factorisation failure */
+  int status; /* 0 converged, 1 max_iter, 2 line-search failure, 3 NaN, 4 factorisation failure, 5 acceptable level */
   int iters;
   int n_factor; /* Riccati factorisations (incl. inertia-correction retries) */
   double f, viol, dual_inf, compl_inf, mu;
