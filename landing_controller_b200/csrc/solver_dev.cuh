@@ -1,16 +1,16 @@
 // solver_dev.cuh -- device side of the batched interior-point solver (included by solver.cu only).
 //
-// ONE CTA (256 threads) = ONE SCENARIO for the whole solve; 2 CTAs are resident per SM and pull
-// scenario ids from an atomic queue (ordered longest-expected-first by k_order).  Phases of one
+// ONE CTA (SRB_NT threads, 256 in the shipped build) = ONE SCENARIO for the whole solve; SRB_CTAS CTAs (2) are resident
+// per SM and pull scenario ids from an atomic queue (ordered longest-expected-first by k_order).  Phases of one
 // interior-point iteration:
-//   (parallel over knots / rows, all 256 threads)
-//     eval        J lists by warp 0 (one knot per lane), H lists by warp 4 (SRB_EVAL_PARTS warps each)
+//   (parallel over knots / rows, all threads)
+//     eval        J lists on the first half of the CTA, H lists on the second half, one knot per thread
 //     row passes  sigma, yhat, optimality-error pieces, grad of the Lagrangian, step recovery,
 //                 fraction-to-the-boundary, merit function  -> block reductions
 //     condensing  everything of a stage that does not depend on P_{k+1} (sweeps.cuh: condense_all)
-//   (sequential over stages, all 256 threads cooperate on one stage)
-//     backward    condensed stage data -> 48x48 stage matrix (lower, elimination order) + G'PG terms ->
-//                 blocked partial Cholesky (24 pivots) -> Yt, P_k, p_k
+//   (sequential over stages, all threads cooperate on one stage)
+//     backward    condensed stage data -> 49x48 stage matrix as FP64 tensor-core tiles in registers (lower, elimination
+//                 order) + W'PW terms -> blocked partial Cholesky (24 pivots, panels of 8) -> Yt, P_k, p_k
 //     forward     u = -L^-T (Y xi + yv), xi+ = G [xi;u] + r, costates
 // All reductions end with the identical value in every thread, so control flow is block-uniform.
 #pragma once
