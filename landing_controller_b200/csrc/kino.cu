@@ -46,19 +46,41 @@ struct JSink {
   }
 };
 
+// One (scenario, knot) is evaluated by four threads of four different CTAs (blockIdx.z = part = leg): each runs the whole
+// knot function behind a compile-time filtering sink and emits only the rows its part owns (kino::row_owner), so the
+// compiler removes the other legs' kinematics from its instance -- the same device the SRB evaluation kernels use
+// (eval.cu: PartSink).  Four times the threads in flight, a third of the work each.
+template <bool LAST, int PART> struct GPartSink {
+  View g;
+  long long b, base;
+  __device__ __forceinline__ void operator()(int rho, double v) {
+    if (kino::row_owner<LAST>(rho) == PART) g.at(base + rho, b) = v;
+  }
+};
+template <bool LAST, int PART>
+__device__ __forceinline__ void kino_g_part(const KinoArgs& a, long long b, int k) {
+  double in[NIN];  // (loaded here, per instance: the loads of inputs a part never uses are dead code)
+#pragma unroll
+  for (int v = 0; v < NIN; v++) in[v] = (LAST && v >= 60) ? 0.0 : a.x.get(kino_col(a.N, k, v), b);
+  GPartSink<LAST, PART> s{a.g, b, 48 + (long long)ROWS_INT * k};
+  kino::knot_rows_t<LAST, double>(in, __ldg(a.dtv + k), a.pr, s,
+                                  (kino::G_LEG0 << PART) | (PART == 0 ? (kino::G_DYN | kino::G_FRIC | kino::G_Z) : 0u) | kino::G_JPOS);
+}
+
 __global__ void __launch_bounds__(128) k_kino_g(KinoArgs a) {
   const long long b = (long long)blockIdx.x * 128 + threadIdx.x;
   if (b >= a.B) return;
-  const int N = a.N, k = blockIdx.y;
+  const int N = a.N, k = blockIdx.y, part = blockIdx.z;
   const bool last = k == N - 2;
-  double in[NIN];
-#pragma unroll 4
-  for (int v = 0; v < NIN; v++) in[v] = (last && v >= 60) ? 0.0 : a.x.get(kino_col(N, k, v), b);
-  GSink s{a.g, b, 48 + (long long)ROWS_INT * k};
-  kino::knot_rows<double>(in, __ldg(a.dtv + k), a.pr, last, s);
-  if (k == 0) {  // boundary rows: q_0, qd_0, c_0 | q_{N-1} twice | qd_{N-1} twice   (:93-101)
-    for (int i = 0; i < 12; i++) a.g.at(i, b) = in[i];
-    for (int i = 0; i < 12; i++) a.g.at(12 + i, b) = in[24 + i];
+  switch (part) {  // (block-uniform)
+    case 0: if (last) kino_g_part<true, 0>(a, b, k); else kino_g_part<false, 0>(a, b, k); break;
+    case 1: if (last) kino_g_part<true, 1>(a, b, k); else kino_g_part<false, 1>(a, b, k); break;
+    case 2: if (last) kino_g_part<true, 2>(a, b, k); else kino_g_part<false, 2>(a, b, k); break;
+    default: if (last) kino_g_part<true, 3>(a, b, k); else kino_g_part<false, 3>(a, b, k); break;
+  }
+  if (k == 0 && part == 0) {  // boundary rows: q_0, qd_0, c_0 | q_{N-1} twice | qd_{N-1} twice   (:93-101)
+    for (int i = 0; i < 12; i++) a.g.at(i, b) = a.x.get(i, b);
+    for (int i = 0; i < 12; i++) a.g.at(12 + i, b) = a.x.get(12LL * N + 12LL * (N - 1) + i, b);
     for (int i = 0; i < 6; i++) {
       const double q = a.x.get(12LL * (N - 1) + i, b), qd = a.x.get(12LL * (N - 1) + 6 + i, b);
       a.g.at(24 + i, b) = q; a.g.at(30 + i, b) = q;
@@ -154,7 +176,7 @@ KinoPlan make_kino_plan(int N) {
 int launch_kino(const KinoArgs& a, bool want_g, bool want_jac, cudaStream_t st) {
   int n = 0;
   const unsigned gx = (unsigned)((a.B + 127) / 128);
-  if (want_g) { k_kino_g<<<dim3(gx, a.N - 1, 1), 128, 0, st>>>(a); n++; }
+  if (want_g) { k_kino_g<<<dim3(gx, a.N - 1, 4), 128, 0, st>>>(a); n++; }
   if (want_jac) { k_kino_jac<<<dim3(gx, a.N - 1, 8), 128, 0, st>>>(a); n++; }
   return n;
 }

@@ -64,8 +64,9 @@ KHD unsigned reach(int v) {  // knot-local input -> row groups
 }
 
 // rows of one knot into out(rho, value).  in[72] as above, h = dt_k; only the row groups in mask are evaluated.
-template <class S, class Sink>
-KHD void knot_rows(const S* in, double h, const Params& pr, bool last, Sink& out, unsigned mask = G_ALL) {
+template <bool LAST, class S, class Sink>
+KHD void knot_rows_t(const S* in, double h, const Params& pr, Sink& out, unsigned mask = G_ALL) {
+  constexpr bool last = LAST;
   const S* X = in;
   const S* jp = in + 12;
   const S* c = in + 24;
@@ -204,6 +205,25 @@ KHD void knot_rows(const S* in, double h, const Params& pr, bool last, Sink& out
     out(rho + 12 + i, jp[i]);
   }
   }
+}
+
+// run-time knot class
+template <class S, class Sink>
+KHD void knot_rows(const S* in, double h, const Params& pr, bool last, Sink& out, unsigned mask = G_ALL) {
+  if (last) knot_rows_t<true, S, Sink>(in, h, pr, out, mask);
+  else knot_rows_t<false, S, Sink>(in, h, pr, out, mask);
+}
+
+// Which thread of a (scenario, knot) quadruple owns row rho when the knot is split by leg (k_kino_g): the rows of leg l
+// (contact, hip box, leg length, torques, foot kinematics, joint limits of that leg) belong to part l, everything else
+// (dynamics, f_z, friction, z) to part 0.  constexpr: behind a filtering sink the compiler drops what a part never emits.
+template <bool LAST> KHD constexpr int row_owner(int rho) {
+  constexpr int per_leg = LAST ? 9 : 15, legs_end = 16 + 4 * per_leg, fk = legs_end + 17;
+  if (rho < 16) return 0;
+  if (rho < legs_end) return (rho - 16) / per_leg;
+  if (rho < fk) return 0;                                   // friction, z
+  if (rho < fk + 24) return ((rho - fk) % 12) / 3;          // c - FK (12, twice)
+  return ((rho - fk - 24) % 12) / 3;                        // joint angles (12, twice)
 }
 
 }  // namespace kino
