@@ -2,8 +2,8 @@
 // (generate_solver/generate_landingCtrller_KNITRO.m:34-193): constraint values g and the sparse Jacobian
 // dg/dx in CCS order for a whole batch of trajectories.  One thread = one (scenario, knot); with the SoA layout every
 // load and store of a warp is one coalesced 256-byte transaction.  The Jacobian columns are exact forward-mode
-// derivatives of the same knot function (kino_knot.cuh, Dual1): one pass per knot-local input, spread over blockIdx.z;
-// a pass evaluates only the row groups its input can reach (kino::reach).
+// derivatives of the same knot function (kino_knot.cuh, DualN): one pass per triple of knot-local inputs, spread over
+// blockIdx.z; a pass types only its own input block as duals and evaluates only the row groups it can reach.
 //
 // x = [X(:) (12 N); jpos(:) (12 (N-1)); U(:) (24 (N-1))], g rows: 48 boundary rows, then 141 per knot (117 for the
 // last) -- the row map is in oracle/kino_ref.py, which is pinned to the solution of this NLP that the reference stores.
@@ -36,13 +36,19 @@ struct GSink {
   long long b, base;
   __device__ __forceinline__ void operator()(int rho, double v) { g.at(base + rho, b) = v; }
 };
-struct JSink {
+// Sink of a Jacobian pass: a row whose value is a plain double does not depend on the seeded block (no entry); a dual
+// row scatters its K tangents to the CCS positions of (row, seeded columns) from the host-made table (-1 = no entry).
+template <int K> struct JSinkN {
   View jac;
   long long b;
-  const int* gp;  // CCS position of (row rho, this column) or -1
-  __device__ __forceinline__ void operator()(int rho, Dual1 v) {
-    const int p = __ldg(gp + rho);
-    if (p >= 0) jac.at(p, b) = v.d;
+  const int* gp;  // table row of the first seeded input: gp[j * ROWS_INT + rho]
+  __device__ __forceinline__ void operator()(int, double) const {}
+  __device__ __forceinline__ void operator()(int rho, const kino::DualN<K>& v) const {
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      const int p = __ldg(gp + j * ROWS_INT + rho);
+      if (p >= 0) jac.at(p, b) = v.d[j];
+    }
   }
 };
 
@@ -89,25 +95,65 @@ __global__ void __launch_bounds__(128) k_kino_g(KinoArgs a) {
   }
 }
 
-// blockIdx.z = slice of the knot-local inputs
+// Jacobian: blockIdx.z = pass.  A pass seeds one triple of knot-local inputs (three tangents: r | rpy | omega | v | the
+// joint angles, foot position, force, next foot position of one leg | a triple of the next state) and runs the knot
+// function with that block typed DualN<3> and every other block a plain double, restricted to the row groups the triple
+// can reach; the rpy triple, which reaches every leg's rows through R, is split into four passes by leg.
+constexpr int JAC_PASSES = 27;
+template <int G> struct PassOf {  // pass -> (first seeded input, row groups)
+  static constexpr int v0 = G < 24 ? 3 * G : 3;
+  static constexpr unsigned mask = G == 1   ? (kino::G_DYN | kino::G_LEG0)
+                                   : G >= 24 ? (kino::G_LEG0 << (G - 23))
+                                             : kino::reach(3 * G);
+};
+template <bool LAST, int G>
+__device__ __forceinline__ void kino_jac_pass(const KinoArgs& a, long long b, int k) {
+  using D = kino::DualN<3>;
+  constexpr int v0 = PassOf<G>::v0, blk = v0 < 12 ? v0 / 3 : v0 < 24 ? 4 : v0 < 36 ? 5 : v0 < 48 ? 6 : v0 < 60 ? 7 : 8;
+  double x[NIN];  // (loads of inputs the pass never uses are dead code)
+#pragma unroll
+  for (int v = 0; v < NIN; v++) x[v] = (LAST && v >= 60) ? 0.0 : a.x.get(kino_col(a.N, k, v), b);
+  const double h = __ldg(a.dtv + k);
+  JSinkN<3> s{a.jac, b, a.gpos + ((long long)k * NIN + v0) * ROWS_INT};
+  constexpr unsigned mask = PassOf<G>::mask;
+  if constexpr (blk < 4) {  // a triple of X_k
+    D t[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) t[j] = kino::seeded<3>(x[v0 + j], j);
+    if constexpr (blk == 0) kino::knot_rows_h<LAST>(t, x + 3, x + 6, x + 9, x + 12, x + 24, x + 36, x + 48, x + 60, h, a.pr, s, mask);
+    if constexpr (blk == 1) kino::knot_rows_h<LAST>(x, t, x + 6, x + 9, x + 12, x + 24, x + 36, x + 48, x + 60, h, a.pr, s, mask);
+    if constexpr (blk == 2) kino::knot_rows_h<LAST>(x, x + 3, t, x + 9, x + 12, x + 24, x + 36, x + 48, x + 60, h, a.pr, s, mask);
+    if constexpr (blk == 3) kino::knot_rows_h<LAST>(x, x + 3, x + 6, t, x + 12, x + 24, x + 36, x + 48, x + 60, h, a.pr, s, mask);
+  } else {  // a triple of a 12-block: the block as duals, tangents on the triple
+    constexpr int base = 12 * (blk - 3), off = v0 - base;
+    D t[12];
+#pragma unroll
+    for (int i = 0; i < 12; i++) t[i] = (i >= off && i < off + 3) ? kino::seeded<3>(x[base + i], i - off) : D(x[base + i]);
+    if constexpr (blk == 4) kino::knot_rows_h<LAST>(x, x + 3, x + 6, x + 9, t, x + 24, x + 36, x + 48, x + 60, h, a.pr, s, mask);
+    if constexpr (blk == 5) kino::knot_rows_h<LAST>(x, x + 3, x + 6, x + 9, x + 12, t, x + 36, x + 48, x + 60, h, a.pr, s, mask);
+    if constexpr (blk == 6) kino::knot_rows_h<LAST>(x, x + 3, x + 6, x + 9, x + 12, x + 24, t, x + 48, x + 60, h, a.pr, s, mask);
+    if constexpr (blk == 7) kino::knot_rows_h<LAST>(x, x + 3, x + 6, x + 9, x + 12, x + 24, x + 36, t, x + 60, h, a.pr, s, mask);
+    if constexpr (blk == 8) kino::knot_rows_h<LAST>(x, x + 3, x + 6, x + 9, x + 12, x + 24, x + 36, x + 48, t, h, a.pr, s, mask);
+  }
+}
+template <bool LAST, int G>
+__device__ __forceinline__ void kino_jac_dispatch(const KinoArgs& a, long long b, int k, int g) {
+  if constexpr (G < JAC_PASSES) {
+    if (g == G) {
+      if constexpr (!(LAST && G >= 20 && G < 24)) kino_jac_pass<LAST, G>(a, b, k);  // (no c_{k+1} in the last knot)
+    } else {
+      kino_jac_dispatch<LAST, G + 1>(a, b, k, g);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(128) k_kino_jac(KinoArgs a) {
   const long long b = (long long)blockIdx.x * 128 + threadIdx.x;
   if (b >= a.B) return;
-  const int N = a.N, k = blockIdx.y;
-  const bool last = k == N - 2;
-  double x[NIN];
-#pragma unroll 4
-  for (int v = 0; v < NIN; v++) x[v] = (last && v >= 60) ? 0.0 : a.x.get(kino_col(N, k, v), b);
-  const double h = __ldg(a.dtv + k);
-  for (int v = blockIdx.z; v < NIN; v += gridDim.z) {  // (interleaved: the passes differ in cost by what they reach)
-    if (last && v >= 60) break;
-    Dual1 in[NIN];
-#pragma unroll 4
-    for (int i = 0; i < NIN; i++) in[i] = Dual1(x[i], i == v ? 1.0 : 0.0);
-    JSink s{a.jac, b, a.gpos + ((long long)k * NIN + v) * ROWS_INT};
-    kino::knot_rows<Dual1>(in, h, a.pr, last, s, kino::reach(v));
-  }
-  if (k == 0 && blockIdx.z == 0)
+  const int N = a.N, k = blockIdx.y, g = blockIdx.z;  // (block-uniform dispatch)
+  if (k == N - 2) kino_jac_dispatch<true, 0>(a, b, k, g);
+  else kino_jac_dispatch<false, 0>(a, b, k, g);
+  if (k == 0 && g == 0)
     for (int i = 0; i < 48; i++) a.jac.at(__ldg(a.bpos + i), b) = 1.0;
 }
 
@@ -135,7 +181,7 @@ KinoPlan make_kino_plan(int N) {
         if (last && v >= 60) continue;
         Dual1 in[NIN];
         for (int i = 0; i < NIN; i++) in[i] = Dual1(xv[i], i == v ? 1.0 : 0.0);
-        auto sink = [&](int rho, Dual1 d) { if (d.d != 0.0) pat[cls][(size_t)v * ROWS_INT + rho] = 1; };
+        auto sink = [&](int rho, Dual1 d) { if (d.d[0] != 0.0) pat[cls][(size_t)v * ROWS_INT + rho] = 1; };
         kino::knot_rows<Dual1>(in, 0.03, pr, last, sink);
       }
     }
@@ -177,7 +223,7 @@ int launch_kino(const KinoArgs& a, bool want_g, bool want_jac, cudaStream_t st) 
   int n = 0;
   const unsigned gx = (unsigned)((a.B + 127) / 128);
   if (want_g) { k_kino_g<<<dim3(gx, a.N - 1, 4), 128, 0, st>>>(a); n++; }
-  if (want_jac) { k_kino_jac<<<dim3(gx, a.N - 1, 8), 128, 0, st>>>(a); n++; }
+  if (want_jac) { k_kino_jac<<<dim3(gx, a.N - 1, JAC_PASSES), 128, 0, st>>>(a); n++; }
   return n;
 }
 
