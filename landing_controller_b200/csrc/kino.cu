@@ -98,13 +98,11 @@ __global__ void __launch_bounds__(128) k_kino_g(KinoArgs a) {
 // Jacobian: blockIdx.z = pass.  A pass seeds one triple of knot-local inputs (three tangents: r | rpy | omega | v | the
 // joint angles, foot position, force, next foot position of one leg | a triple of the next state) and runs the knot
 // function with that block typed DualN<3> and every other block a plain double, restricted to the row groups the triple
-// can reach; the rpy triple, which reaches every leg's rows through R, is split into four passes by leg.
-constexpr int JAC_PASSES = 27;
+// can reach; the rpy triple, which reaches every leg's rows through R, is split into five passes (dynamics, four legs).
+constexpr int JAC_PASSES = 28;
 template <int G> struct PassOf {  // pass -> (first seeded input, row groups)
   static constexpr int v0 = G < 24 ? 3 * G : 3;
-  static constexpr unsigned mask = G == 1   ? (kino::G_DYN | kino::G_LEG0)
-                                   : G >= 24 ? (kino::G_LEG0 << (G - 23))
-                                             : kino::reach(3 * G);
+  static constexpr unsigned mask = G == 1 ? kino::G_DYN : G >= 24 ? (kino::G_LEG0 << (G - 24)) : kino::reach(3 * G);
 };
 template <bool LAST, int G>
 __device__ __forceinline__ void kino_jac_pass(const KinoArgs& a, long long b, int k) {
@@ -136,24 +134,30 @@ __device__ __forceinline__ void kino_jac_pass(const KinoArgs& a, long long b, in
     if constexpr (blk == 8) kino::knot_rows_h<LAST>(x, x + 3, x + 6, x + 9, x + 12, x + 24, x + 36, x + 48, t, h, a.pr, s, mask);
   }
 }
-template <bool LAST, int G>
+template <bool LAST, int G, int G1>
 __device__ __forceinline__ void kino_jac_dispatch(const KinoArgs& a, long long b, int k, int g) {
-  if constexpr (G < JAC_PASSES) {
+  if constexpr (G < G1) {
     if (g == G) {
       if constexpr (!(LAST && G >= 20 && G < 24)) kino_jac_pass<LAST, G>(a, b, k);  // (no c_{k+1} in the last knot)
     } else {
-      kino_jac_dispatch<LAST, G + 1>(a, b, k, g);
+      kino_jac_dispatch<LAST, G + 1, G1>(a, b, k, g);
     }
   }
 }
 
+// Passes G0..G1-1; blockIdx.x = pass + (G1 - G0) * scenario block: the passes of one (scenario block, knot) read the same
+// x and are scheduled together, so all but the first find it in L2.  One kernel per class of passes (launch_kino), so
+// that the light passes are not held to the register count -- hence occupancy -- of the rpy passes.
+template <int G0, int G1>
 __global__ void __launch_bounds__(128) k_kino_jac(KinoArgs a) {
-  const long long b = (long long)blockIdx.x * 128 + threadIdx.x;
+  constexpr int NPASS = G1 - G0;
+  const int g = G0 + (int)(blockIdx.x % NPASS);
+  const long long b = (long long)(blockIdx.x / NPASS) * 128 + threadIdx.x;
   if (b >= a.B) return;
-  const int N = a.N, k = blockIdx.y, g = blockIdx.z;  // (block-uniform dispatch)
-  if (k == N - 2) kino_jac_dispatch<true, 0>(a, b, k, g);
-  else kino_jac_dispatch<false, 0>(a, b, k, g);
-  if (k == 0 && g == 0)
+  const int N = a.N, k = blockIdx.y;  // (block-uniform dispatch)
+  if (k == N - 2) kino_jac_dispatch<true, G0, G1>(a, b, k, g);
+  else kino_jac_dispatch<false, G0, G1>(a, b, k, g);
+  if (G0 == 0 && k == 0 && g == 0)
     for (int i = 0; i < 48; i++) a.jac.at(__ldg(a.bpos + i), b) = 1.0;
 }
 
@@ -223,7 +227,17 @@ int launch_kino(const KinoArgs& a, bool want_g, bool want_jac, cudaStream_t st) 
   int n = 0;
   const unsigned gx = (unsigned)((a.B + 127) / 128);
   if (want_g) { k_kino_g<<<dim3(gx, a.N - 1, 4), 128, 0, st>>>(a); n++; }
-  if (want_jac) { k_kino_jac<<<dim3(gx, a.N - 1, JAC_PASSES), 128, 0, st>>>(a); n++; }
+  if (want_jac) {
+    k_kino_jac<0, 1><<<dim3(gx * 1, a.N - 1, 1), 128, 0, st>>>(a);     // r
+    k_kino_jac<1, 2><<<dim3(gx * 1, a.N - 1, 1), 128, 0, st>>>(a);     // rpy: dynamics rows
+    k_kino_jac<2, 4><<<dim3(gx * 2, a.N - 1, 1), 128, 0, st>>>(a);     // omega, v
+    k_kino_jac<4, 8><<<dim3(gx * 4, a.N - 1, 1), 128, 0, st>>>(a);     // joint angles by leg
+    k_kino_jac<8, 12><<<dim3(gx * 4, a.N - 1, 1), 128, 0, st>>>(a);    // foot positions by leg
+    k_kino_jac<12, 16><<<dim3(gx * 4, a.N - 1, 1), 128, 0, st>>>(a);   // forces by leg
+    k_kino_jac<16, 24><<<dim3(gx * 8, a.N - 1, 1), 128, 0, st>>>(a);   // next state, next foot positions
+    k_kino_jac<24, 28><<<dim3(gx * 4, a.N - 1, 1), 128, 0, st>>>(a);   // rpy: rows of one leg
+    n += 8;
+  }
   return n;
 }
 
