@@ -485,6 +485,9 @@ def main():
                 ref = cpu_reference()
                 s21 = lc.LandingSolver(N=21, device=local_rank)
                 rows = [{k: r[k] for k in keys} for r in measure(21, 16384, 10, "soa", solver=s21, device=local_rank)]
+                # the kino-dynamic functions (the KNITRO variant's N = 21 problem)
+                from bench_kino import measure_kino
+                line["roofline"]["kino_kernels_n21"] = [{k: r[k] for k in keys} for r in measure_kino(21, 16384, 10, solver=s21, device=local_rank)]
                 s21.close()
                 for r in rows:
                     r["cpu_baseline"] = ref.get(r["function"]) if ref else None

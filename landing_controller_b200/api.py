@@ -52,7 +52,7 @@ class Options(ctypes.Structure):
                 ("mu_init", ctypes.c_double), ("bound_push", ctypes.c_double),
                 ("bound_frac", ctypes.c_double), ("bound_relax_factor", ctypes.c_double),
                 ("max_soc", ctypes.c_int), ("jam_iters", ctypes.c_int), ("jam_alpha", ctypes.c_double),
-                ("max_restarts", ctypes.c_int), ("reserved", ctypes.c_int * 5)]
+                ("max_restarts", ctypes.c_int), ("reserved", ctypes.c_int * 5), ("restart_mu", ctypes.c_double)]
 
 
 class Tvlqr(ctypes.Structure):

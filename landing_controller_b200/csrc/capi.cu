@@ -339,6 +339,7 @@ void landing_options_default(landing_options* o) {
   o->jam_iters = 5;
   o->max_restarts = 8;
   o->jam_alpha = 0.02;
+  o->restart_mu = 0.0;  // = mu_init
 }
 
 int landing_eval_batch(landing_ctx* c, long long B, int memspace, int layout, const landing_eval_io* io) {

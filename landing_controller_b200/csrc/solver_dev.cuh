@@ -1065,9 +1065,9 @@ __device__ void solve_one(const KParams& P, Ws& w, double* smem, long long b) {
     if (accepted && opt.jam_iters > 0 && tiny >= opt.jam_iters && restarts < opt.max_restarts) accepted = false;
     if (!accepted) {
       tiny = 0;
-      if (restarts < opt.max_restarts) {  // re-centre: slacks back inside their bounds, multipliers reset, mu = mu_init
+      if (restarts < opt.max_restarts) {  // re-centre: slacks back inside their bounds, multipliers reset, mu = restart_mu
         restarts++;
-        mu = opt.mu_init;
+        mu = opt.restart_mu > 0.0 ? opt.restart_mu : opt.mu_init;
         init_slacks(P, w, tab, mu);
         nfilt = 0;
         theta0 = -1.0;

@@ -50,6 +50,7 @@ void ip_options_default(ip_options *o) {
   o->delta_c = 1e-7;
   o->acceptable_tol = 1e-4;
   o->acceptable_iter = 0; /* (off by default: see DESIGN.md 3) */
+  o->restart_mu = 0.0; /* = mu_init */
 }
 
 typedef struct {
@@ -851,10 +852,10 @@ static int ip_solve_ws(ipws *w, const double *p, const double *x0, const ip_opti
     if (!accepted) {
       tiny = 0;
       /* no restoration phase: re-centre instead -- slacks pushed back inside their bounds at the
-       * current x, multipliers reset, barrier parameter back to mu_init, filter cleared */
+       * current x, multipliers reset, barrier parameter back to restart_mu, filter cleared */
       if (restarts < opt->max_restarts) {
         restarts++;
-        mu = opt->mu_init;
+        mu = opt->restart_mu > 0.0 ? opt->restart_mu : opt->mu_init;
         init_slacks(w, opt, mu);
         w->nfilt = 0;
         theta0 = -1;

@@ -57,6 +57,7 @@ typedef struct ip_options {
    * dual infeasibility 1e10, complementarity 1e-2).  Status 5.  acceptable_iter = 0 switches it off. */
   double acceptable_tol;
   int acceptable_iter;
+  double restart_mu; /* barrier parameter a re-centring restarts from (<= 0: mu_init); landing_options.restart_mu */
 } ip_options;
 
 typedef struct ip_result {

@@ -15,7 +15,8 @@ class IpOptions(ctypes.Structure):
                 ("jam_alpha", ctypes.c_double), ("jam_iters", ctypes.c_int), ("max_restarts", ctypes.c_int),
                 ("run_Qf", ctypes.c_double * 3), ("kin_box", ctypes.c_double * 3),
                 ("formulation", ctypes.c_int), ("cs", ctypes.POINTER(ctypes.c_int)), ("QX", ctypes.c_double * 12),
-                ("delta_c", ctypes.c_double), ("acceptable_tol", ctypes.c_double), ("acceptable_iter", ctypes.c_int)]
+                ("delta_c", ctypes.c_double), ("acceptable_tol", ctypes.c_double), ("acceptable_iter", ctypes.c_int),
+                ("restart_mu", ctypes.c_double)]
 
     def set_schedule(self, cs, QX):
         """fixed-contact-schedule formulation: cs [N-1, 4] of 0/1 (kept alive), running state weights QX [12]"""

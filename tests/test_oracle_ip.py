@@ -141,3 +141,16 @@ def test_fixed_contact_schedule_reference_problem_and_config0():
     assert r["status"][0] == 0 and r["iters"][0] < 60
     X, c, f = _check_schedule_solution(r["x"][0], N, cs)
     assert abs(X[-1, 9]) < 0.2 and abs(X[-1, 11]) < 0.3                        # the forward and vertical speed are absorbed
+
+
+def test_restart_mu_option_default_is_mu_init():
+    """restart_mu <= 0 (the default) re-centres to mu_init: identical results to restart_mu = mu_init; a smaller value
+    changes the iteration (and on these grid drops shortens it) without losing a scenario."""
+    from landing_controller_b200.sweeps import grid_sweep
+    drops = grid_sweep(1024)[::64]
+    a = solve_cpu(30, drops)
+    b = solve_cpu(30, drops, opt=default_options(restart_mu=0.1))
+    c = solve_cpu(30, drops, opt=default_options(restart_mu=0.01))
+    assert np.array_equal(a["iters"], b["iters"]) and np.array_equal(a["x"], b["x"])
+    assert (a["status"] == 0).all() and (c["status"] == 0).all()
+    assert not np.array_equal(a["iters"], c["iters"]) and c["iters"].sum() < a["iters"].sum()
