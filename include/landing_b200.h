@@ -228,6 +228,30 @@ const long long *landing_kino_sparsity(int n_knots); /* CCS {nrow, ncol, colind[
 int landing_kino_eval_batch(landing_ctx *ctx, long long B, int memspace, int layout, const landing_kino_problem *pb,
                             const double *x, double *g, double *jac);
 
+/* The rest of what a solver of the kino-dynamic NLP needs per drop condition -- what generate_landingCtrller_KNITRO.m
+ * :198-262,300-327 computes before it calls the solver: the bounds lbg / ubg [B x m] (Opti canonical form of :93-193
+ * with q_init / qd_init / c_init of the drop, the velocity-dependent kinematic box kin_box_limits.m of the body-frame
+ * velocity :246-248, initial feet c_init :232-236), the initial guess x0 [B x n_x] = [X; jpos_guess; U] assembled
+ * from an SRB solution x_srb [B x (36N-24)] as landing_solve_batch returns it (:302-323; NULL: the reference
+ * trajectories Xref / Uref of :272-286, which are also the SRB stage's own initial guess), and the terminal cost
+ * f = (X_N - Xref_N)' QN (X_N - Xref_N) with its gradient (:86-88).  drops [B x 12] = (q_init, qd_init) as for
+ * landing_solve_batch.  Any output may be NULL.  Defaults = the values of :214-262. */
+typedef struct landing_kino_setup {
+  double q_term_min[6], q_term_max[6], qd_term_min[6], qd_term_max[6]; /* :214-217 */
+  double z_min;        /* q_min(3) = 0.075 (:219; only the z bound is enforced, :184) */
+  double l_leg_max;    /* 0.4 */
+  double jpos_min[12], jpos_max[12]; /* (-pi/3, -pi/2, 0), (pi/3, pi/2, 3 pi/4) per leg */
+  double tau_max[3];   /* gear ratio x 3 Nm: 18, 18, 27.99 (get_robot_model.m:237-241) */
+  double QN[12];       /* 0 0 100 10 10 0 10 10 10 10 10 10 */
+  double q_term_ref[6], qd_term_ref[6]; /* (0 0 0.25 0 0 0), 0 */
+  double jpos_guess[3]; /* 0, -pi/4, pi/2 (:325) */
+} landing_kino_setup;
+void landing_kino_setup_default(landing_kino_setup *ks);
+int landing_kino_setup_batch(landing_ctx *ctx, long long B, int memspace, int layout, const landing_kino_setup *ks,
+                             const double *drops, const double *x_srb, double *lbg, double *ubg, double *x0);
+int landing_kino_cost_batch(landing_ctx *ctx, long long B, int memspace, int layout, const landing_kino_setup *ks,
+                            const double *x, double *f, double *grad_f);
+
 /* Measured FP64 FMA throughput of the context's device in TFLOP/s (a DFMA micro-kernel timed with CUDA
  * events): the roofline denominator of the interior-point kernel, which is FP64-pipe bound by design. */
 int landing_fp64_peak(landing_ctx *ctx, double *tflops);

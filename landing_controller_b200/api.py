@@ -67,6 +67,17 @@ class KinoProblem(ctypes.Structure):
                 ("Ib_inv", ctypes.c_double * 3), ("dt", _dp)]
 
 
+class KinoSetup(ctypes.Structure):
+    """landing_kino_setup: bounds / initial-guess / cost data of the kino-dynamic NLP
+    (generate_landingCtrller_KNITRO.m:214-262,325)."""
+    _fields_ = [("q_term_min", ctypes.c_double * 6), ("q_term_max", ctypes.c_double * 6),
+                ("qd_term_min", ctypes.c_double * 6), ("qd_term_max", ctypes.c_double * 6),
+                ("z_min", ctypes.c_double), ("l_leg_max", ctypes.c_double),
+                ("jpos_min", ctypes.c_double * 12), ("jpos_max", ctypes.c_double * 12), ("tau_max", ctypes.c_double * 3),
+                ("QN", ctypes.c_double * 12), ("q_term_ref", ctypes.c_double * 6), ("qd_term_ref", ctypes.c_double * 6),
+                ("jpos_guess", ctypes.c_double * 3)]
+
+
 class SolveIO(ctypes.Structure):
     _fields_ = [("drops", _dp), ("x0", _dp), ("x_star", _dp), ("f_star", _dp), ("lam_g", _dp),
                 ("viol", _dp), ("status", _ip), ("iters", _ip)]
@@ -98,6 +109,13 @@ def load_library(path=LIB_PATH):
         lib.landing_kino_sparsity.argtypes = [ctypes.c_int]
         lib.landing_kino_eval_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
                                                 ctypes.POINTER(KinoProblem), _dp, _dp, _dp]
+    if hasattr(lib, "landing_kino_setup_batch"):
+        lib.landing_kino_setup_default.argtypes = [ctypes.POINTER(KinoSetup)]
+        lib.landing_kino_setup_default.restype = None
+        lib.landing_kino_setup_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                                 ctypes.POINTER(KinoSetup), _dp, _dp, _dp, _dp, _dp]
+        lib.landing_kino_cost_batch.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int, ctypes.c_int,
+                                                ctypes.POINTER(KinoSetup), _dp, _dp, _dp]
     lib.landing_launch_count.restype = ctypes.c_longlong
     lib.landing_launch_count.argtypes = [ctypes.c_void_p]
     if hasattr(lib, "landing_fp64_peak"):
@@ -377,6 +395,42 @@ class LandingSolver:
         B = x.shape[0] if layout == AOS else x.shape[1]
         self._check(self.lib.landing_kino_eval_batch(self.ctx, B, DEVICE, layout, ctypes.byref(pb), _ptr(x), _ptr(g), _ptr(jac)),
                     "landing_kino_eval_batch")
+
+    def kino_setup_data(self):
+        """landing_kino_setup with the reference's values (generate_landingCtrller_KNITRO.m:214-262,325)."""
+        ks = KinoSetup()
+        self.lib.landing_kino_setup_default(ctypes.byref(ks))
+        return ks
+
+    def kino_setup_host(self, drops, x_srb=None, ks=None, want_bounds=True, want_x0=True):
+        """lbg, ubg [B, m] and the initial guess x0 [B, n_x] = [X; jpos_guess; U] of the kino-dynamic NLP for a batch of
+        drop conditions [B, 12]; x_srb [B, 36N-24]: SRB solutions (landing_solve_batch) to start from, None: the
+        reference trajectories (generate_landingCtrller_KNITRO.m:272-286,302-325).  Host arrays, AoS."""
+        d = self.kino_dims()
+        ks = ks or self.kino_setup_data()
+        drops = np.ascontiguousarray(drops, dtype=np.float64)
+        B = drops.shape[0]
+        if x_srb is not None:
+            x_srb = np.ascontiguousarray(x_srb, dtype=np.float64)
+            if x_srb.shape != (B, 36 * self.N - 24):
+                raise ValueError("x_srb must be [B, 36N-24]")
+        lb = np.zeros((B, d["m"])) if want_bounds else None
+        ub = np.zeros((B, d["m"])) if want_bounds else None
+        x0 = np.zeros((B, d["nx"])) if want_x0 else None
+        self._check(self.lib.landing_kino_setup_batch(self.ctx, B, HOST, AOS, ctypes.byref(ks), _ptr(drops), _ptr(x_srb),
+                                                      _ptr(lb), _ptr(ub), _ptr(x0)), "landing_kino_setup_batch")
+        return lb, ub, x0
+
+    def kino_cost_host(self, x, ks=None):
+        """Terminal cost f [B] and its gradient [B, n_x] of the kino-dynamic NLP (generate_landingCtrller_KNITRO.m:86-88)."""
+        d = self.kino_dims()
+        ks = ks or self.kino_setup_data()
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        B = x.shape[0]
+        f, gf = np.zeros(B), np.zeros((B, d["nx"]))
+        self._check(self.lib.landing_kino_cost_batch(self.ctx, B, HOST, AOS, ctypes.byref(ks), _ptr(x), _ptr(f), _ptr(gf)),
+                    "landing_kino_cost_batch")
+        return f, gf
 
     def synchronize(self):
         self._check(self.lib.landing_synchronize(self.ctx), "landing_synchronize")

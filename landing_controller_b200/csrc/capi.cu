@@ -228,6 +228,102 @@ int landing_kino_dims(int N, long long d[4]) {
 
 const long long* landing_kino_sparsity(int N) { return N < 3 ? nullptr : get_kino_plan(N)->sparsity.data(); }
 
+void landing_kino_setup_default(landing_kino_setup* k) {
+  // generate_landingCtrller_KNITRO.m:214-262,325; get_robot_model.m:237-241
+  std::memset(k, 0, sizeof(*k));
+  const double qtmin[6] = {-10, -10, 0.15, -0.1, -0.1, -10}, qtmax[6] = {10, 10, 5, 0.1, 0.1, 10};
+  const double qdtmin[6] = {-10, -10, -10, -.5, -.5, -.5}, qdtmax[6] = {10, 10, 10, .5, .5, .5};
+  const double QN[12] = {0, 0, 100, 10, 10, 0, 10, 10, 10, 10, 10, 10};
+  const double PI = 3.14159265358979323846;
+  for (int i = 0; i < 6; i++) {
+    k->q_term_min[i] = qtmin[i]; k->q_term_max[i] = qtmax[i];
+    k->qd_term_min[i] = qdtmin[i]; k->qd_term_max[i] = qdtmax[i];
+  }
+  for (int i = 0; i < 12; i++) k->QN[i] = QN[i];
+  k->q_term_ref[2] = 0.25;
+  k->z_min = 0.075;
+  k->l_leg_max = 0.4;
+  for (int l = 0; l < 4; l++) {
+    k->jpos_min[3 * l] = -PI / 3; k->jpos_min[3 * l + 1] = -PI / 2; k->jpos_min[3 * l + 2] = 0.0;
+    k->jpos_max[3 * l] = PI / 3; k->jpos_max[3 * l + 1] = PI / 2; k->jpos_max[3 * l + 2] = 3 * PI / 4;
+  }
+  k->tau_max[0] = 18.0; k->tau_max[1] = 18.0; k->tau_max[2] = 27.99;
+  k->jpos_guess[0] = 0.0; k->jpos_guess[1] = -PI / 4; k->jpos_guess[2] = PI / 2;
+}
+
+// inputs / outputs of the two set-up calls staged through the context's buffer when they live in host memory
+struct KinoBuf { const double* in; double* out; long long n; };
+static int kino_stage(landing_ctx* c, long long B, int memspace, KinoBuf* bufs, int nb, const double** din, double** dout) {
+  size_t tot = 0;
+  for (int i = 0; i < nb; i++) if (bufs[i].in || bufs[i].out) tot += sizeof(double) * bufs[i].n * B;
+  if (memspace != LANDING_HOST) {
+    for (int i = 0; i < nb; i++) { din[i] = bufs[i].in; dout[i] = bufs[i].out; }
+    return LANDING_OK;
+  }
+  int rc = ensure_stage(c, tot + 256);
+  if (rc) return rc;
+  char* s = (char*)c->stage;
+  for (int i = 0; i < nb; i++) {
+    din[i] = nullptr; dout[i] = nullptr;
+    if (!bufs[i].in && !bufs[i].out) continue;
+    const size_t by = sizeof(double) * bufs[i].n * B;
+    if (bufs[i].in) { CU(cudaMemcpyAsync(s, bufs[i].in, by, cudaMemcpyHostToDevice, c->stream)); din[i] = (const double*)s; }
+    else dout[i] = (double*)s;
+    s += by;
+  }
+  return LANDING_OK;
+}
+static int kino_unstage(landing_ctx* c, long long B, int memspace, KinoBuf* bufs, int nb, double** dout) {
+  if (memspace != LANDING_HOST) return LANDING_OK;
+  for (int i = 0; i < nb; i++)
+    if (bufs[i].out) CU(cudaMemcpyAsync(bufs[i].out, dout[i], sizeof(double) * bufs[i].n * B, cudaMemcpyDeviceToHost, c->stream));
+  CU(cudaStreamSynchronize(c->stream));
+  return LANDING_OK;
+}
+
+int landing_kino_setup_batch(landing_ctx* c, long long B, int memspace, int layout, const landing_kino_setup* ks,
+                             const double* drops, const double* x_srb, double* lbg, double* ubg, double* x0) {
+  if (!c || !ks || !drops || B < 0) return fail(LANDING_ERR_ARG, "landing_kino_setup_batch: bad arguments");
+  if (B == 0 || (!lbg && !ubg && !x0)) return LANDING_OK;
+  DeviceGuard guard_(c->device);
+  auto pl = get_kino_plan(c->N);
+  const long long nsrb = 36LL * c->N - 24;
+  KinoBuf bufs[5] = {{drops, nullptr, 12}, {x_srb, nullptr, nsrb}, {nullptr, lbg, pl->m}, {nullptr, ubg, pl->m}, {nullptr, x0, pl->nx}};
+  const double* din[5]; double* dout[5];
+  int rc = kino_stage(c, B, memspace, bufs, 5, din, dout);
+  if (rc) return rc;
+  KinoSetupArgs a{};
+  a.N = c->N; a.B = B; a.ks = *ks;
+  a.drops = make_cview(din[0], 12, B, layout);
+  a.x_srb = make_cview(din[1], nsrb, B, layout);
+  a.lbg = make_view(dout[2], pl->m, B, layout);
+  a.ubg = make_view(dout[3], pl->m, B, layout);
+  a.x0 = make_view(dout[4], pl->nx, B, layout);
+  c->launches += launch_kino_setup(a, c->stream);
+  CU(cudaGetLastError());
+  return kino_unstage(c, B, memspace, bufs, 5, dout);
+}
+
+int landing_kino_cost_batch(landing_ctx* c, long long B, int memspace, int layout, const landing_kino_setup* ks,
+                            const double* x, double* f, double* grad_f) {
+  if (!c || !ks || !x || B < 0) return fail(LANDING_ERR_ARG, "landing_kino_cost_batch: bad arguments");
+  if (B == 0 || (!f && !grad_f)) return LANDING_OK;
+  DeviceGuard guard_(c->device);
+  auto pl = get_kino_plan(c->N);
+  KinoBuf bufs[3] = {{x, nullptr, pl->nx}, {nullptr, f, 1}, {nullptr, grad_f, pl->nx}};
+  const double* din[3]; double* dout[3];
+  int rc = kino_stage(c, B, memspace, bufs, 3, din, dout);
+  if (rc) return rc;
+  KinoSetupArgs a{};
+  a.N = c->N; a.B = B; a.ks = *ks;
+  a.x = make_cview(din[0], pl->nx, B, layout);
+  a.f = make_view(dout[1], 1, B, layout);
+  a.grad_f = make_view(dout[2], pl->nx, B, layout);
+  c->launches += launch_kino_cost(a, c->stream);
+  CU(cudaGetLastError());
+  return kino_unstage(c, B, memspace, bufs, 3, dout);
+}
+
 int landing_kino_eval_batch(landing_ctx* c, long long B, int memspace, int layout, const landing_kino_problem* pb,
                             const double* x, double* g, double* jac) {
   if (!c || !pb || !pb->dt || !x || B < 0) return fail(LANDING_ERR_ARG, "landing_kino_eval_batch: bad arguments");

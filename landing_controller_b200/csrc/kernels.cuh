@@ -77,6 +77,17 @@ struct KinoArgs {
   const int *gpos, *bpos;
 };
 int launch_kino(const KinoArgs& a, bool want_g, bool want_jac, cudaStream_t st);
+struct KinoSetupArgs {
+  int N;
+  long long B;
+  landing_kino_setup ks;
+  CView drops, x_srb;  // [12 x B]; [36N-24 x B] or null
+  View lbg, ubg, x0;   // any may be null
+  CView x;             // cost: [n_x x B]
+  View f, grad_f;
+};
+int launch_kino_setup(const KinoSetupArgs& a, cudaStream_t st);
+int launch_kino_cost(const KinoSetupArgs& a, cudaStream_t st);
 
 // returns number of kernel launches issued
 int launch_eval(const EvalArgs& a, cudaStream_t st);

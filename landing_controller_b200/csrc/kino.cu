@@ -161,6 +161,138 @@ __global__ void __launch_bounds__(128) k_kino_jac(KinoArgs a) {
     for (int i = 0; i < 48; i++) a.jac.at(__ldg(a.bpos + i), b) = 1.0;
 }
 
+// ---------------------------------------------------------------- bounds, initial guess, terminal cost
+// (generate_landingCtrller_KNITRO.m:198-262,300-327; include/landing_b200.h: landing_kino_setup_batch)
+__device__ __forceinline__ void rot_xyz(const double* rpy, double* R) {  // rpyToRotMat_xyz.m:2, body -> world, row-major
+  double sr, cr, sp, cp, sy, cy;
+  sincos(rpy[0], &sr, &cr);
+  sincos(rpy[1], &sp, &cp);
+  sincos(rpy[2], &sy, &cy);
+  R[0] = cp * cy; R[1] = -(cp * sy); R[2] = sp;
+  R[3] = cr * sy + sr * sp * cy; R[4] = cr * cy - sr * sp * sy; R[5] = -(sr * cp);
+  R[6] = sr * sy - cr * sp * cy; R[7] = sr * cy + cr * sp * sy; R[8] = cr * cp;
+}
+__device__ __forceinline__ double foot_sx(int l) { return l < 2 ? 1.0 : -1.0; }   // sideSign of :200 (x, y; z = 1)
+__device__ __forceinline__ double foot_sy(int l) { return (l & 1) ? 1.0 : -1.0; }
+__device__ __forceinline__ double kin_box_limit(double v, double bmax) {           // utilities_landing/kin_box_limits.m
+  return fabs(v) < 2.0 ? fabs(v * bmax / 2.0) : bmax;
+}
+
+__global__ void __launch_bounds__(128) k_kino_setup(KinoSetupArgs a) {
+  const long long b = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (b >= a.B) return;
+  const int N = a.N, k = blockIdx.y;
+  const landing_kino_setup& ks = a.ks;
+  const double INF = HUGE_VAL;
+  double q0[6], qd0[6], R0[9];
+#pragma unroll
+  for (int i = 0; i < 6; i++) { q0[i] = a.drops.get(i, b); qd0[i] = a.drops.get(6 + i, b); }
+  rot_xyz(q0 + 3, R0);
+  auto set = [&](long long row, double l, double u) {
+    if (a.lbg.p) a.lbg.at(row, b) = l;
+    if (a.ubg.p) a.ubg.at(row, b) = u;
+  };
+  // state of knot k of the initial guess: the SRB solution, else the reference trajectory (:272-275)
+  double Xk[12];
+  if (a.x0.p) {
+    const double t = (double)k / (double)(N - 1);
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const double from = i < 6 ? q0[i] : qd0[i - 6], to = i < 6 ? ks.q_term_ref[i] : ks.qd_term_ref[i - 6];
+      Xk[i] = a.x_srb.p ? a.x_srb.get(12LL * k + i, b) : from + (to - from) * t;
+      a.x0.at(12LL * k + i, b) = Xk[i];
+    }
+  }
+  if (k == N - 1) {  // boundary rows (:93-101)
+    if (a.lbg.p || a.ubg.p) {
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        set(i, q0[i], q0[i]);
+        set(6 + i, qd0[i], qd0[i]);
+        set(24 + i, ks.q_term_min[i], INF);
+        set(30 + i, -INF, ks.q_term_max[i]);
+        set(36 + i, ks.qd_term_min[i], INF);
+        set(42 + i, -INF, ks.qd_term_max[i]);
+      }
+#pragma unroll
+      for (int l = 0; l < 4; l++) {  // c_init (:232-236)
+        const double p[3] = {foot_sx(l) * 0.2, foot_sy(l) * 0.15, -0.3};
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          const double c = q0[i] + R0[3 * i] * p[0] + R0[3 * i + 1] * p[1] + R0[3 * i + 2] * p[2];
+          set(12 + 3 * l + i, c, c);
+        }
+      }
+    }
+    return;
+  }
+  if (a.x0.p) {
+    const long long jo = 12LL * N + 12LL * k, uo = 12LL * N + 12LL * (N - 1) + 24LL * k;
+#pragma unroll
+    for (int i = 0; i < 12; i++) a.x0.at(jo + i, b) = ks.jpos_guess[i % 3];  // (:325)
+    if (a.x_srb.p) {
+      for (int i = 0; i < 24; i++) a.x0.at(uo + i, b) = a.x_srb.get(12LL * N + 24LL * k + i, b);
+    } else {  // Uref (:276-286): reference feet under the reference body, no force
+      double Rk[9];
+      rot_xyz(Xk + 3, Rk);
+#pragma unroll
+      for (int l = 0; l < 4; l++) {
+        const double p[3] = {foot_sx(l) * 0.2, foot_sy(l) * 0.2, -0.3};
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          a.x0.at(uo + 3 * l + i, b) = Xk[i] + Rk[3 * i] * p[0] + Rk[3 * i + 1] * p[1] + Rk[3 * i + 2] * p[2];
+          a.x0.at(uo + 12 + 3 * l + i, b) = 0.0;
+        }
+      }
+    }
+  }
+  if (!a.lbg.p && !a.ubg.p) return;
+  // kinematic box from the body-frame velocity of the drop (:246-248)
+  const double vb0 = R0[0] * qd0[3] + R0[3] * qd0[4] + R0[6] * qd0[5], vb1 = R0[1] * qd0[3] + R0[4] * qd0[4] + R0[7] * qd0[5];
+  const double kx = 0.125 + kin_box_limit(vb0, 0.15), ky = 0.125 + kin_box_limit(vb1, 0.25);
+  const bool last = k == N - 2;
+  const long long base = 48 + (long long)ROWS_INT * k;
+  for (int i = 0; i < 12; i++) set(base + i, 0.0, 0.0);        // dynamics (:128-131)
+  for (int l = 0; l < 4; l++) set(base + 12 + l, 0.0, INF);    // f_z >= 0 (:134)
+  const int per_leg = last ? 9 : 15;
+  for (int l = 0; l < 4; l++) {
+    long long r = base + 16 + per_leg * l;
+    set(r++, 0.0, INF);          // c_z >= 0 (:141)
+    set(r++, -INF, 0.001);       // f_z c_z <= 0.001 (:142)
+    if (!last) {
+      for (int i = 0; i < 3; i++) set(r++, -INF, 0.001);   // no-slip (:145-146)
+      for (int i = 0; i < 3; i++) set(r++, -0.001, INF);
+    }
+    set(r++, -kx, kx);                                      // kinematic box (:161-167)
+    if ((l & 1) == 0) set(r++, -ky, 0.05); else set(r++, -0.05, ky);
+    set(r++, -0.4, -0.075);
+    set(r++, -INF, ks.l_leg_max * ks.l_leg_max);            // leg length (:168)
+    for (int i = 0; i < 3; i++) set(r++, -ks.tau_max[i], ks.tau_max[i]);  // torques (:173-175)
+  }
+  long long r = base + 16 + 4 * per_leg;
+  for (int i = 0; i < 16; i++) set(r++, -INF, 0.0);         // friction pyramid (:179-182)
+  set(r++, ks.z_min, INF);                                  // z_k >= q_min(3) (:185)
+  for (int i = 0; i < 12; i++) set(r++, -0.01, INF);        // c - FK (:190-191)
+  for (int i = 0; i < 12; i++) set(r++, -INF, 0.01);
+  for (int i = 0; i < 12; i++) set(r++, ks.jpos_min[i], INF);  // joint limits (:192-193)
+  for (int i = 0; i < 12; i++) set(r++, -INF, ks.jpos_max[i]);
+}
+
+// f = (X_N - Xref_N)' QN (X_N - Xref_N) (:86-88); grad_f is pre-zeroed by the launcher
+__global__ void __launch_bounds__(128) k_kino_cost(KinoSetupArgs a) {
+  const long long b = (long long)blockIdx.x * 128 + threadIdx.x;
+  if (b >= a.B) return;
+  const long long xo = 12LL * (a.N - 1);
+  double fv = 0.0;
+#pragma unroll
+  for (int i = 0; i < 12; i++) {
+    const double d = a.x.get(xo + i, b) - (i < 6 ? a.ks.q_term_ref[i] : a.ks.qd_term_ref[i - 6]);
+    fv += a.ks.QN[i] * d * d;
+    if (a.grad_f.p) a.grad_f.at(xo + i, b) = 2.0 * a.ks.QN[i] * d;
+  }
+  if (a.f.p) a.f.at(0, b) = fv;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------- host: pattern and CCS tables
@@ -239,6 +371,17 @@ int launch_kino(const KinoArgs& a, bool want_g, bool want_jac, cudaStream_t st) 
     n += 8;
   }
   return n;
+}
+
+int launch_kino_setup(const KinoSetupArgs& a, cudaStream_t st) {
+  k_kino_setup<<<dim3((unsigned)((a.B + 127) / 128), a.N, 1), 128, 0, st>>>(a);
+  return 1;
+}
+
+int launch_kino_cost(const KinoSetupArgs& a, cudaStream_t st) {
+  if (a.grad_f.p) cudaMemsetAsync(a.grad_f.p, 0, sizeof(double) * (12LL * a.N + 36LL * (a.N - 1)) * a.B, st);
+  k_kino_cost<<<(unsigned)((a.B + 127) / 128), 128, 0, st>>>(a);
+  return 1;
 }
 
 }  // namespace srb

@@ -112,3 +112,67 @@ def test_gpu_kino_functions_match_the_oracle(N):
         QN = np.array([0, 0, 100, 10, 10, 0, 10, 10, 10, 10, 10, 10.0])
         r[240:252] += 2 * QN * (xs[240:252] - np.array([0, 0, 0.25, 0, 0, 0, 0, 0, 0, 0, 0, 0.0]))
         assert np.abs(r).max() <= 1e-4 * np.abs(Jd.T * lam).max()
+
+
+@pytest.mark.gpu
+def test_gpu_kino_setup_bounds_guess_and_cost():
+    """landing_kino_setup_batch / landing_kino_cost_batch: what generate_landingCtrller_KNITRO.m computes per drop before
+    it calls the solver.  Bounds against the oracle (oracle/kino_ref.py:bounds) with the drop's c_init and velocity-
+    dependent kinematic box; at the drop conditions of the two STORED KNITRO solutions the stored points must be feasible
+    for the library's bounds (which pins c_init, kin_box and the row order against reference output); initial guess from
+    an SRB solution and from the reference trajectories; terminal cost and gradient."""
+    import landing_controller_b200 as lc
+    N = 21
+    s = lc.LandingSolver(N=N, device=0)
+    d = s.kino_dims()
+    ss = np.array([[1, -1, 1], [1, 1, 1], [-1, -1, 1], [-1, 1, 1.0]])
+    drops = lc.random_sweep(6, seed=3)
+    xs = []
+    for i, tag in enumerate(("ms", "gs")):  # the stored solutions' own drop conditions
+        _, x, _, (q0, qd0, _) = stored(tag)
+        drops[i, :6], drops[i, 6:] = q0, qd0
+        xs.append(x)
+    rng = np.random.default_rng(0)
+    x_srb = rng.normal(size=(6, 36 * N - 24))
+    lb, ub, x0 = s.kino_setup_host(drops, x_srb=x_srb)
+    for b in range(6):
+        pbo = kr.default_problem(N)
+        R = kr.rpy_to_rot_xyz(drops[b, 3:6])
+        vb = R.T @ drops[b, 9:12]
+        pbo["kin_box"] = np.array([kr.kin_box_limits(vb[0], "x"), kr.kin_box_limits(vb[1], "y")])
+        c_init = np.concatenate([drops[b, :3] + R @ (ss[l] * np.array([0.2, 0.15, -0.3])) for l in range(4)])
+        lo, uo = kr.bounds(pbo, drops[b, :6], drops[b, 6:], c_init)
+        assert np.array_equal(np.isfinite(lo), np.isfinite(lb[b])) and np.array_equal(np.isfinite(uo), np.isfinite(ub[b]))
+        fl, fu = np.isfinite(lo), np.isfinite(uo)
+        assert np.max(np.abs(lb[b][fl] - lo[fl])) <= 1e-15 and np.max(np.abs(ub[b][fu] - uo[fu])) <= 1e-15
+        # initial guess: X and U of the SRB solution around the constant joint-angle guess
+        assert np.array_equal(x0[b, :12 * N], x_srb[b, :12 * N]) and np.array_equal(x0[b, 24 * N - 12:], x_srb[b, 12 * N:])
+        assert np.allclose(x0[b, 12 * N:24 * N - 12], np.tile([0, -np.pi / 4, np.pi / 2], 4 * (N - 1)), atol=1e-15)
+    for i, tag in enumerate(("ms", "gs")):
+        pb, x, _, _ = stored(tag)
+        g = kr.eval_g(pb, x)
+        viol = np.maximum(np.maximum(lb[i] - g, g - ub[i]), 0.0)
+        assert viol.max() <= (1e-6 if tag == "ms" else 5e-5), (tag, viol.max(), int(viol.argmax()))
+    # no SRB solution: the reference trajectories Xref / Uref (:272-286)
+    _, _, xr = s.kino_setup_host(drops, want_bounds=False)
+    X, J, U = kr.split(xr[2], N)
+    q_ref = np.array([0, 0, 0.25, 0, 0, 0.0])
+    for k in (0, 7, N - 1):
+        t = k / (N - 1)
+        assert np.allclose(X[k, :6], drops[2, :6] + (q_ref - drops[2, :6]) * t, atol=1e-14)
+        assert np.allclose(X[k, 6:], drops[2, 6:] * (1 - t), atol=1e-14)
+    k = 5
+    Rk = kr.rpy_to_rot_xyz(X[k, 3:6])
+    cref = np.concatenate([X[k, :3] + Rk @ (ss[l] * np.array([0.2, 0.2, -0.3])) for l in range(4)])
+    assert np.allclose(U[k, :12], cref, atol=1e-14) and np.all(U[k, 12:] == 0)
+    # terminal cost (:86-88)
+    xx = rng.normal(size=(4, d["nx"]))
+    f, gf = s.kino_cost_host(xx)
+    QN = np.array([0, 0, 100, 10, 10, 0, 10, 10, 10, 10, 10, 10.0])
+    ref = np.array([0, 0, 0.25, 0, 0, 0, 0, 0, 0, 0, 0, 0.0])
+    e = xx[:, 12 * (N - 1):12 * N] - ref
+    assert np.allclose(f, (QN * e * e).sum(1), rtol=1e-14)
+    go = np.zeros_like(xx)
+    go[:, 12 * (N - 1):12 * N] = 2 * QN * e
+    assert np.allclose(gf, go, rtol=1e-14, atol=0)
+    s.close()
