@@ -23,7 +23,7 @@ __device__ __forceinline__ double skew_entry(const double* v, int i, int j) {  /
   return s * v[k];
 }
 
-__global__ void __launch_bounds__(TNT) k_tvlqr(TvlqrArgs a) {
+__global__ void __launch_bounds__(TNT, 5) k_tvlqr(TvlqrArgs a) {
   __shared__ double P[NSV * LDA], A[NSV * LDA], W[NSV * LDA], Bm[NSV * LDB], S[NSV * LDB];
   __shared__ double xd[24], ud[12], Rt[9], Ibi[9], tau[3], fsum[3], Ibom[3], Rinv[12];
   const long long b = blockIdx.x;

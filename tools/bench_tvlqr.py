@@ -9,7 +9,7 @@ import landing_controller_b200 as lc
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 30
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 4096
-s = lc.LandingSolver(N=N)
+s = lc.LandingSolver(N=N, lib_path=os.environ.get("LANDING_LIB", lc.api.LIB_PATH))
 dev = torch.device("cuda:0")
 drops = lc.grid_sweep(1024)
 x = torch.tensor(s.solve(drops)["x"], device=dev).repeat((B + 1023) // 1024, 1)[:B].contiguous()
