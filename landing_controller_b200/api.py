@@ -421,6 +421,13 @@ class LandingSolver:
                                                       _ptr(lb), _ptr(ub), _ptr(x0)), "landing_kino_setup_batch")
         return lb, ub, x0
 
+    def kino_setup_device(self, drops, x_srb=None, lbg=None, ubg=None, x0=None, ks=None, layout=AOS):
+        """Same with CUDA torch tensors already in HBM (enqueued on the library stream); any output may be None."""
+        ks = ks or self.kino_setup_data()
+        B = drops.shape[0] if layout == AOS else drops.shape[1]
+        self._check(self.lib.landing_kino_setup_batch(self.ctx, B, DEVICE, layout, ctypes.byref(ks), _ptr(drops), _ptr(x_srb),
+                                                      _ptr(lbg), _ptr(ubg), _ptr(x0)), "landing_kino_setup_batch")
+
     def kino_cost_host(self, x, ks=None):
         """Terminal cost f [B] and its gradient [B, n_x] of the kino-dynamic NLP (generate_landingCtrller_KNITRO.m:86-88)."""
         d = self.kino_dims()
