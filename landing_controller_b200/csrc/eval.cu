@@ -67,11 +67,14 @@ struct ScatterSink {  // g / jac / hess values straight into the CCS value array
 // the same output, and the compile-time filter leaves each thread a quarter of the Jacobian entries and 9 accumulators
 // (one thread per knot needs 255 registers + spills and runs at 8 warps per SM).  Measured on B200 (16k scenarios, N = 30,
 // SoA): NGP = 1 0.56 ms, NGP = 4 0.84 ms -- the parts repeat the rotation / wrench sub-expressions and re-read x, which
-// costs more than the registers it frees -- so one part is the default.
+// costs more than the registers it frees -- so one part is the default.  Dealing the entries by ROWS to the four warps of
+// a 32-scenario CTA instead (the split of k_eval's Jacobian kernel; c_q / f_q sums complete in part q, the X_k partial
+// sums through shared memory) was measured too: 0.60 ms at 2 CTAs per SM (255 registers), 1.00 ms at 3, 0.83 ms at 4.
 #ifndef EVAL_NP_GRAD
 #define EVAL_NP_GRAD 1
 #endif
 constexpr int NGP = EVAL_NP_GRAD;
+
 __device__ __forceinline__ constexpr int grad_owner(int var) {  // var: 0-11 X | 12-23 c | 24-35 f ; X+, c+: nobody
   return var < 12 ? (var & 3) : (var < 36 ? ((var - 12) % 12) / 3 : -1);
 }
@@ -222,44 +225,30 @@ __device__ __forceinline__ void grad_x_part(const EvalArgs& a, const Knot& kn, c
 // dynamics rows and f_z,l of knot k-1 in the no-slip rows, both in closed form (no second template evaluation).  The
 // boundary thread owns X_{N-1}.  (The former version did 48-60 RED.ADD.F64 per thread on a pre-zeroed array: 29 % of the
 // HBM bandwidth.)  grad_p is pre-zeroed; only the eight scalar parameters shared by all knots are accumulated atomically.
-__global__ void __launch_bounds__(TPB, NGP > 1 ? 3 : 1) k_grad(EvalArgs a) {
-  const long long b = (long long)blockIdx.x * TPB + threadIdx.x;
-  const int k = blockIdx.y, N = a.pl.N;
-  if (b >= a.B) return;
+__device__ __forceinline__ void grad_boundary(const EvalArgs& a, long long b) {  // X_{N-1}: objective + terminal rows
+  const int N = a.pl.N;
   const ParamOff& o = a.pl.off;
-  if (k == N - 1) {
-    if (blockIdx.z != 0) return;
-    const int xo = 12 * (N - 1), pb = 36 + 104 * (N - 2);  // rows of the last knot (80-row layout: dynamics first)
-    const double lf = a.lam_f.get(0, b);
-    for (int i = 0; i < 12; i++) {
-      const double d = a.x.get(xo + i, b) - a.p.get(xo + i, b);
-      const double qn = a.p.get(o.QN + i, b);
-      if (a.grad_x.p) {
-        const int r1 = i < 6 ? 12 + i : 24 + (i - 6);
-        // X+ column of the last knot's dynamics rows: pos, rpy -> rows 0-5; omega -> rows 9-11; v -> rows 6-8
-        const int dr = i < 6 ? i : (i < 9 ? i + 3 : i - 3);
-        a.grad_x.at(xo + i, b) = lf * 2.0 * qn * d + a.lam_g.get(r1, b) + a.lam_g.get(r1 + 6, b) + a.lam_g.get(pb + dr, b);
-      }
-      if (a.grad_p.p) {
-        a.grad_p.at(xo + i, b) = -lf * 2.0 * qn * d;
-        a.grad_p.at(o.QN + i, b) = lf * d * d;
-      }
+  const int xo = 12 * (N - 1), pb = 36 + 104 * (N - 2);  // rows of the last knot (80-row layout: dynamics first)
+  const double lf = a.lam_f.get(0, b);
+  for (int i = 0; i < 12; i++) {
+    const double d = a.x.get(xo + i, b) - a.p.get(xo + i, b);
+    const double qn = a.p.get(o.QN + i, b);
+    if (a.grad_x.p) {
+      const int r1 = i < 6 ? 12 + i : 24 + (i - 6);
+      // X+ column of the last knot's dynamics rows: pos, rpy -> rows 0-5; omega -> rows 9-11; v -> rows 6-8
+      const int dr = i < 6 ? i : (i < 9 ? i + 3 : i - 3);
+      a.grad_x.at(xo + i, b) = lf * 2.0 * qn * d + a.lam_g.get(r1, b) + a.lam_g.get(r1 + 6, b) + a.lam_g.get(pb + dr, b);
     }
-    return;
-  }
-  Knot kn;
-  const bool last = (k == N - 2);
-  load_knot(a, k, b, kn, last);
-  LamRow lam{a.lam_g, b, 36 + 104 * k};
-  if (a.grad_x.p) {
-    switch (blockIdx.z) {  // (block-uniform)
-      case 0: grad_x_part<0>(a, kn, lam, k, b, last); break;
-      case 1: grad_x_part<1 % NGP>(a, kn, lam, k, b, last); break;
-      case 2: grad_x_part<2 % NGP>(a, kn, lam, k, b, last); break;
-      default: grad_x_part<3 % NGP>(a, kn, lam, k, b, last); break;
+    if (a.grad_p.p) {
+      a.grad_p.at(xo + i, b) = -lf * 2.0 * qn * d;
+      a.grad_p.at(o.QN + i, b) = lf * d * d;
     }
   }
-  if (blockIdx.z != 0) return;
+}
+
+// parameter sensitivities of one knot's rows (grad_gamma_p; pre-zeroed, shared scalars accumulated atomically)
+__device__ __forceinline__ void grad_p_knot(const EvalArgs& a, const Knot& kn, const LamRow& lam, int k, long long b, bool last) {
+  const ParamOff& o = a.pl.off;
   if (a.grad_p.p) {
     // parameter sensitivities of the knot rows: dt_k, mu, mass, Ib, Ib_inv
     double sf, cf, st, ct, sp, cp;
@@ -311,6 +300,30 @@ __global__ void __launch_bounds__(TPB, NGP > 1 ? 3 : 1) k_grad(EvalArgs a) {
       smu += -FRIC * kn.f[3 * l + 2] * (lam(fr + l) + lam(fr + 4 + l) + lam(fr + 8 + l) + lam(fr + 12 + l));
     atomicAdd(&a.grad_p.at(o.mu, b), smu);
   }
+}
+
+__global__ void __launch_bounds__(TPB, NGP > 1 ? 3 : 1) k_grad(EvalArgs a) {
+  const long long b = (long long)blockIdx.x * TPB + threadIdx.x;
+  const int k = blockIdx.y, N = a.pl.N;
+  if (b >= a.B) return;
+  if (k == N - 1) {
+    if (blockIdx.z == 0) grad_boundary(a, b);
+    return;
+  }
+  Knot kn;
+  const bool last = (k == N - 2);
+  load_knot(a, k, b, kn, last);
+  LamRow lam{a.lam_g, b, 36 + 104 * k};
+  if (a.grad_x.p) {
+    switch (blockIdx.z) {  // (block-uniform)
+      case 0: grad_x_part<0>(a, kn, lam, k, b, last); break;
+      case 1: grad_x_part<1 % NGP>(a, kn, lam, k, b, last); break;
+      case 2: grad_x_part<2 % NGP>(a, kn, lam, k, b, last); break;
+      default: grad_x_part<3 % NGP>(a, kn, lam, k, b, last); break;
+    }
+  }
+  if (blockIdx.z != 0) return;
+  grad_p_knot(a, kn, lam, k, b, last);
 }
 
 // lbg(p), ubg(p) -- optistack_internal.cpp:742-870 applied to generate_landingCtrller_IPOPT.m:90-169
