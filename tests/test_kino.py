@@ -175,4 +175,40 @@ def test_gpu_kino_setup_bounds_guess_and_cost():
     go = np.zeros_like(xx)
     go[:, 12 * (N - 1):12 * N] = 2 * QN * e
     assert np.allclose(gf, go, rtol=1e-14, atol=0)
+    # device buffers, SoA layout: the same numbers
+    import torch
+    dev = torch.device("cuda:0")
+    dT = torch.tensor(np.ascontiguousarray(drops.T), device=dev)
+    xT = torch.tensor(np.ascontiguousarray(x_srb.T), device=dev)
+    lbT = torch.zeros(d["m"], 6, dtype=torch.float64, device=dev)
+    ubT, x0T = torch.zeros_like(lbT), torch.zeros(d["nx"], 6, dtype=torch.float64, device=dev)
+    s.kino_setup_device(dT, x_srb=xT, lbg=lbT, ubg=ubT, x0=x0T, layout=lc.SOA)
+    s.synchronize()
+    assert np.array_equal(lbT.cpu().numpy().T, lb) and np.array_equal(ubT.cpu().numpy().T, ub)
+    assert np.array_equal(x0T.cpu().numpy().T, x0)
+    s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_kino_smallest_problem_and_ragged_batch():
+    """N = 3 (one interior knot + the last knot) and a batch that does not fill a CTA: g against the oracle, the Jacobian
+    against central differences of the oracle on every column."""
+    import landing_controller_b200 as lc
+    N, B = 3, 131
+    s = lc.LandingSolver(N=N, device=0)
+    d = s.kino_dims()
+    pbo = kr.default_problem(N)
+    pb = s.kino_problem(pbo["dt"], mu=pbo["mu"], mass=pbo["mass"], Ib=pbo["Ib"], Ib_inv=pbo["Ib_inv"])
+    x = np.random.default_rng(5).uniform(-0.6, 0.6, size=(B, d["nx"]))
+    g, jac = s.kino_eval_host(x, pb)
+    colind, row = s.kino_sparsity()
+    for b in (0, 127, 128, 130):
+        go = kr.eval_g(pbo, x[b])
+        assert np.max(np.abs(g[b] - go) / np.maximum(1.0, np.abs(go))) <= 1e-12
+    b = 130
+    Jd = np.zeros((d["m"], d["nx"]))
+    for c in range(d["nx"]):
+        Jd[row[colind[c]:colind[c + 1]], c] = jac[b, colind[c]:colind[c + 1]]
+    Jo = kr.jac_fd(pbo, x[b], literal=False)
+    assert np.max(np.abs(Jd - Jo)) <= 2e-6 * max(1.0, np.abs(Jo).max())
     s.close()
