@@ -2,6 +2,7 @@
 // Host side only: context, device staging of host buffers, launches.  No CPU compute path:
 // every entry point that produces numbers needs a CUDA device and fails loudly without one.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -48,6 +49,8 @@ struct landing_ctx {
   // grow-only device staging for host-buffer calls
   void* stage = nullptr;
   size_t stage_bytes = 0;
+  void* pin = nullptr;  // mapped pinned host buffer of small LANDING_HOST evaluation calls (zero-copy)
+  size_t pin_bytes = 0;
   // grow-only scratch for the transposed (SoA) copies of AoS batches
   void* tr = nullptr;
   size_t tr_bytes = 0;
@@ -99,6 +102,17 @@ static int ensure_tr(landing_ctx* c, size_t bytes) {
   c->tr_bytes = 0;
   CU(cudaMalloc(&c->tr, bytes));
   c->tr_bytes = bytes;
+  return LANDING_OK;
+}
+
+static int ensure_pin(landing_ctx* c, size_t bytes) {
+  if (bytes <= c->pin_bytes) return LANDING_OK;
+  if (c->pin) cudaFreeHost(c->pin);
+  c->pin = nullptr;
+  c->pin_bytes = 0;
+  if (bytes < (64u << 10)) bytes = 64u << 10;
+  CU(cudaHostAlloc(&c->pin, bytes, cudaHostAllocMapped));
+  c->pin_bytes = bytes;
   return LANDING_OK;
 }
 
@@ -178,6 +192,7 @@ void landing_destroy(landing_ctx* c) {
   DeviceGuard guard_(c->device);
   solver_free(c->ws);
   if (c->stage) cudaFree(c->stage);
+  if (c->pin) cudaFreeHost(c->pin);
   if (c->tr) cudaFree(c->tr);
   if (c->d_maps) cudaFree(c->d_maps);
   if (c->d_dt) cudaFree(c->d_dt);
@@ -452,19 +467,28 @@ int landing_eval_batch(landing_ctx* c, long long B, int memspace, int layout, co
   const double* din[4];
   double* dout[7];
   int* dstatus = io->status;
+  // Small host calls -- the CasADi ABI's one scenario per call above all -- go ZERO-COPY: inputs are copied by the CPU
+  // into a mapped pinned buffer, the kernels read them and write their results through the device alias of that buffer,
+  // and the CPU copies the results out after the stream synchronisation.  One launch + one synchronisation per call
+  // instead of up to eleven pageable cudaMemcpyAsync (LANDING_NO_ZEROCOPY=1 restores the staged copies).
+  bool zero_copy = false;
   if (memspace == LANDING_HOST) {
     size_t tot = 0;
     for (int i = 0; i < 4; i++) if (in_p[i]) tot += sizeof(double) * in_n[i] * B;
     for (int i = 0; i < 7; i++) if (out_p[i]) tot += sizeof(double) * out_n[i] * B;
     tot += sizeof(int) * B + 256;
-    int rc = ensure_stage(c, tot);
+    static const bool no_zc = getenv("LANDING_NO_ZEROCOPY") != nullptr;
+    // (not for nlp_grad: its parameter sensitivities are accumulated with device-scope atomics)
+    zero_copy = !no_zc && tot <= (512u << 10) && B < 64 && !io->grad_x && !io->grad_p;
+    int rc = zero_copy ? ensure_pin(c, tot) : ensure_stage(c, tot);
     if (rc) return rc;
-    char* cur = (char*)c->stage;
+    char* cur = (char*)(zero_copy ? c->pin : c->stage);
     for (int i = 0; i < 4; i++) {
       din[i] = nullptr;
       if (in_p[i]) {
         din[i] = (const double*)cur;
-        CU(cudaMemcpyAsync(cur, in_p[i], sizeof(double) * in_n[i] * B, cudaMemcpyHostToDevice, c->stream));
+        if (zero_copy) std::memcpy(cur, in_p[i], sizeof(double) * in_n[i] * B);
+        else CU(cudaMemcpyAsync(cur, in_p[i], sizeof(double) * in_n[i] * B, cudaMemcpyHostToDevice, c->stream));
         cur += sizeof(double) * in_n[i] * B;
       }
     }
@@ -524,7 +548,12 @@ int landing_eval_batch(landing_ctx* c, long long B, int memspace, int layout, co
       }
     CU(cudaGetLastError());
   }
-  if (memspace == LANDING_HOST) {
+  if (memspace == LANDING_HOST && zero_copy) {
+    CU(cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 7; i++)
+      if (out_p[i]) std::memcpy(out_p[i], dout[i], sizeof(double) * out_n[i] * B);
+    if (io->status) std::memcpy(io->status, dstatus, sizeof(int) * B);
+  } else if (memspace == LANDING_HOST) {
     for (int i = 0; i < 7; i++)
       if (out_p[i])
         CU(cudaMemcpyAsync(out_p[i], dout[i], sizeof(double) * out_n[i] * B, cudaMemcpyDeviceToHost, c->stream));
