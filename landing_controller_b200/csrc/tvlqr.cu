@@ -25,7 +25,7 @@ __device__ __forceinline__ double skew_entry(const double* v, int i, int j) {  /
 
 __global__ void __launch_bounds__(TNT, 5) k_tvlqr(TvlqrArgs a) {
   __shared__ double P[NSV * LDA], A[NSV * LDA], W[NSV * LDA], Bm[NSV * LDB], S[NSV * LDB];
-  __shared__ double xd[24], ud[12], Rt[9], Ibi[9], tau[3], fsum[3], Ibom[3], Rinv[12];
+  __shared__ double xd[24], ud[12], Rt[9], Ibi[9], tau[3], fsum[3], Ibom[3], Rinv[12], sc[6];
   const long long b = blockIdx.x;
   const int tid = threadIdx.x, N = a.N;
   const double* x = a.x_star + b * a.nx;
@@ -43,21 +43,27 @@ __global__ void __launch_bounds__(TNT, 5) k_tvlqr(TvlqrArgs a) {
   if (tid >= 32 && tid < 44) Rinv[tid - 32] = 1.0 / q.R[tid - 32];
   __syncthreads();
   const double hk = q.T / (double)(N - 1);
+  // knot interval of the reference point: the smallest ko with t <= (ko + 1) hk (capped at N - 2).  Searched once for the
+  // last time point; t only decreases afterwards, so the interval of the previous step is walked down (the search from 0 at
+  // every step was 14 % of the kernel's instructions, a dependent I2F-DMUL-DSETP chain that every thread repeated).
+  int ko = 0;
+  {
+    const double t_end = (q.n_steps - 1) * q.dt;
+    while (t_end > (ko + 1) * hk && ko < N - 2) ko++;
+  }
   for (int k = q.n_steps - 1; k >= 0; k--) {
     // reference point at t = k dt (quadruped_SRBM_NLP.m:478-487)
     const double t_int = k * q.dt;
-    int ko = 0;
-    while (t_int > (ko + 1) * hk && ko < N - 2) ko++;
+    while (ko > 0 && t_int <= ko * hk) ko--;
     const double al = ((ko + 1) * hk - t_int) / hk;
     if (tid < 12) xd[tid] = al * x[12 * ko + tid] + (1.0 - al) * x[12 * (ko + 1) + tid];
     else if (tid < 24) xd[tid] = x[12 * N + 24 * ko + (tid - 12)];
     else if (tid < 36) ud[tid - 24] = x[12 * N + 24 * ko + 12 + (tid - 24)];
     __syncthreads();
+    if (tid < 3) sincos(xd[3 + tid], &sc[tid], &sc[3 + tid]);  // (three lanes of warp 0, one angle each)
+    __syncwarp();
     if (tid == 0) {  // R' = rpyToRotMat(rpy) (body -> world), torque, force sum, Ib * omega
-      double sr, cr, sp, cp, sy, cy;
-      sincos(xd[3], &sr, &cr);
-      sincos(xd[4], &sp, &cp);
-      sincos(xd[5], &sy, &cy);
+      const double sr = sc[0], cr = sc[3], sp = sc[1], cp = sc[4], sy = sc[2], cy = sc[5];
       Rt[0] = cy * cp; Rt[1] = cy * sp * sr - sy * cr; Rt[2] = cy * sp * cr + sy * sr;
       Rt[3] = sy * cp; Rt[4] = sy * sp * sr + cy * cr; Rt[5] = sy * sp * cr - cy * sr;
       Rt[6] = -sp; Rt[7] = cp * sr; Rt[8] = cp * cr;
