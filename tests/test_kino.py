@@ -71,6 +71,36 @@ def test_stored_knitro_point_is_stationary_for_the_restated_jacobian():
     assert scale > 1e-2 and np.abs(r).max() <= 1e-4 * scale, (np.abs(r).max(), scale)
 
 
+def test_library_kino_pattern_covers_the_oracle_jacobian():
+    """Host logic of the product library, no GPU needed: the CCS pattern of dg/dx that landing_kino_sparsity builds (by
+    probing the typed knot function on the host) has the oracle's sizes, sorted rows per column, and contains every
+    non-zero of the oracle's finite-difference Jacobian at random points -- while staying sparse (13 536 entries at N=21)."""
+    import ctypes
+    import landing_controller_b200 as lc
+    lib = lc.load_library()
+    N = 21
+    d = (ctypes.c_longlong * 4)()
+    assert lib.landing_kino_dims(N, d) == 0
+    nx, m, nnz = int(d[1]), int(d[2]), int(d[3])
+    assert (nx, m) == (kr.dims(N)["nx"], kr.dims(N)["m"]) and nnz == 13536
+    sp = np.ctypeslib.as_array(lib.landing_kino_sparsity(N), shape=(2 + nx + 1 + nnz,))
+    assert sp[0] == m and sp[1] == nx
+    colind, row = sp[2:2 + nx + 1], sp[2 + nx + 1:]
+    assert colind[0] == 0 and colind[-1] == nnz and np.all(np.diff(colind) > 0)  # every variable enters some row
+    for c in range(nx):
+        r = row[colind[c]:colind[c + 1]]
+        assert np.all(np.diff(r) > 0) and r[0] >= 0 and r[-1] < m
+    pbo = kr.default_problem(N)
+    rng = np.random.default_rng(11)
+    cols = np.sort(rng.choice(nx, size=120, replace=False))
+    for rep in range(2):
+        x = rng.uniform(-0.7, 0.7, size=nx)
+        Jo = kr.jac_fd(pbo, x, cols=cols, literal=False)
+        for c in cols:
+            nzr = np.nonzero(np.abs(Jo[:, c]) > 1e-6)[0]
+            assert np.isin(nzr, row[colind[c]:colind[c + 1]]).all(), (c, nzr)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("N", [21, 30])
 def test_gpu_kino_functions_match_the_oracle(N):
