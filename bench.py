@@ -47,6 +47,7 @@ def pick_config(args, world):
     name = args.config if args.config != "auto" else ("1k" if world == 1 else "16k")
     cfg = dict(CONFIGS[name])
     cfg["name"] = name
+    cfg["restart_mu"] = getattr(args, "restart_mu", 0.0)
     if args.knots:
         cfg["knots"] = args.knots
     if args.batch:
@@ -62,7 +63,8 @@ def config_dict(cfg, world):
             "batch_per_gpu": cfg["total"] // world,
             "parallelism": "scenario-sharded x%d (interleaved shards of the %d-scenario sweep), one all-gather of the result records"
                            % (world, cfg["total"]),
-            "options": "tol 1e-4, constr_viol_tol 1e-3, max_iter 3000 (generate_landingCtrller_IPOPT.m:232-236)",
+            "options": "tol 1e-4, constr_viol_tol 1e-3, max_iter 3000 (generate_landingCtrller_IPOPT.m:232-236)"
+                       + (", NON-DEFAULT restart_mu %g" % cfg["restart_mu"] if cfg.get("restart_mu", 0.0) > 0.0 else ""),
             "l2": "GPU arm: the per-scenario solver scratch of the 296 resident CTAs (%.2f GB) exceeds the 126 MB L2 and "
                   "every step rewrites all of it; no flush needed" % (1e-9 * scratch_bytes(cfg["knots"], 296))}
 
@@ -190,6 +192,10 @@ def cpu_run(N, drops, threads, cfg=None):
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from oracle_ip import solve_cpu
     pb, opt = schedule_setup(cfg) if cfg and cfg.get("formulation") == "schedule" else (None, None)
+    if cfg and cfg.get("restart_mu", 0.0) > 0.0:
+        from oracle_ip import default_options
+        opt = opt or default_options()
+        opt.restart_mu = cfg["restart_mu"]
     t = time.perf_counter()
     r = solve_cpu(N, drops, opt, pb, threads=threads, fast=True)
     dt = time.perf_counter() - t
@@ -268,6 +274,8 @@ def main():
     ap.add_argument("--knots", type=int, default=0, help="override: knots per trajectory")
     ap.add_argument("--cpu-sample", type=int, default=0, help="scenarios in the CPU sample (0 = auto)")
     ap.add_argument("--no-eval-kernels", action="store_true", help="skip the evaluation-kernel roofline lines")
+    ap.add_argument("--restart-mu", type=float, default=0.0,
+                    help="NOT the default: landing_options.restart_mu for both arms (DESIGN.md 3); 0 = mu_init")
     ap.add_argument("--no-one-gpu-base", action="store_true",
                     help="N > 1: skip the 1-GPU solve of the same fixed workload on rank 0 (strong-scaling base)")
     args = ap.parse_args()
@@ -292,6 +300,8 @@ def main():
     cfg = pick_config(args, world)
     N = cfg["knots"]
     solver = lc.LandingSolver(N=N, device=local_rank)
+    if cfg.get("restart_mu", 0.0) > 0.0:
+        solver.options.restart_mu = cfg["restart_mu"]
     if cfg.get("formulation") == "schedule":
         schedule_setup(cfg, solver)
     nx = solver.dims["nx"]
