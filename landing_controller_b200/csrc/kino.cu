@@ -73,7 +73,10 @@ __device__ __forceinline__ void kino_g_part(const KinoArgs& a, long long b, int 
                                   (kino::G_LEG0 << PART) | (PART == 0 ? (kino::G_DYN | kino::G_FRIC | kino::G_Z) : 0u) | kino::G_JPOS);
 }
 
-__global__ void __launch_bounds__(128) k_kino_g(KinoArgs a) {
+#ifndef KINO_G_CTAS
+#define KINO_G_CTAS 4  // (128 registers: 0.159 ms instead of 0.165 ms at 16k scenarios, N = 21; 5 / 6 CTAs are slower)
+#endif
+__global__ void __launch_bounds__(128, KINO_G_CTAS) k_kino_g(KinoArgs a) {
   const long long b = (long long)blockIdx.x * 128 + threadIdx.x;
   if (b >= a.B) return;
   const int N = a.N, k = blockIdx.y, part = blockIdx.z;
@@ -148,8 +151,16 @@ __device__ __forceinline__ void kino_jac_dispatch(const KinoArgs& a, long long b
 // Passes G0..G1-1; blockIdx.x = pass + (G1 - G0) * scenario block: the passes of one (scenario block, knot) read the same
 // x and are scheduled together, so all but the first find it in L2.  One kernel per class of passes (launch_kino), so
 // that the light passes are not held to the register count -- hence occupancy -- of the rpy passes.
+// Six CTAs per SM (80 registers; a few hundred bytes of spills in the rpy-leg passes): the passes are bound by the latency
+// of their dependent FP64 chains, not by arithmetic or bandwidth.  Measured at 16k scenarios, N = 21: no cap 1.07 ms, 5 CTAs
+// 0.99, 6 CTAs 0.95, 8 CTAs 1.12.  Both neighbours of this organisation were measured slower: the five passes of a leg
+// in ONE thread on one copy of x and one evaluation of the sincos (1.22 ms) and a finer split of the r / c / f triples
+// into dynamics and leg passes (40 passes: 1.21 ms).
+#ifndef KINO_JAC_CTAS
+#define KINO_JAC_CTAS 6
+#endif
 template <int G0, int G1>
-__global__ void __launch_bounds__(128) k_kino_jac(KinoArgs a) {
+__global__ void __launch_bounds__(128, KINO_JAC_CTAS) k_kino_jac(KinoArgs a) {
   constexpr int NPASS = G1 - G0;
   const int g = G0 + (int)(blockIdx.x % NPASS);
   const long long b = (long long)(blockIdx.x / NPASS) * 128 + threadIdx.x;

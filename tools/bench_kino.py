@@ -17,7 +17,7 @@ def measure_kino(N=21, B=16384, reps=10, solver=None, device=0):
     import torch
     import landing_controller_b200 as lc
     from bench_eval import hbm_peak
-    s = solver or lc.LandingSolver(N=N, device=device)
+    s = solver or lc.LandingSolver(N=N, device=device, lib_path=os.environ.get("LANDING_LIB", lc.api.LIB_PATH))
     d = s.kino_dims()
     pb = s.kino_problem(np.array(DT_VAL) if N == 21 else np.full(N - 1, 0.6 / (N - 1)))
     dev = torch.device("cuda", device)
