@@ -370,6 +370,19 @@ int landing_kino_eval_batch(landing_ctx* c, long long B, int memspace, int layou
     dg = g ? (double*)(s + bx) : nullptr;
     dj = jac ? (double*)(s + bx + bg) : nullptr;
   }
+  // AoS batches (one vector per scenario, what landing_solve_batch / landing_kino_setup_batch hand over) are evaluated
+  // on transposed copies like the SRB functions (landing_eval_batch): three times the traffic, all of it coalesced.
+  double *aos_g = nullptr, *aos_j = nullptr;
+  if (layout == LANDING_AOS && B >= 64) {
+    rc = ensure_tr(c, sizeof(double) * (pl.nx + (dg ? pl.m : 0) + (dj ? pl.nnz : 0)) * B + 256);
+    if (rc) return rc;
+    double* cur = (double*)c->tr;
+    c->launches += launch_transpose(dx, cur, B, pl.nx, c->stream);  // [B][n_x] -> [n_x][B]
+    dx = cur; cur += pl.nx * B;
+    if (dg) { aos_g = dg; dg = cur; cur += pl.m * B; }
+    if (dj) { aos_j = dj; dj = cur; cur += pl.nnz * B; }
+    layout = LANDING_SOA;
+  }
   KinoArgs a{};
   a.N = c->N; a.B = B;
   a.x = make_cview(dx, pl.nx, B, layout);
@@ -380,6 +393,9 @@ int landing_kino_eval_batch(landing_ctx* c, long long B, int memspace, int layou
   a.dtv = c->d_dt;
   a.gpos = c->d_kino; a.bpos = c->d_kino + pl.gpos.size();
   c->launches += launch_kino(a, dg != nullptr, dj != nullptr, c->stream);
+  CU(cudaGetLastError());
+  if (aos_g) { c->launches += launch_transpose(dg, aos_g, pl.m, B, c->stream); dg = aos_g; }    // [m][B] -> [B][m]
+  if (aos_j) { c->launches += launch_transpose(dj, aos_j, pl.nnz, B, c->stream); dj = aos_j; }
   CU(cudaGetLastError());
   if (memspace == LANDING_HOST) {
     if (g) CU(cudaMemcpyAsync(g, dg, sizeof(double) * pl.m * B, cudaMemcpyDeviceToHost, c->stream));
