@@ -2,8 +2,9 @@
 // (generate_solver/generate_landingCtrller_KNITRO.m:34-193): constraint values g and the sparse Jacobian
 // dg/dx in CCS order for a whole batch of trajectories.  One thread = one (scenario, knot); with the SoA layout every
 // load and store of a warp is one coalesced 256-byte transaction.  The Jacobian columns are exact forward-mode
-// derivatives of the same knot function (kino_knot.cuh, DualN): one pass per triple of knot-local inputs, spread over
-// blockIdx.z; a pass types only its own input block as duals and evaluates only the row groups it can reach.
+// derivatives of the same knot function (kino_knot.cuh, DualN): one pass per triple of knot-local inputs, each pass its
+// own thread; a pass types only its own input block as duals and evaluates only the row groups it can reach.  Bounds,
+// initial guess and terminal cost of the same NLP: k_kino_setup, k_kino_cost.
 //
 // x = [X(:) (12 N); jpos(:) (12 (N-1)); U(:) (24 (N-1))], g rows: 48 boundary rows, then 141 per knot (117 for the
 // last) -- the row map is in oracle/kino_ref.py, which is pinned to the solution of this NLP that the reference stores.
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(128, KINO_G_CTAS) k_kino_g(KinoArgs a) {
   }
 }
 
-// Jacobian: blockIdx.z = pass.  A pass seeds one triple of knot-local inputs (three tangents: r | rpy | omega | v | the
+// Jacobian.  A pass seeds one triple of knot-local inputs (three tangents: r | rpy | omega | v | the
 // joint angles, foot position, force, next foot position of one leg | a triple of the next state) and runs the knot
 // function with that block typed DualN<3> and every other block a plain double, restricted to the row groups the triple
 // can reach; the rpy triple, which reaches every leg's rows through R, is split into five passes (dynamics, four legs).
