@@ -242,3 +242,35 @@ def test_gpu_kino_smallest_problem_and_ragged_batch():
     Jo = kr.jac_fd(pbo, x[b], literal=False)
     assert np.max(np.abs(Jd - Jo)) <= 2e-6 * max(1.0, np.abs(Jo).max())
     s.close()
+
+
+@pytest.mark.gpu
+def test_gpu_kino_edge_cases():
+    """Empty batch, single outputs, missing arguments: B = 0 is a no-op, every output is optional and the requested one
+    does not depend on which others are requested, NULL inputs are refused with an error code (no crash)."""
+    import ctypes
+    import landing_controller_b200 as lc
+    N = 21
+    s = lc.LandingSolver(N=N, device=0)
+    d = s.kino_dims()
+    pbo = kr.default_problem(N)
+    pb = s.kino_problem(pbo["dt"])
+    x = np.random.default_rng(2).uniform(-0.5, 0.5, size=(3, d["nx"]))
+    g, jac = s.kino_eval_host(x, pb)
+    g1, none = s.kino_eval_host(x, pb, want_jac=False)
+    none2, j1 = s.kino_eval_host(x, pb, want_g=False)
+    assert none is None and none2 is None and np.array_equal(g1, g) and np.array_equal(j1, jac)
+    g0, j0 = s.kino_eval_host(np.zeros((0, d["nx"])), pb)
+    assert g0.shape == (0, d["m"]) and j0.shape == (0, d["nnzJ"])
+    lib, dp = s.lib, ctypes.POINTER(ctypes.c_double)
+    null = ctypes.cast(None, dp)
+    assert lib.landing_kino_eval_batch(s.ctx, 3, lc.HOST, lc.AOS, ctypes.byref(pb), null, null, null) != 0
+    assert b"kino" in lib.landing_last_error()
+    ks = s.kino_setup_data()
+    assert lib.landing_kino_setup_batch(s.ctx, 3, lc.HOST, lc.AOS, ctypes.byref(ks), null, null, null, null, null) != 0
+    drops = lc.random_sweep(3, seed=4)
+    lb, ub, none3 = s.kino_setup_host(drops, want_x0=False)
+    lb2, ub2, x0 = s.kino_setup_host(drops)
+    assert none3 is None and np.array_equal(lb, lb2) and np.array_equal(ub, ub2) and x0.shape == (3, d["nx"])
+    assert np.all(lb <= ub)
+    s.close()
